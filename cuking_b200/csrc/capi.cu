@@ -1,0 +1,704 @@
+// C ABI of libcuking_b200.so (include/cuking_b200.h): contexts, plane storage, pack / import / export, the pairwise
+// call with its result compaction, sort and copy-out.  Reference seam: /root/reference/cuking.cu:505-523 (planning +
+// allocation), :675-703 (pack), :713-765 (result buffer, launch, overflow check, sort).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "internal.cuh"
+#include "synth.cuh"
+
+namespace ck {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s at %s:%d", int(e), cudaGetErrorString(e), what, file, line);
+  g_last_error = buf;
+  return e == cudaErrorMemoryAllocation ? CK_ERR_OUT_OF_MEMORY : CK_ERR_CUDA;
+}
+
+namespace {
+
+struct DeviceGuard {  // every entry point runs on the ctx's device and restores the caller's
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+struct DevBuf {  // RAII device allocation for per-call temporaries
+  void *p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <typename T>
+  T *as() const { return static_cast<T *>(p); }
+};
+
+__global__ void make_sort_keys_kernel(const ck_result *res, uint32_t n, unsigned long long *keys, uint32_t *idx) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = (static_cast<unsigned long long>(res[i].sample_i) << 32) | res[i].sample_j;
+    idx[i] = i;
+  }
+}
+__global__ void gather_results_kernel(const ck_result *in, const uint32_t *idx, uint32_t n, ck_result *out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[idx[i]];
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+int king_variant_from_env() {
+  const char *v = getenv("CUKING_KING_VARIANT");
+  if (v == nullptr || *v == 0) return -1;
+  return atoi(v);
+}
+
+}  // namespace
+}  // namespace ck
+
+using namespace ck;
+
+// default pairwise kernel variant: 0 = 5 POPC per pair-word, 1 = carry-save (2.5 POPC + 5 more LOP3)
+static int g_default_variant = 1;
+
+extern "C" {
+
+int ck_abi_version(void) { return CK_ABI_VERSION; }
+const char *ck_last_error(void) { return g_last_error.c_str(); }
+
+int ck_device_count(int *count) {
+  if (!count) return fail(CK_ERR_INVALID_ARGUMENT, "count is NULL");
+  CK_CUDA(cudaGetDeviceCount(count));
+  return CK_OK;
+}
+
+/* ---- shard planning ---- */
+
+int ck_submatrix_init(uint32_t num_samples, uint32_t split_factor, uint32_t shard_index, ck_submatrix *out) {
+  if (!out) return fail(CK_ERR_INVALID_ARGUMENT, "out is NULL");
+  if (split_factor == 0) return fail(CK_ERR_INVALID_ARGUMENT, "Invalid split factor");
+  if (!make_submatrix(num_samples, split_factor, shard_index, out))
+    return fail(CK_ERR_INVALID_ARGUMENT, "Invalid shard index");
+  return CK_OK;
+}
+uint32_t ck_num_shards(uint32_t k) { return uint32_t(uint64_t(k) * (uint64_t(k) + 1) / 2); }
+uint32_t ck_submatrix_num_rows(const ck_submatrix *sm) { return sm_rows(*sm); }
+uint32_t ck_submatrix_num_cols(const ck_submatrix *sm) { return sm_cols(*sm); }
+uint32_t ck_submatrix_num_samples(const ck_submatrix *sm) { return sm_samples(*sm); }
+uint32_t ck_submatrix_contains(const ck_submatrix *sm, uint32_t s) { return sm_contains(*sm, s) ? 1u : 0u; }
+uint32_t ck_submatrix_sample_offset(const ck_submatrix *sm, uint32_t s) { return sm_ref_offset(*sm, s); }
+uint32_t ck_words_per_sample(uint32_t num_sites) { return ref_words_per_sample(num_sites); }
+
+/* ---- context ---- */
+
+int ck_ctx_create(int device, ck_ctx **out) {
+  if (!out) return fail(CK_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  CK_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(CK_ERR_INVALID_ARGUMENT, "no such CUDA device");
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  CK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(CK_ERR_CUDA, std::string("libcuking_b200 is built for sm_100a only; device is ") + prop.name);
+  ck_ctx *ctx = new (std::nothrow) ck_ctx();
+  if (!ctx) return fail(CK_ERR_OUT_OF_MEMORY, "host allocation failed");
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev[1])) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->d_counter, 2 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->d_pack_err, 2 * sizeof(uint32_t))) != cudaSuccess) {
+    ck_ctx_destroy(ctx);
+    return fail_cuda(e, "ck_ctx_create", __FILE__, __LINE__);
+  }
+  ctx->stream = ctx->own_stream;
+  ctx->king_variant = king_variant_from_env();
+  *out = ctx;
+  return CK_OK;
+}
+
+int ck_ctx_set_stream(ck_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return fail(CK_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return CK_OK;
+}
+
+int ck_ctx_set_king_variant(ck_ctx *ctx, int variant) {
+  if (!ctx) return fail(CK_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (variant < -1 || variant > 1) return fail(CK_ERR_INVALID_ARGUMENT, "unknown pairwise kernel variant");
+  ctx->king_variant = variant;
+  return CK_OK;
+}
+
+int ck_ctx_synchronize(ck_ctx *ctx) {
+  if (!ctx) return fail(CK_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  DeviceGuard guard(ctx->device);
+  CK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CK_OK;
+}
+
+int ck_ctx_get_timings(ck_ctx *ctx, ck_timings *out) {
+  if (!ctx || !out) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = ctx->timings;
+  return CK_OK;
+}
+
+int ck_ctx_destroy(ck_ctx *ctx) {
+  if (!ctx) return CK_OK;
+  DeviceGuard guard(ctx->device);
+  if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+    if (ctx->staging[i]) cudaFree(ctx->staging[i]);
+    if (ctx->pinned_free[i]) cudaEventDestroy(ctx->pinned_free[i]);
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  }
+  if (ctx->d_counter) cudaFree(ctx->d_counter);
+  if (ctx->d_pack_err) cudaFree(ctx->d_pack_err);
+  if (ctx->syn_row) cudaFree(ctx->syn_row);
+  if (ctx->syn_col) cudaFree(ctx->syn_col);
+  if (ctx->syn_alt) cudaFree(ctx->syn_alt);
+  if (ctx->result_buf) cudaFree(ctx->result_buf);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return CK_OK;
+}
+
+/* ---- planes ---- */
+
+int ck_planes_create(ck_ctx *ctx, const ck_submatrix *sm, uint32_t num_sites, ck_planes **out) {
+  if (!ctx || !sm || !out) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  if (sm->i_end < sm->i_begin || sm->j_end < sm->j_begin) return fail(CK_ERR_INVALID_ARGUMENT, "inverted sample range");
+  if (!sm_diagonal(*sm) && !(sm->i_end <= sm->j_begin || sm->j_end <= sm->i_begin))
+    return fail(CK_ERR_INVALID_ARGUMENT, "row and column ranges must be identical or disjoint");
+  if (num_sites == 0) return fail(CK_ERR_INVALID_ARGUMENT, "num_sites is 0");
+  DeviceGuard guard(ctx->device);
+  ck_planes *pl = new (std::nothrow) ck_planes();
+  if (!pl) return fail(CK_ERR_OUT_OF_MEMORY, "host allocation failed");
+  pl->ctx = ctx;
+  pl->map = make_slot_map(*sm);
+  pl->num_sites = num_sites;
+  pl->words = padded_words(num_sites);
+  if (pl->map.num_blocks > 65535u) {
+    delete pl;
+    return fail(CK_ERR_INVALID_ARGUMENT, "more than 65535 x 64 samples in one shard; raise --split_factor");
+  }
+  cudaError_t e;
+  if ((e = cudaMalloc(&pl->raw, std::max<size_t>(pl->raw_words(), 1) * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&pl->compute, std::max<size_t>(pl->compute_words(), 1) * 4)) != cudaSuccess) {
+    ck_planes_destroy(pl);
+    return fail_cuda(e, "cudaMalloc(planes)", __FILE__, __LINE__);
+  }
+  *out = pl;
+  return ck_planes_reset(pl);
+}
+
+int ck_planes_reset(ck_planes *pl) {
+  if (!pl) return fail(CK_ERR_INVALID_ARGUMENT, "planes is NULL");
+  DeviceGuard guard(pl->ctx->device);
+  if (pl->raw_words()) CK_CUDA(launch_fill_missing(pl->raw, pl->raw_words(), pl->ctx->stream));
+  pl->compute_stale = true;
+  CK_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+  return CK_OK;
+}
+
+int ck_planes_destroy(ck_planes *pl) {
+  if (!pl) return CK_OK;
+  DeviceGuard guard(pl->ctx->device);
+  cudaStreamSynchronize(pl->ctx->stream);
+  if (pl->raw) cudaFree(pl->raw);
+  if (pl->compute) cudaFree(pl->compute);
+  delete pl;
+  return CK_OK;
+}
+
+int ck_planes_num_sites(const ck_planes *pl, uint32_t *num_sites) {
+  if (!pl || !num_sites) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  *num_sites = pl->num_sites;
+  return CK_OK;
+}
+
+int ck_planes_device_bytes(const ck_planes *pl, uint64_t *bytes) {
+  if (!pl || !bytes) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  *bytes = uint64_t(pl->raw_words() + pl->compute_words()) * 4;
+  return CK_OK;
+}
+
+static int ensure_compute(ck_planes *pl) {
+  if (!pl->compute_stale) return CK_OK;
+  ck_ctx *ctx = pl->ctx;
+  CK_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (pl->raw_words()) CK_CUDA(launch_finalize(*pl, ctx->stream));
+  CK_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CK_CUDA(cudaEventSynchronize(ctx->ev[1]));
+  ctx->timings.finalize_ms = elapsed(ctx->ev[0], ctx->ev[1]);
+  pl->compute_stale = false;
+  return CK_OK;
+}
+
+int ck_planes_finalize(ck_planes *pl) {
+  if (!pl) return fail(CK_ERR_INVALID_ARGUMENT, "planes is NULL");
+  DeviceGuard guard(pl->ctx->device);
+  return ensure_compute(pl);
+}
+
+static int ensure_staging(ck_ctx *ctx, size_t bytes) {
+  if (ctx->pinned_bytes >= bytes) return CK_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+    if (ctx->staging[i]) cudaFree(ctx->staging[i]);
+    ctx->pinned[i] = ctx->staging[i] = nullptr;
+  }
+  ctx->pinned_bytes = 0;
+  for (int i = 0; i < 2; ++i) {
+    CK_CUDA(cudaHostAlloc(&ctx->pinned[i], bytes, cudaHostAllocDefault));
+    CK_CUDA(cudaMalloc(&ctx->staging[i], bytes));
+    if (!ctx->pinned_free[i]) CK_CUDA(cudaEventCreateWithFlags(&ctx->pinned_free[i], cudaEventDisableTiming));
+  }
+  ctx->pinned_bytes = bytes;
+  return CK_OK;
+}
+
+int ck_pack_triples(ck_planes *pl, const int64_t *row_idx, const int64_t *col_idx, const int32_t *n_alt_alleles,
+                    size_t n, int on_device) {
+  if (!pl) return fail(CK_ERR_INVALID_ARGUMENT, "planes is NULL");
+  if (n == 0) return CK_OK;
+  if (!row_idx || !col_idx || !n_alt_alleles) return fail(CK_ERR_INVALID_ARGUMENT, "NULL triple array");
+  ck_ctx *ctx = pl->ctx;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = ctx->stream;
+  CK_CUDA(cudaMemsetAsync(ctx->d_pack_err, 0xff, 2 * sizeof(uint32_t), s));
+  pl->compute_stale = true;
+  CK_CUDA(cudaEventRecord(ctx->ev[0], s));
+  if (on_device) {
+    CK_CUDA(launch_pack(*pl, row_idx, col_idx, n_alt_alleles, n, 0, ctx->d_pack_err, s));
+  } else {
+    // Host arrays: memcpy into one of two pinned buffers while the GPU consumes the other (H2D + pack kernel).
+    constexpr size_t kChunk = size_t(4) << 20;  // triples per chunk (80 MiB of staging per buffer)
+    constexpr size_t kBytesPer = 8 + 8 + 4;
+    const size_t chunk = std::min(n, kChunk);
+    const size_t chunk_pad = (chunk + 1) & ~size_t(1);
+    int rc = ensure_staging(ctx, chunk_pad * kBytesPer);
+    if (rc != CK_OK) return rc;
+    size_t done = 0;
+    for (int buf = 0; done < n; buf ^= 1) {
+      const size_t m = std::min(chunk, n - done);
+      CK_CUDA(cudaEventSynchronize(ctx->pinned_free[buf]));  // a never-recorded event is complete
+      char *h = static_cast<char *>(ctx->pinned[buf]);
+      char *d = static_cast<char *>(ctx->staging[buf]);
+      memcpy(h, row_idx + done, m * 8);
+      memcpy(h + chunk_pad * 8, col_idx + done, m * 8);
+      memcpy(h + chunk_pad * 16, n_alt_alleles + done, m * 4);
+      CK_CUDA(cudaMemcpyAsync(d, h, chunk_pad * kBytesPer, cudaMemcpyHostToDevice, s));
+      CK_CUDA(launch_pack(*pl, reinterpret_cast<int64_t *>(d), reinterpret_cast<int64_t *>(d + chunk_pad * 8),
+                          reinterpret_cast<int32_t *>(d + chunk_pad * 16), m, done, ctx->d_pack_err, s));
+      CK_CUDA(cudaEventRecord(ctx->pinned_free[buf], s));
+      done += m;
+    }
+  }
+  CK_CUDA(cudaEventRecord(ctx->ev[1], s));
+  uint32_t err[2];
+  CK_CUDA(cudaMemcpyAsync(err, ctx->d_pack_err, sizeof(err), cudaMemcpyDeviceToHost, s));
+  CK_CUDA(cudaStreamSynchronize(s));
+  ctx->timings.pack_ms = elapsed(ctx->ev[0], ctx->ev[1]);
+  if (err[0] != 0xffffffffu) {
+    const size_t idx = size_t(err[0]) - 1;
+    int32_t value = 0;
+    if (on_device)
+      cudaMemcpy(&value, n_alt_alleles + idx, sizeof(value), cudaMemcpyDeviceToHost);
+    else
+      value = n_alt_alleles[idx];
+    return fail(CK_ERR_INVALID_GENOTYPE, "Invalid value for n_alt_alleles (" + std::to_string(value) +
+                                             ") encountered at triple " + std::to_string(idx));
+  }
+  if (err[1] != 0xffffffffu)
+    return fail(CK_ERR_OUT_OF_RANGE, "row_idx out of range [0, num_sites) at triple " + std::to_string(size_t(err[1]) - 1));
+  return CK_OK;
+}
+
+int ck_planes_import_bitset(ck_planes *pl, const uint64_t *bit_set, int on_device) {
+  if (!pl || !bit_set) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  ck_ctx *ctx = pl->ctx;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = ctx->stream;
+  const size_t bytes = size_t(ref_words_per_sample(pl->num_sites)) * sm_samples(pl->map.sm) * 8;
+  DevBuf tmp;
+  const uint64_t *d_src = bit_set;
+  CK_CUDA(cudaEventRecord(ctx->ev[0], s));
+  if (!on_device) {
+    CK_CUDA(tmp.alloc(bytes));
+    CK_CUDA(cudaMemcpyAsync(tmp.p, bit_set, bytes, cudaMemcpyHostToDevice, s));
+    d_src = tmp.as<uint64_t>();
+  }
+  CK_CUDA(cudaEventRecord(ctx->ev[1], s));
+  if (pl->raw_words()) {
+    CK_CUDA(launch_fill_missing(pl->raw, pl->raw_words(), s));
+    CK_CUDA(launch_import_ref(*pl, d_src, s));
+  }
+  cudaEvent_t ev2;
+  CK_CUDA(cudaEventCreate(&ev2));
+  cudaEventRecord(ev2, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  ctx->timings.h2d_ms = elapsed(ctx->ev[0], ctx->ev[1]);
+  ctx->timings.import_ms = elapsed(ctx->ev[1], ev2);
+  cudaEventDestroy(ev2);
+  CK_CUDA(e);
+  pl->compute_stale = true;
+  return CK_OK;
+}
+
+int ck_planes_export_bitset(ck_planes *pl, uint64_t *bit_set, int on_device) {
+  if (!pl || !bit_set) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  ck_ctx *ctx = pl->ctx;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = ctx->stream;
+  const size_t bytes = size_t(ref_words_per_sample(pl->num_sites)) * sm_samples(pl->map.sm) * 8;
+  DevBuf tmp;
+  uint64_t *d_dst = bit_set;
+  if (!on_device) {
+    CK_CUDA(tmp.alloc(bytes));
+    d_dst = tmp.as<uint64_t>();
+  }
+  // words of the reference layout that have no plane word behind them do not exist (Wp >= W), so every word is written
+  if (pl->raw_words()) CK_CUDA(launch_export_ref(*pl, d_dst, s));
+  if (!on_device) CK_CUDA(cudaMemcpyAsync(bit_set, d_dst, bytes, cudaMemcpyDeviceToHost, s));
+  CK_CUDA(cudaStreamSynchronize(s));
+  return CK_OK;
+}
+
+int ck_planes_synthesize(ck_planes *pl, const ck_synth_params *params) {
+  if (!pl || !params) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  ck_ctx *ctx = pl->ctx;
+  DeviceGuard guard(ctx->device);
+  if (pl->raw_words()) {
+    CK_CUDA(launch_fill_missing(pl->raw, pl->raw_words(), ctx->stream));
+    CK_CUDA(launch_synth_planes(*pl, params->seed, missing_threshold(params->missing_rate), ctx->stream));
+  }
+  pl->compute_stale = true;
+  CK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CK_OK;
+}
+
+/* ---- pairwise ---- */
+
+static int ensure_result_buf(ck_ctx *ctx, size_t records) {
+  if (ctx->result_cap >= records) return CK_OK;
+  if (ctx->result_buf) cudaFree(ctx->result_buf);
+  ctx->result_buf = nullptr;
+  ctx->result_cap = 0;
+  CK_CUDA(cudaMalloc(&ctx->result_buf, std::max<size_t>(records, 1) * sizeof(ck_result)));
+  ctx->result_cap = records;
+  return CK_OK;
+}
+
+// Sorts n device records by (sample_i, sample_j) — the pair is unique, so this equals the reference's
+// (sample_i, sample_j, kin) order (cuking.cu:761-765) — into `out` (device).
+static int sort_results(ck_ctx *ctx, const ck_result *in, uint32_t n, ck_result *out) {
+  cudaStream_t s = ctx->stream;
+  DevBuf keys_a, keys_b, idx_a, idx_b, tmp;
+  CK_CUDA(keys_a.alloc(size_t(n) * 8));
+  CK_CUDA(keys_b.alloc(size_t(n) * 8));
+  CK_CUDA(idx_a.alloc(size_t(n) * 4));
+  CK_CUDA(idx_b.alloc(size_t(n) * 4));
+  const unsigned grid = (n + 255) / 256;
+  make_sort_keys_kernel<<<grid, 256, 0, s>>>(in, n, keys_a.as<unsigned long long>(), idx_a.as<uint32_t>());
+  CK_CUDA(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  CK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a.as<unsigned long long>(),
+                                          keys_b.as<unsigned long long>(), idx_a.as<uint32_t>(), idx_b.as<uint32_t>(),
+                                          int(n), 0, 64, s));
+  CK_CUDA(tmp.alloc(tmp_bytes));
+  CK_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_a.as<unsigned long long>(),
+                                          keys_b.as<unsigned long long>(), idx_a.as<uint32_t>(), idx_b.as<uint32_t>(),
+                                          int(n), 0, 64, s));
+  gather_results_kernel<<<grid, 256, 0, s>>>(in, idx_b.as<uint32_t>(), n, out);
+  CK_CUDA(cudaGetLastError());
+  CK_CUDA(cudaStreamSynchronize(s));
+  return CK_OK;
+}
+
+static KingLaunch base_launch(const ck_planes *pl) {
+  const ck_submatrix &sm = pl->map.sm;
+  KingLaunch k{};
+  k.compute = pl->compute;
+  k.words = pl->words;
+  k.row_block0 = 0;
+  k.num_row_blocks = ceil_div(sm_rows(sm), kTileSamples);
+  k.col_block0 = pl->map.col_slot0 / kTileSamples;
+  k.num_col_blocks = ceil_div(sm_cols(sm), kTileSamples);
+  k.row_global0 = sm.i_begin;
+  k.col_global0 = sm.j_begin;
+  k.num_rows = sm_rows(sm);
+  k.num_cols = sm_cols(sm);
+  k.triangular = sm_diagonal(sm) ? 1u : 0u;
+  return k;
+}
+
+int ck_king_num_tiles(const ck_planes *pl, uint64_t *num_tiles) {
+  if (!pl || !num_tiles) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  const KingLaunch k = base_launch(pl);
+  *num_tiles = king_num_tiles(k.num_row_blocks, k.num_col_blocks, k.triangular != 0);
+  return CK_OK;
+}
+
+int ck_king_tiles(ck_planes *pl, uint64_t tile_begin, uint64_t tile_end, float kin_threshold, uint32_t max_results,
+                  ck_result *results, int results_on_device, uint32_t *num_results, int sort) {
+  if (!pl || !num_results) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (max_results > 0 && !results) return fail(CK_ERR_INVALID_ARGUMENT, "results is NULL");
+  *num_results = 0;
+  ck_ctx *ctx = pl->ctx;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = ctx->stream;
+  KingLaunch k = base_launch(pl);
+  const uint64_t total = king_num_tiles(k.num_row_blocks, k.num_col_blocks, k.triangular != 0);
+  if (tile_begin > tile_end || tile_end > total) return fail(CK_ERR_INVALID_ARGUMENT, "tile range outside the tile grid");
+  int rc = ensure_compute(pl);
+  if (rc != CK_OK) return rc;
+
+  // Pairs are appended to a device buffer: the caller's when it is device memory and no sort is needed, else ours.
+  ck_result *d_emit = nullptr;
+  const bool direct = results_on_device && !sort;
+  if (direct) {
+    d_emit = results;
+  } else {
+    rc = ensure_result_buf(ctx, max_results);
+    if (rc != CK_OK) return rc;
+    d_emit = ctx->result_buf;
+  }
+  k.tile_begin = tile_begin;
+  k.tile_end = tile_end;
+  k.kin_threshold = kin_threshold;
+  k.max_results = max_results;
+  k.results = d_emit;
+  k.counter = ctx->d_counter;
+  k.dump_counts = nullptr;
+  k.dump_kin = nullptr;
+  ctx->timings.king_launches = 0;
+  CK_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), s));
+  CK_CUDA(cudaEventRecord(ctx->ev[0], s));
+  if (tile_end > tile_begin) {
+    const int variant = ctx->king_variant >= 0 ? ctx->king_variant : g_default_variant;
+    CK_CUDA(launch_king(k, variant, s, &ctx->timings.king_launches));
+  }
+  CK_CUDA(cudaEventRecord(ctx->ev[1], s));
+  unsigned long long count = 0;
+  CK_CUDA(cudaMemcpyAsync(&count, ctx->d_counter, sizeof(count), cudaMemcpyDeviceToHost, s));
+  CK_CUDA(cudaStreamSynchronize(s));
+  ctx->timings.king_ms = elapsed(ctx->ev[0], ctx->ev[1]);
+  *num_results = count > 0xffffffffull ? 0xffffffffu : uint32_t(count);
+  if (count > max_results)  // cuking.cu:747-751
+    return fail(CK_ERR_RESULT_OVERFLOW, "Could not store all results: try increasing the --max_results parameter.");
+  const uint32_t n = uint32_t(count);
+  if (n == 0) return CK_OK;
+
+  cudaEvent_t t0, t1, t2;
+  CK_CUDA(cudaEventCreate(&t0));
+  CK_CUDA(cudaEventCreate(&t1));
+  CK_CUDA(cudaEventCreate(&t2));
+  cudaEventRecord(t0, s);
+  const ck_result *d_final = d_emit;
+  DevBuf sorted;
+  if (sort) {
+    ck_result *d_sorted = nullptr;
+    if (results_on_device) {
+      d_sorted = results;
+    } else {
+      cudaError_t e = sorted.alloc(size_t(n) * sizeof(ck_result));
+      if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(sorted results)", __FILE__, __LINE__);
+      d_sorted = sorted.as<ck_result>();
+    }
+    rc = sort_results(ctx, d_emit, n, d_sorted);
+    if (rc != CK_OK) return rc;
+    ctx->timings.king_launches += 3;  // key build, radix sort (one logical launch), gather
+    d_final = d_sorted;
+  }
+  cudaEventRecord(t1, s);
+  if (!results_on_device) CK_CUDA(cudaMemcpyAsync(results, d_final, size_t(n) * sizeof(ck_result), cudaMemcpyDeviceToHost, s));
+  cudaEventRecord(t2, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  ctx->timings.sort_ms = elapsed(t0, t1);
+  ctx->timings.d2h_ms = elapsed(t1, t2);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaEventDestroy(t2);
+  CK_CUDA(e);
+  return CK_OK;
+}
+
+int ck_king(ck_planes *pl, float kin_threshold, uint32_t max_results, ck_result *results, int results_on_device,
+            uint32_t *num_results, int sort) {
+  if (!pl) return fail(CK_ERR_INVALID_ARGUMENT, "planes is NULL");
+  uint64_t tiles = 0;
+  int rc = ck_king_num_tiles(pl, &tiles);
+  if (rc != CK_OK) return rc;
+  return ck_king_tiles(pl, 0, tiles, kin_threshold, max_results, results, results_on_device, num_results, sort);
+}
+
+int ck_king_counts(ck_planes *pl, const uint32_t *sample_i, const uint32_t *sample_j, size_t num_pairs,
+                   ck_counts *counts, float *kin) {
+  if (!pl || !sample_i || !sample_j || !counts || !kin) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  ck_ctx *ctx = pl->ctx;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = ctx->stream;
+  const ck_submatrix &sm = pl->map.sm;
+  const size_t rows = sm_rows(sm), cols = sm_cols(sm);
+  if (rows * cols > (size_t(1) << 28)) return fail(CK_ERR_INVALID_ARGUMENT, "ck_king_counts is a parity hook for shards of at most 2^28 pairs");
+  for (size_t q = 0; q < num_pairs; ++q) {
+    const bool ok = sample_i[q] >= sm.i_begin && sample_i[q] < sm.i_end && sample_j[q] >= sm.j_begin &&
+                    sample_j[q] < sm.j_end && sample_i[q] < sample_j[q];
+    if (!ok) return fail(CK_ERR_INVALID_ARGUMENT, "pair " + std::to_string(q) + " is not an i < j pair of this shard");
+  }
+  int rc = ensure_compute(pl);
+  if (rc != CK_OK) return rc;
+  DevBuf d_counts, d_kin;
+  CK_CUDA(d_counts.alloc(rows * cols * sizeof(ck_counts)));
+  CK_CUDA(d_kin.alloc(rows * cols * sizeof(float)));
+  CK_CUDA(cudaMemsetAsync(d_counts.p, 0, rows * cols * sizeof(ck_counts), s));
+  CK_CUDA(cudaMemsetAsync(d_kin.p, 0, rows * cols * sizeof(float), s));
+  KingLaunch k = base_launch(pl);
+  k.tile_begin = 0;
+  k.tile_end = king_num_tiles(k.num_row_blocks, k.num_col_blocks, k.triangular != 0);
+  k.kin_threshold = 2.f;  // nothing is emitted: kin <= 0.5
+  k.max_results = 0;
+  k.results = nullptr;
+  k.counter = ctx->d_counter;
+  k.dump_counts = d_counts.as<ck_counts>();
+  k.dump_kin = d_kin.as<float>();
+  CK_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), s));
+  const int variant = ctx->king_variant >= 0 ? ctx->king_variant : g_default_variant;
+  CK_CUDA(launch_king(k, variant, s, nullptr));
+  std::vector<ck_counts> h_counts(rows * cols);
+  std::vector<float> h_kin(rows * cols);
+  CK_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, rows * cols * sizeof(ck_counts), cudaMemcpyDeviceToHost, s));
+  CK_CUDA(cudaMemcpyAsync(h_kin.data(), d_kin.p, rows * cols * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK_CUDA(cudaStreamSynchronize(s));
+  for (size_t q = 0; q < num_pairs; ++q) {
+    const size_t idx = size_t(sample_i[q] - sm.i_begin) * cols + (sample_j[q] - sm.j_begin);
+    counts[q] = h_counts[idx];
+    kin[q] = h_kin[idx];
+  }
+  return CK_OK;
+}
+
+int ck_king_host_bitset(ck_ctx *ctx, uint32_t num_samples, uint32_t split_factor, uint32_t shard_index,
+                        uint32_t num_sites, const uint64_t *bit_set, float kin_threshold, uint32_t max_results,
+                        ck_result *results, uint32_t *num_results) {
+  if (!ctx || !bit_set || !num_results) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  ck_submatrix sm;
+  int rc = ck_submatrix_init(num_samples, split_factor, shard_index, &sm);
+  if (rc != CK_OK) return rc;
+  ck_planes *pl = nullptr;
+  rc = ck_planes_create(ctx, &sm, num_sites, &pl);
+  if (rc != CK_OK) return rc;
+  rc = ck_planes_import_bitset(pl, bit_set, 0);
+  if (rc == CK_OK) rc = ck_king(pl, kin_threshold, max_results, results, 0, num_results, 1);
+  ck_planes_destroy(pl);
+  return rc;
+}
+
+/* ---- synthetic inputs ---- */
+
+int ck_synth_genotypes_host(const ck_synth_params *params, uint32_t sample_begin, uint32_t sample_end,
+                            uint32_t site_begin, uint32_t site_end, int8_t *out) {
+  if (!params || !out) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (sample_end < sample_begin || site_end < site_begin) return fail(CK_ERR_INVALID_ARGUMENT, "inverted range");
+  const uint32_t thr = missing_threshold(params->missing_rate);
+  const size_t num_sites = site_end - site_begin;
+  if (sample_begin == sample_end) return CK_OK;
+  for (uint32_t group = sample_begin / 8; group <= (sample_end - 1) / 8; ++group) {
+    const PedigreeKeys keys = pedigree_keys(params->seed, group);
+    for (uint32_t site = site_begin; site < site_end; ++site) {
+      int8_t g[8];
+      pedigree_genotypes(keys, site, thr, g);
+      for (uint32_t m = 0; m < 8; ++m) {
+        const uint32_t s = group * 8 + m;
+        if (s >= sample_begin && s < sample_end) out[size_t(s - sample_begin) * num_sites + (site - site_begin)] = g[m];
+      }
+    }
+  }
+  return CK_OK;
+}
+
+int ck_synth_triples_device(ck_ctx *ctx, const ck_synth_params *params, uint32_t sample_begin, uint32_t sample_end,
+                            uint32_t site_begin, uint32_t site_end, const int64_t **row_idx, const int64_t **col_idx,
+                            const int32_t **n_alt_alleles, size_t *num_triples) {
+  if (!ctx || !params || !row_idx || !col_idx || !n_alt_alleles || !num_triples)
+    return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (sample_end < sample_begin || site_end <= site_begin) return fail(CK_ERR_INVALID_ARGUMENT, "empty or inverted range");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = ctx->stream;
+  const uint32_t sites = site_end - site_begin;
+  const uint32_t thr = missing_threshold(params->missing_rate);
+  DevBuf counts, offsets, tmp;
+  CK_CUDA(counts.alloc(size_t(sites) * 8));
+  CK_CUDA(offsets.alloc(size_t(sites) * 8));
+  CK_CUDA(launch_synth_count(params->seed, thr, sample_begin, sample_end, site_begin, site_end,
+                             counts.as<unsigned long long>(), s));
+  size_t tmp_bytes = 0;
+  CK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.as<unsigned long long>(),
+                                        offsets.as<unsigned long long>(), int(sites), s));
+  CK_CUDA(tmp.alloc(tmp_bytes));
+  CK_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.as<unsigned long long>(),
+                                        offsets.as<unsigned long long>(), int(sites), s));
+  unsigned long long last_off = 0, last_cnt = 0;
+  CK_CUDA(cudaMemcpyAsync(&last_off, offsets.as<unsigned long long>() + (sites - 1), 8, cudaMemcpyDeviceToHost, s));
+  CK_CUDA(cudaMemcpyAsync(&last_cnt, counts.as<unsigned long long>() + (sites - 1), 8, cudaMemcpyDeviceToHost, s));
+  CK_CUDA(cudaStreamSynchronize(s));
+  const size_t total = size_t(last_off + last_cnt);
+  if (total > ctx->syn_cap) {
+    if (ctx->syn_row) cudaFree(ctx->syn_row);
+    if (ctx->syn_col) cudaFree(ctx->syn_col);
+    if (ctx->syn_alt) cudaFree(ctx->syn_alt);
+    ctx->syn_row = ctx->syn_col = nullptr;
+    ctx->syn_alt = nullptr;
+    ctx->syn_cap = 0;
+    const size_t cap = (total + 1) & ~size_t(1);
+    CK_CUDA(cudaMalloc(&ctx->syn_row, cap * 8));
+    CK_CUDA(cudaMalloc(&ctx->syn_col, cap * 8));
+    CK_CUDA(cudaMalloc(&ctx->syn_alt, cap * 4));
+    ctx->syn_cap = cap;
+  }
+  if (total)
+    CK_CUDA(launch_synth_emit(params->seed, thr, sample_begin, sample_end, site_begin, site_end,
+                              offsets.as<unsigned long long>(), ctx->syn_row, ctx->syn_col, ctx->syn_alt, s));
+  CK_CUDA(cudaStreamSynchronize(s));
+  *row_idx = ctx->syn_row;
+  *col_idx = ctx->syn_col;
+  *n_alt_alleles = ctx->syn_alt;
+  *num_triples = total;
+  return CK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// Internal declarations shared by the translation units of libcuking_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "../../include/cuking_b200.h"
+#include "layout.cuh"
+#include "shard_plan.h"
+
+namespace ck {
+
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line);
+
+#define CK_CUDA(expr)                                                      \
+  do {                                                                     \
+    cudaError_t ck_e_ = (expr);                                            \
+    if (ck_e_ != cudaSuccess) return ::ck::fail_cuda(ck_e_, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+
+}  // namespace ck
+
+struct ck_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;       // own_stream or a caller-supplied one
+  cudaStream_t copy_stream = nullptr;  // host staging copies overlap the pack kernel
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  ck_timings timings{};
+  int num_sms = 0;
+  // scratch owned by the ctx
+  unsigned long long *d_counter = nullptr;  // [0] emitted-pair counter
+  uint32_t *d_pack_err = nullptr;           // [0] invalid-genotype index+1 (min), [1] out-of-range index+1 (min)
+  void *pinned[2] = {nullptr, nullptr};   // host staging for ck_pack_triples(on_device = 0)
+  void *staging[2] = {nullptr, nullptr};  // device side of the same double buffer
+  size_t pinned_bytes = 0;
+  cudaEvent_t pinned_free[2] = {nullptr, nullptr};
+  // synthetic triples scratch
+  int64_t *syn_row = nullptr, *syn_col = nullptr;
+  int32_t *syn_alt = nullptr;
+  size_t syn_cap = 0;
+  // emitted-pair buffer reused across ck_king* calls
+  ck_result *result_buf = nullptr;
+  size_t result_cap = 0;
+  int king_variant = -1;  // -1 = library default
+};
+
+struct ck_planes {
+  ck_ctx *ctx = nullptr;
+  ck::SlotMap map{};
+  uint32_t num_sites = 0;
+  uint32_t words = 0;          // padded 32-bit words per plane (multiple of kChunkWords)
+  uint32_t *raw = nullptr;     // [num_blocks][words][2][64]
+  uint32_t *compute = nullptr; // [num_blocks][words][3][64]
+  bool compute_stale = true;   // raw changed since the last finalize
+  size_t raw_words() const { return size_t(map.num_blocks) * words * ck::kRawPlanes * ck::kTileSamples; }
+  size_t compute_words() const { return size_t(map.num_blocks) * words * ck::kComputePlanes * ck::kTileSamples; }
+};
+
+namespace ck {
+
+// ---- pack_kernels.cu ----
+cudaError_t launch_fill_missing(uint32_t *raw, size_t num_words, cudaStream_t s);
+cudaError_t launch_pack(const ck_planes &pl, const int64_t *row, const int64_t *col, const int32_t *alt, size_t n,
+                        size_t index_base, uint32_t *d_err, cudaStream_t s);
+cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s);
+cudaError_t launch_import_ref(const ck_planes &pl, const uint64_t *d_bit_set, cudaStream_t s);
+cudaError_t launch_export_ref(const ck_planes &pl, uint64_t *d_bit_set, cudaStream_t s);
+cudaError_t launch_synth_planes(const ck_planes &pl, uint64_t seed, uint32_t miss_thr, cudaStream_t s);
+cudaError_t launch_synth_count(uint64_t seed, uint32_t miss_thr, uint32_t sample_begin, uint32_t sample_end,
+                               uint32_t site_begin, uint32_t site_end, unsigned long long *d_site_counts,
+                               cudaStream_t s);
+cudaError_t launch_synth_emit(uint64_t seed, uint32_t miss_thr, uint32_t sample_begin, uint32_t sample_end,
+                              uint32_t site_begin, uint32_t site_end, const unsigned long long *d_site_offsets,
+                              int64_t *row, int64_t *col, int32_t *alt, cudaStream_t s);
+
+// ---- king_kernel.cu ----
+struct KingLaunch {
+  const uint32_t *compute;  // compute planes
+  uint32_t words;           // padded words per plane
+  uint32_t row_block0, num_row_blocks;
+  uint32_t col_block0, num_col_blocks;
+  uint32_t row_global0, col_global0;  // global sample index of slot row_block0*64 / col_block0*64
+  uint32_t num_rows, num_cols;
+  uint32_t triangular;                // rows and columns are the same sample range
+  uint64_t tile_begin, tile_end;
+  float kin_threshold;
+  uint64_t max_results;
+  ck_result *results;                 // device
+  unsigned long long *counter;        // device, emitted pairs
+  ck_counts *dump_counts;             // optional dense [num_rows][num_cols] dump (parity hook), else nullptr
+  float *dump_kin;
+};
+uint64_t king_num_tiles(uint32_t num_row_blocks, uint32_t num_col_blocks, bool triangular);
+cudaError_t launch_king(const KingLaunch &k, int variant, cudaStream_t s, uint32_t *launches);
+
+}  // namespace ck

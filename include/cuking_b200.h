@@ -1,0 +1,201 @@
+/*
+ * cuking_b200.h — C ABI of the B200-native pairwise-KING hot path (libcuking_b200.so).
+ *
+ * The reference (populationgenomics/cuKING) is one executable with no plugin/FFI layer; the seam this ABI
+ * replaces is the host -> device boundary inside its Run() (reference paths relative to /root/reference):
+ *
+ *   shard planning        struct Submatrix                       cuking.cu:129-179
+ *   bit-set allocation    NewCudaArray<uint64_t> + memset 0xFF   cuking.cu:513-523
+ *   transpose / pack      AtomicClearBit loop                    cuking.cu:317-323, :675-703
+ *   the kernel launch     ComputeKingKernel<<<grid,128>>>(...)   cuking.cu:191-195, :734-744
+ *   result record         struct KingResult                      cuking.cu:182-186
+ *   overflow check        result_index_and_flag[1]               cuking.cu:747-751
+ *   result sort           std::sort by (i, j, kin)               cuking.cu:761-765
+ *
+ * Conventions: every call returns an int status (CK_OK == 0) and never throws or exits; the message for the
+ * last failure on the calling thread is available from ck_last_error().  The caller owns host buffers; the
+ * library owns device buffers behind opaque handles.  One ck_ctx per GPU; calls on one ctx are not thread-safe,
+ * different ctxs are independent.  Calls are stream-ordered on the ctx's stream and synchronous at return unless
+ * documented otherwise.  There is no CPU fallback: without a CUDA device every device call fails with CK_ERR_CUDA.
+ */
+#ifndef CUKING_B200_H_
+#define CUKING_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CK_ABI_VERSION 1
+
+enum ck_status {
+  CK_OK = 0,
+  CK_ERR_INVALID_ARGUMENT = 1, /* absl::InvalidArgumentError at cuking.cu:437-462 */
+  CK_ERR_CUDA = 2,             /* any CUDA runtime failure (the reference ignores them, cuking.cu:744) */
+  CK_ERR_RESULT_OVERFLOW = 3,  /* absl::ResourceExhaustedError at cuking.cu:747-751 */
+  CK_ERR_INVALID_GENOTYPE = 4, /* absl::FailedPreconditionError at cuking.cu:698-701 */
+  CK_ERR_OUT_OF_RANGE = 5,     /* row_idx >= num_sites: undefined behaviour in the reference, an error here */
+  CK_ERR_OUT_OF_MEMORY = 6     /* the reference exit(1)s at cuking.cu:114-118 */
+};
+
+/* Bounds of the relatedness sub-matrix one shard computes.  Mirrors struct Submatrix, cuking.cu:129-179. */
+typedef struct ck_submatrix {
+  uint32_t i_begin, i_end; /* sample row range    */
+  uint32_t j_begin, j_end; /* sample column range */
+} ck_submatrix;
+
+/* One retained pair.  Bit-compatible with struct KingResult, cuking.cu:182-186 (24 bytes). */
+typedef struct ck_result {
+  uint32_t sample_i, sample_j; /* global sample indices, sample_i < sample_j */
+  float kin;                   /* KING between-family kinship, fp32, expression order of cuking.cu:289-294 */
+  uint32_t ibs0, ibs1, ibs2;   /* cuking.cu:305-307 */
+} ck_result;
+
+/* Raw per-pair counters of cuking.cu:214-240, for parity tests (ck_king_counts). */
+typedef struct ck_counts {
+  uint32_t het_i, het_j, both_het, opposing_hom, concordant_hom, shared_sites;
+} ck_counts;
+
+typedef struct ck_ctx ck_ctx;       /* one GPU + one stream */
+typedef struct ck_planes ck_planes; /* device-resident genotype bit planes for a set of sample slots */
+
+/* Parameters of the synthetic genotype generator: HWE founders, planted pedigrees in blocks of
+ * 8 consecutive samples, per-genotype missingness.  Pure function of (seed, sample, site). */
+typedef struct ck_synth_params {
+  uint64_t seed;
+  double missing_rate; /* m: P(genotype missing) */
+} ck_synth_params;
+
+/* Timing of the most recent calls on a ctx, measured with CUDA events on the ctx's stream. */
+typedef struct ck_timings {
+  float pack_ms;     /* last ck_pack_triples: pack kernel only */
+  float finalize_ms; /* last plane finalisation (raw -> compute planes) */
+  float import_ms;   /* last ck_planes_import_bitset transpose kernel(s) */
+  float king_ms;     /* last pairwise kernel */
+  float sort_ms;     /* last device result sort */
+  float h2d_ms, d2h_ms;
+  uint32_t king_launches; /* kernels launched by the last ck_king* call (pairwise + sort helpers) */
+} ck_timings;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+
+int ck_abi_version(void);
+const char *ck_last_error(void);
+int ck_device_count(int *count);
+
+/* ---- shard planning: cuking.cu:129-179, validation :454-462 ---------------------------------------------- */
+
+/* Fails with CK_ERR_INVALID_ARGUMENT for split_factor == 0 ("Invalid split factor", cuking.cu:454-457) and for
+ * shard_index >= k(k+1)/2 ("Invalid shard index", :459-462).  Unlike the reference, a block that starts past
+ * num_samples yields an empty range instead of an underflowed one (SURVEY.md §8a4 latent bug). */
+int ck_submatrix_init(uint32_t num_samples, uint32_t split_factor, uint32_t shard_index, ck_submatrix *out);
+uint32_t ck_num_shards(uint32_t split_factor);                         /* k(k+1)/2, cloud_batch_submit.py:73 */
+uint32_t ck_submatrix_num_rows(const ck_submatrix *sm);                /* cuking.cu:154 */
+uint32_t ck_submatrix_num_cols(const ck_submatrix *sm);                /* cuking.cu:156 */
+uint32_t ck_submatrix_num_samples(const ck_submatrix *sm);             /* cuking.cu:159-162 */
+uint32_t ck_submatrix_contains(const ck_submatrix *sm, uint32_t s);    /* cuking.cu:165-168 */
+uint32_t ck_submatrix_sample_offset(const ck_submatrix *sm, uint32_t s); /* cuking.cu:171-175 */
+/* u64 words per sample in the REFERENCE layout: 2 * ceil(pad32(num_sites) / 64), cuking.cu:498-500, :513. */
+uint32_t ck_words_per_sample(uint32_t num_sites);
+
+/* ---- context --------------------------------------------------------------------------------------------- */
+
+int ck_ctx_create(int device, ck_ctx **out);
+/* Run all later work of this ctx on an existing cudaStream_t (e.g. torch's current stream).  NULL restores the
+ * ctx-owned stream. */
+int ck_ctx_set_stream(ck_ctx *ctx, void *cuda_stream);
+/* Pairwise kernel variant: 0 = 5 POPC per pair and 32 sites, 1 = carry-save (2.5 POPC + 5 more LOP3), -1 = library
+ * default (also settable with the CUKING_KING_VARIANT environment variable).  Results are identical. */
+int ck_ctx_set_king_variant(ck_ctx *ctx, int variant);
+int ck_ctx_synchronize(ck_ctx *ctx);
+int ck_ctx_get_timings(ck_ctx *ctx, ck_timings *out);
+/* Measures, on this GPU and now, the sustained issue rate of POPC.32 and LOP3 (lane-ops per second, whole chip).
+ * The pairwise kernel is bound by these pipes, not by HBM or the tensor cores; bench.py quotes its roofline against
+ * the POPC figure.  Takes a few milliseconds. */
+int ck_measure_int_peaks(ck_ctx *ctx, double *popc_lane_ops_per_s, double *lop3_lane_ops_per_s);
+int ck_ctx_destroy(ck_ctx *ctx);
+
+/* ---- planes: replaces the managed bit_set of cuking.cu:513-523 --------------------------------------------- */
+
+/* Allocates planes for the samples of one shard; every genotype starts missing (cuking.cu:520-523).  Sample
+ * s of the sub-matrix lives in slot ck_submatrix_sample_offset(sm, s), exactly as in the reference. */
+int ck_planes_create(ck_ctx *ctx, const ck_submatrix *sm, uint32_t num_sites, ck_planes **out);
+int ck_planes_reset(ck_planes *planes); /* back to all-missing */
+int ck_planes_destroy(ck_planes *planes);
+/* Derives the compute planes (true-het / defined / true-hom-alt) from the packed raw planes.  Implicit in the first
+ * ck_king* call after a pack / import / synthesize; exposed so that it can be timed or moved off the critical path. */
+int ck_planes_finalize(ck_planes *planes);
+int ck_planes_num_sites(const ck_planes *planes, uint32_t *num_sites);
+int ck_planes_device_bytes(const ck_planes *planes, uint64_t *bytes);
+
+/* Transpose / pack, cuking.cu:675-703.  For each triple whose col_idx is in the sub-matrix (cuking.cu:677):
+ * n_alt_alleles 0 clears both bits, 1 clears the hom-alt bit, 2 clears the het bit (AND-accumulation, so
+ * duplicate or conflicting triples combine exactly as in the reference and order never matters).  row_idx and
+ * col_idx are truncated to 32 bits like cuking.cu:676,:680.  Any other n_alt_alleles value fails the call with
+ * CK_ERR_INVALID_GENOTYPE (cuking.cu:698-701); row_idx >= num_sites fails with CK_ERR_OUT_OF_RANGE.
+ * The three arrays are host pointers (on_device == 0; staged through pinned memory) or device pointers. */
+int ck_pack_triples(ck_planes *planes, const int64_t *row_idx, const int64_t *col_idx, const int32_t *n_alt_alleles,
+                    size_t num_triples, int on_device);
+
+/* Exchange with the reference bit-set layout (cuking.cu:204-212, :507-523): sample-major uint64 words, slot o at
+ * [o*W, (o+1)*W), het plane first, hom-alt plane second, W = ck_words_per_sample(num_sites); site r is bit r&63 of
+ * word r>>6; (het, hom-alt) = (1,1) means missing, including the padding sites.  The buffer covers all
+ * ck_submatrix_num_samples slots.  Import REPLACES the planes' contents. */
+int ck_planes_import_bitset(ck_planes *planes, const uint64_t *bit_set, int on_device);
+int ck_planes_export_bitset(ck_planes *planes, uint64_t *bit_set, int on_device);
+
+/* Fills the planes with the synthetic cohort of SURVEY.md §8d (global sample index = sub-matrix sample). */
+int ck_planes_synthesize(ck_planes *planes, const ck_synth_params *params);
+
+/* ---- the pairwise kernel: replaces the launch at cuking.cu:734-744 ---------------------------------------- */
+
+/* For every pair (i, j), i in the sub-matrix rows, j in its columns, i < j: the six counters of cuking.cu:232-239,
+ * kin (cuking.cu:289-294), and a record for each pair with kin > kin_threshold (strict, cuking.cu:297).
+ * results: caller buffer of max_results records, host (results_on_device == 0) or device memory.
+ * *num_results receives the number of pairs above the threshold.  If it exceeds max_results the call returns
+ * CK_ERR_RESULT_OVERFLOW (cuking.cu:747-751) and the buffer contents are unspecified.
+ * sort != 0 orders the records by (sample_i, sample_j, kin) like cuking.cu:761-765; otherwise order is unspecified. */
+int ck_king(ck_planes *planes, float kin_threshold, uint32_t max_results, ck_result *results, int results_on_device,
+            uint32_t *num_results, int sort);
+
+/* Same, restricted to the linear range [tile_begin, tile_end) of the sub-matrix's 64x64-sample tile grid (row-major
+ * over the tiles that contain at least one i < j pair).  This is how one shard is split across the GPUs of a box:
+ * each GPU holds the planes and takes a contiguous slice of ck_king_num_tiles().  Results of all slices together
+ * equal ck_king's. */
+int ck_king_num_tiles(const ck_planes *planes, uint64_t *num_tiles);
+int ck_king_tiles(ck_planes *planes, uint64_t tile_begin, uint64_t tile_end, float kin_threshold,
+                  uint32_t max_results, ck_result *results, int results_on_device, uint32_t *num_results, int sort);
+
+/* Parity hook: raw counters and kin for an explicit list of (sample_i, sample_j) pairs (global indices, both in
+ * the sub-matrix), bypassing threshold and compaction.  counts/kin are host arrays of num_pairs entries. */
+int ck_king_counts(ck_planes *planes, const uint32_t *sample_i, const uint32_t *sample_j, size_t num_pairs,
+                   ck_counts *counts, float *kin);
+
+/* The reference seam in one call, host buffers in and out (what a maintainer would call from Run() in place of
+ * cuking.cu:713-765): bit_set in the reference layout for Submatrix(num_samples, split_factor, shard_index),
+ * copied host->device, evaluated, sorted, and copied back. */
+int ck_king_host_bitset(ck_ctx *ctx, uint32_t num_samples, uint32_t split_factor, uint32_t shard_index,
+                        uint32_t num_sites, const uint64_t *bit_set, float kin_threshold, uint32_t max_results,
+                        ck_result *results, uint32_t *num_results);
+
+/* ---- synthetic inputs (bench / tests) --------------------------------------------------------------------- */
+
+/* Dense genotypes of the synthetic cohort on the HOST: out[(s - sample_begin) * num_sites_out + (r - site_begin)]
+ * in {0,1,2} or -1 for missing.  Same function the device generator evaluates. */
+int ck_synth_genotypes_host(const ck_synth_params *params, uint32_t sample_begin, uint32_t sample_end,
+                            uint32_t site_begin, uint32_t site_end, int8_t *out);
+
+/* Sparse triples of the synthetic cohort, generated ON THE DEVICE in Hail's order (site-major, sample-minor,
+ * missing entries absent; mt_to_cuking_inputs.py:28-30) for samples [sample_begin, sample_end) x sites
+ * [site_begin, site_end).  The three device arrays are library-owned and valid until the next call or
+ * ck_ctx_destroy. */
+int ck_synth_triples_device(ck_ctx *ctx, const ck_synth_params *params, uint32_t sample_begin, uint32_t sample_end,
+                            uint32_t site_begin, uint32_t site_end, const int64_t **row_idx, const int64_t **col_idx,
+                            const int32_t **n_alt_alleles, size_t *num_triples);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUKING_B200_H_ */

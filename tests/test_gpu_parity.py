@@ -1,0 +1,288 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and, where present, the reference's own
+ComputeKingKernel (oracle/_ref).  Integer fields bit-exact; kin bit-exact (same fp32 operation order)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cuking_b200 as ck
+from cuking_b200 import capi
+from oracle import king_oracle as ko
+from oracle import ref_kernel
+from tests.helpers import random_genotypes, triples_of, oracle_bitset, ko_sm, assert_results_equal, bits_equal_f32
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ck.Context(0)
+    yield c
+    c.close()
+
+
+def device_planes(ctx, g, sm, order="site"):
+    pl = ctx.planes(sm, g.shape[1])
+    site, sample, alt = triples_of(g, order)
+    pl.pack(site, sample, alt)
+    return pl
+
+
+# ---- pack / layout --------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("n,s,k,shard", [(9, 130, 1, 0), (70, 1000, 1, 0), (130, 517, 3, 1), (130, 517, 3, 3),
+                                          (257, 64, 2, 1), (5, 1, 1, 0), (64, 32, 1, 0), (65, 33, 1, 0)])
+def test_pack_matches_oracle_bitset(ctx, n, s, k, shard):
+    rng = np.random.default_rng(n * 1000 + s)
+    g = random_genotypes(rng, n, s, missing=0.05)
+    sm = ck.submatrix(n, k, shard)
+    want = oracle_bitset(g, ko_sm(sm))
+    for order in ("site", "sample"):
+        with device_planes(ctx, g, sm, order) as pl:
+            assert np.array_equal(pl.export_bitset(), want)
+
+
+def test_pack_duplicates_conflicts_and_filter(ctx):
+    # AND semantics (cuking.cu:687-697) incl. the out-of-shard filter (:677) applied before validation (:698)
+    rng = np.random.default_rng(7)
+    n, s = 50, 300
+    sm = ck.submatrix(n, 2, 1)  # rows [0,25) cols [25,50)
+    m = 20_000
+    row = rng.integers(0, s, m).astype(np.int64)
+    col = rng.integers(0, n + 10, m).astype(np.int64)  # some samples beyond the cohort: skipped
+    alt = rng.integers(0, 3, m).astype(np.int32)
+    alt[col >= n] = 9                                   # invalid but filtered out
+    want = ko.new_bitset(ko_sm(sm), s)
+    assert ko.pack(want, s, ko_sm(sm), row, col, alt) == -1
+    with ctx.planes(sm, s) as pl:
+        pl.pack(row[: m // 2], col[: m // 2], alt[: m // 2])  # incremental packing accumulates
+        pl.pack(row[m // 2:], col[m // 2:], alt[m // 2:])
+        assert np.array_equal(pl.export_bitset(), want)
+        pl.reset()
+        assert np.all(pl.export_bitset() == np.uint64(0xFFFFFFFFFFFFFFFF))
+
+
+def test_pack_device_pointers_and_unaligned(ctx):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(8)
+    g = random_genotypes(rng, 40, 200)
+    sm = ck.submatrix(40)
+    site, sample, alt = triples_of(g)
+    want = oracle_bitset(g, ko_sm(sm))
+    dev = torch.device("cuda:0")
+    for off in (0, 1):  # off=1: views that start 8 / 4 bytes into an allocation -> not 16-byte aligned -> scalar path
+        r = torch.from_numpy(np.concatenate([np.zeros(off, np.int64), site])).to(dev)[off:]
+        c = torch.from_numpy(np.concatenate([np.zeros(off, np.int64), sample])).to(dev)[off:]
+        a = torch.from_numpy(np.concatenate([np.zeros(off, np.int32), alt])).to(dev)[off:]
+        assert (r.data_ptr() % 16 == 0) == (off == 0)
+        with ctx.planes(sm, 200) as pl:
+            pl.pack(r, c, a)
+            assert np.array_equal(pl.export_bitset(), want)
+
+
+def test_pack_rejects_bad_genotype_and_site(ctx):
+    sm = ck.submatrix(4)
+    with ctx.planes(sm, 100) as pl:
+        with pytest.raises(ck.CukingError, match=r"Invalid value for n_alt_alleles \(3\)") as e:
+            pl.pack(np.array([1, 2, 3]), np.array([0, 1, 2]), np.array([0, 3, 1]))
+        assert e.value.code == capi.CK_ERR_INVALID_GENOTYPE  # cuking.cu:698-701
+        with pytest.raises(ck.CukingError) as e:
+            pl.pack(np.array([100]), np.array([0]), np.array([0]))
+        assert e.value.code == capi.CK_ERR_OUT_OF_RANGE
+
+
+@pytest.mark.parametrize("n,s,k,shard", [(100, 777, 1, 0), (100, 777, 3, 2), (64, 2048, 1, 0)])
+def test_import_export_round_trip(ctx, n, s, k, shard):
+    rng = np.random.default_rng(n + s)
+    g = random_genotypes(rng, n, s, missing=0.1)
+    sm = ck.submatrix(n, k, shard)
+    bs = oracle_bitset(g, ko_sm(sm))
+    with ctx.planes(sm, s) as pl:
+        pl.import_bitset(bs)
+        assert np.array_equal(pl.export_bitset(), bs)
+
+
+# ---- pairwise kernel ---------------------------------------------------------------------------------------------
+
+
+def load_kats():
+    with open(os.path.join(GOLDEN, "kat_vectors.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("kat", load_kats(), ids=lambda k: k["id"])
+def test_known_answer_vectors_on_gpu(ctx, kat, variant):
+    ctx.set_king_variant(variant)
+    g = np.array([kat["genotypes_i"], kat["genotypes_j"]], dtype=np.int8)
+    sm = ck.submatrix(2)
+    with device_planes(ctx, g, sm) as pl:
+        counts, kin = pl.counts([0], [1])
+        for f in ("het_i", "het_j", "both_het", "opposing_hom", "concordant_hom", "shared_sites"):
+            assert counts[0][f] == kat[f], f
+        if kat["kin_f32_hex"] == "nan":
+            assert np.isnan(kin[0])
+        else:
+            assert kin.view(np.uint32)[0] == int(kat["kin_f32_hex"], 16)
+        res = pl.king(-1.0, 4)
+        assert len(res) == (1 if kat["emitted_at_threshold_minus_1"] else 0)
+        if len(res):
+            assert (res[0]["ibs0"], res[0]["ibs1"], res[0]["ibs2"]) == (kat["ibs0"], kat["ibs1"], kat["ibs2"])
+    ctx.set_king_variant(-1)
+
+
+CASES = [
+    # n, sites, split, shard, threshold
+    (2, 1, 1, 0, -1.0), (3, 31, 1, 0, -1.0), (10, 32, 1, 0, -1.0), (17, 33, 1, 0, -1.0), (64, 63, 1, 0, -1.0),
+    (65, 64, 1, 0, -1.0), (66, 65, 1, 0, 0.05), (129, 511, 1, 0, 0.05), (200, 513, 1, 0, 0.0884),
+    (300, 1000, 2, 0, 0.05), (300, 1000, 2, 1, -1.0), (300, 1000, 2, 2, 0.05), (301, 999, 4, 5, -1.0),
+    (301, 999, 4, 9, -1.0), (1000, 1600, 3, 1, 0.05), (130, 10_017, 1, 0, 0.0442),
+]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,s,k,shard,thr", CASES)
+def test_king_matches_oracle(ctx, n, s, k, shard, thr, variant):
+    ctx.set_king_variant(variant)
+    rng = np.random.default_rng(n * 31 + s * 7 + shard)
+    g = random_genotypes(rng, n, s, missing=0.04)
+    if n > 6:
+        g[3] = -1                      # an all-missing sample
+        g[5][g[5] == 1] = 0            # a sample without hets: min_hets == 0 -> NaN / -inf, never emitted
+    sm = ck.submatrix(n, k, shard)
+    osm = ko_sm(sm)
+    want, count, _ = ko.king(oracle_bitset(g, osm), s, osm, thr, 1 << 20)
+    with device_planes(ctx, g, sm) as pl:
+        got = pl.king(thr, 1 << 20)
+        assert pl.last_count == count
+        assert_results_equal(got, want)
+        # raw counters for a sample of pairs (includes pairs below the threshold)
+        ii = rng.integers(sm.i_begin, sm.i_end, 64)
+        jj = rng.integers(sm.j_begin, sm.j_end, 64)
+        keep = ii < jj
+        if keep.any():
+            ii, jj = ii[keep], jj[keep]
+            counts, kin = pl.counts(ii, jj)
+            L = ko.lib()
+            import ctypes as C
+            bs = oracle_bitset(g, osm)
+            for q in range(len(ii)):
+                c, kq = ko.pair_counts(bs, s, L.ko_sample_offset(C.byref(osm), int(ii[q])),
+                                       L.ko_sample_offset(C.byref(osm), int(jj[q])))
+                assert {f: int(counts[q][f]) for f in c} == c
+                assert bits_equal_f32([kin[q]], [kq]) or (np.isnan(kin[q]) and np.isnan(kq))
+    ctx.set_king_variant(-1)
+
+
+def test_king_unsorted_is_a_permutation(ctx):
+    rng = np.random.default_rng(21)
+    g = random_genotypes(rng, 150, 400)
+    sm = ck.submatrix(150)
+    with device_planes(ctx, g, sm) as pl:
+        a = pl.king(0.0, 1 << 16, sort=True)
+        b = pl.king(0.0, 1 << 16, sort=False)
+        assert np.array_equal(np.sort(b, order=["sample_i", "sample_j"]), a)
+
+
+def test_overflow_reports_resource_exhausted(ctx):
+    rng = np.random.default_rng(22)
+    g = random_genotypes(rng, 80, 300)
+    sm = ck.submatrix(80)
+    _, count, ovf = ko.king(oracle_bitset(g, ko_sm(sm)), 300, ko_sm(sm), -1.0, 100)
+    assert ovf
+    with device_planes(ctx, g, sm) as pl:
+        with pytest.raises(ck.CukingError, match="--max_results") as e:
+            pl.king(-1.0, 100)
+        assert e.value.code == capi.CK_ERR_RESULT_OVERFLOW  # cuking.cu:747-751
+        assert pl.last_count == count                       # the counter keeps counting (cuking.cu:299)
+        assert len(pl.king(-1.0, count)) == count           # exactly enough room works
+
+
+def test_tile_slices_union_equals_full(ctx):
+    # the multi-GPU partition: contiguous slices of the tile grid, no exchange between slices
+    rng = np.random.default_rng(23)
+    for n, k, shard in [(333, 1, 0), (333, 2, 1)]:
+        g = random_genotypes(rng, n, 500)
+        sm = ck.submatrix(n, k, shard)
+        with device_planes(ctx, g, sm) as pl:
+            full = pl.king(0.02, 1 << 18)
+            tiles = pl.num_tiles()
+            for parts in (2, 3, 8):
+                cuts = [tiles * p // parts for p in range(parts + 1)]
+                got = np.concatenate([pl.king(0.02, 1 << 18, tiles=(cuts[p], cuts[p + 1])) for p in range(parts)])
+                got = np.sort(got, order=["sample_i", "sample_j"])
+                assert_results_equal(got, full)
+
+
+def test_host_bitset_seam_matches_oracle(ctx):
+    rng = np.random.default_rng(24)
+    n, s = 260, 900
+    g = random_genotypes(rng, n, s)
+    for k, shard in [(1, 0), (2, 1)]:
+        osm = ko.submatrix(n, k, shard)
+        bs = oracle_bitset(g, osm)
+        want, _, _ = ko.king(bs, s, osm, 0.05, 1 << 16)
+        got = ctx.king_host_bitset(n, k, shard, s, bs, 0.05, 1 << 16)
+        assert_results_equal(got, want)
+
+
+# ---- synthetic cohort ------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("n,s,k,shard", [(100, 700, 1, 0), (203, 333, 3, 1), (64, 10_000, 1, 0)])
+def test_synth_planes_equal_packed_triples_equal_host_generator(ctx, n, s, k, shard):
+    torch = pytest.importorskip("torch")
+    sm = ck.submatrix(n, k, shard)
+    g = ck.synth_genotypes_host(42, 0.02, 0, n, 0, s)
+    want = oracle_bitset(g, ko_sm(sm))
+    with ctx.planes(sm, s) as a:
+        a.synthesize(42, 0.02)
+        assert np.array_equal(a.export_bitset(), want)
+    r, c, al, cnt = ctx.synth_triples_device(42, 0.02, 0, n, 0, s)
+    assert cnt == int(np.sum(g >= 0))
+    with ctx.planes(sm, s) as b:
+        b.pack_device_ptrs(r, c, al, cnt)
+        assert np.array_equal(b.export_bitset(), want)
+
+
+def test_synth_triples_are_in_hail_order(ctx):
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    n, s = 70, 90
+    r, c, al, cnt = ctx.synth_triples_device(42, 0.1, 3, n, 5, s)
+    g = ck.synth_genotypes_host(42, 0.1, 3, n, 5, s)
+    site, sample, alt = triples_of(g)
+    libcudart = C.CDLL("libcudart.so")
+    def fetch(ptr, dtype):
+        out = np.empty(cnt, dtype=dtype)
+        assert libcudart.cudaMemcpy(C.c_void_p(out.ctypes.data), C.c_void_p(ptr), C.c_size_t(out.nbytes), 2) == 0
+        return out
+    assert np.array_equal(fetch(r, np.int64), site + 5)
+    assert np.array_equal(fetch(c, np.int64), sample + 3)
+    assert np.array_equal(fetch(al, np.int32), alt)
+
+
+# ---- three-way: reference kernel itself -------------------------------------------------------------------------
+
+
+@pytest.mark.skipif(not ref_kernel.available(), reason="oracle/_ref/libcuking_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("n,s,k,shard,thr", [(1000, 10_000, 1, 0, 0.05), (400, 3000, 2, 1, -1.0), (257, 1999, 3, 3, -1.0)])
+def test_three_way_reference_kernel_oracle_product(ctx, n, s, k, shard, thr):
+    g = ck.synth_genotypes_host(42, 0.02, 0, n, 0, s)
+    sm = ck.submatrix(n, k, shard)
+    osm = ko_sm(sm)
+    bs = oracle_bitset(g, osm)
+    cap = 1 << 20
+    want, count, _ = ko.king(bs, s, osm, thr, cap)
+    ref, ref_count, ref_ovf, _ = ref_kernel.king(bs, n, k, shard, ko.words_per_sample(s), thr, cap)
+    assert ref_count == count and not ref_ovf
+    assert_results_equal(ref, want)           # oracle == the reference's own kernel
+    for variant in (0, 1):
+        ctx.set_king_variant(variant)
+        with ctx.planes(sm, s) as pl:
+            pl.import_bitset(bs)
+            assert_results_equal(pl.king(thr, cap), ref)  # product == the reference's own kernel
+    ctx.set_king_variant(-1)
