@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -506,6 +507,10 @@ int ck_king_tiles(ck_planes *pl, uint64_t tile_begin, uint64_t tile_end, float k
   k.dump_counts = nullptr;
   k.dump_kin = nullptr;
   ctx->timings.king_launches = 0;
+  static const bool dbg = getenv("CUKING_DEBUG_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+  auto tp0 = now();
   CK_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), s));
   CK_CUDA(cudaEventRecord(ctx->ev[0], s));
   if (tile_end > tile_begin) {
@@ -517,6 +522,8 @@ int ck_king_tiles(ck_planes *pl, uint64_t tile_begin, uint64_t tile_end, float k
   CK_CUDA(cudaMemcpyAsync(&count, ctx->d_counter, sizeof(count), cudaMemcpyDeviceToHost, s));
   CK_CUDA(cudaStreamSynchronize(s));
   ctx->timings.king_ms = elapsed(ctx->ev[0], ctx->ev[1]);
+  if (dbg) fprintf(stderr, "[ck] king: host %.2f ms, kernel %.2f ms\n", ms_since(tp0), ctx->timings.king_ms);
+  auto tp1 = now();
   *num_results = count > 0xffffffffull ? 0xffffffffu : uint32_t(count);
   if (count > max_results)  // cuking.cu:747-751
     return fail(CK_ERR_RESULT_OVERFLOW, "Could not store all results: try increasing the --max_results parameter.");
@@ -544,12 +551,14 @@ int ck_king_tiles(ck_planes *pl, uint64_t tile_begin, uint64_t tile_end, float k
     ctx->timings.king_launches += 3;  // key build, radix sort (one logical launch), gather
     d_final = d_sorted;
   }
+  if (dbg) fprintf(stderr, "[ck] sort: host %.2f ms\n", ms_since(tp1));
   cudaEventRecord(t1, s);
   if (!results_on_device) CK_CUDA(cudaMemcpyAsync(results, d_final, size_t(n) * sizeof(ck_result), cudaMemcpyDeviceToHost, s));
   cudaEventRecord(t2, s);
   cudaError_t e = cudaStreamSynchronize(s);
   ctx->timings.sort_ms = elapsed(t0, t1);
   ctx->timings.d2h_ms = elapsed(t1, t2);
+  if (dbg) fprintf(stderr, "[ck] sort+d2h: host %.2f ms (device sort %.2f, d2h %.2f)\n", ms_since(tp1), ctx->timings.sort_ms, ctx->timings.d2h_ms);
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
   cudaEventDestroy(t2);
