@@ -1,0 +1,172 @@
+#include "parquet_io.h"
+
+#include <arrow/io/file.h>
+#include <parquet/api/reader.h>
+#include <parquet/api/writer.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <filesystem>
+
+namespace cuking {
+namespace fs = std::filesystem;
+
+std::string ListParquetFiles(const std::string &dir, std::vector<std::string> *files) {
+  std::error_code ec;
+  if (!fs::is_directory(dir, ec)) return "Input is not a directory: " + dir;
+  for (const auto &entry : fs::directory_iterator(dir, ec)) {
+    if (!entry.is_regular_file()) continue;  // skips _temporary/ etc. (non-recursive, cuking.cu:530-534)
+    const std::string name = entry.path().filename().string();
+    if (name.size() < 8 || name.compare(name.size() - 8, 8, ".parquet") != 0) continue;  // cuking.cu:537-539
+    files->push_back(entry.path().string());
+  }
+  if (ec) return "Failed to list " + dir + ": " + ec.message();
+  std::sort(files->begin(), files->end());
+  return "";
+}
+
+namespace {
+
+template <typename ReaderT, typename T>
+std::string ReadColumn(parquet::ColumnReader *column, parquet::Type::type want, const std::string &path, T *dst,
+                       size_t capacity, size_t *offset, std::vector<int16_t> *def_scratch) {
+  if (column->type() != want)  // cuking.cu:608-612, :630-634, :652-656
+    return "Expected " + parquet::TypeToString(want) + " type, found " + parquet::TypeToString(column->type()) + " in " + path;
+  if (column->descr()->max_repetition_level() > 0) return "Repeated column in " + path;
+  const bool optional = column->descr()->max_definition_level() > 0;
+  auto *reader = static_cast<ReaderT *>(column);
+  while (reader->HasNext()) {
+    const int64_t room = int64_t(capacity - *offset);
+    if (room <= 0) return "More values than rows in " + path;
+    int64_t values_read = 0, levels_read = 0;
+    if (optional) {
+      // Spark writes these columns OPTIONAL; the reference passes null def-levels because there are no nulls
+      // (cuking.cu:617-623).  Read the levels and insist on that.
+      const int64_t batch = std::min<int64_t>(room, 1 << 20);
+      def_scratch->resize(size_t(batch));
+      levels_read = reader->ReadBatch(batch, def_scratch->data(), nullptr, dst + *offset, &values_read);
+      if (values_read != levels_read) return "Null values in " + path;
+    } else {
+      levels_read = reader->ReadBatch(room, nullptr, nullptr, dst + *offset, &values_read);
+    }
+    if (values_read == 0 && levels_read == 0) break;
+    *offset += size_t(values_read);
+  }
+  return "";
+}
+
+}  // namespace
+
+std::string ReadTriples(const std::string &path, Triples *out) {
+  try {
+    std::unique_ptr<parquet::ParquetFileReader> reader = parquet::ParquetFileReader::OpenFile(path, /*memory_map=*/false);
+    const auto md = reader->metadata();
+    constexpr int kNumColumns = 3;
+    if (md->num_columns() != kNumColumns)  // cuking.cu:585-590
+      return "Expected 3 columns, found " + std::to_string(md->num_columns()) + " in " + path;
+    const size_t num_rows = size_t(md->num_rows());
+    out->row_idx.resize(num_rows);
+    out->col_idx.resize(num_rows);
+    out->n_alt_alleles.resize(num_rows);
+    size_t o0 = 0, o1 = 0, o2 = 0;
+    std::vector<int16_t> def_scratch;
+    for (int rg = 0; rg < md->num_row_groups(); ++rg) {
+      auto group = reader->RowGroup(rg);
+      std::string err;
+      auto c0 = group->Column(0);
+      err = ReadColumn<parquet::Int64Reader>(c0.get(), parquet::Type::INT64, path, out->row_idx.data(), num_rows, &o0, &def_scratch);
+      if (!err.empty()) return err;
+      auto c1 = group->Column(1);
+      err = ReadColumn<parquet::Int64Reader>(c1.get(), parquet::Type::INT64, path, out->col_idx.data(), num_rows, &o1, &def_scratch);
+      if (!err.empty()) return err;
+      auto c2 = group->Column(2);
+      err = ReadColumn<parquet::Int32Reader>(c2.get(), parquet::Type::INT32, path, out->n_alt_alleles.data(), num_rows, &o2, &def_scratch);
+      if (!err.empty()) return err;
+    }
+    if (o0 != num_rows || o1 != num_rows || o2 != num_rows) return "Column lengths differ from the row count in " + path;
+  } catch (const std::exception &e) {  // parquet::ParquetException, cuking.cu:580-583
+    return "Error reading " + path + ": " + e.what();
+  }
+  return "";
+}
+
+std::string WriteResults(const std::string &dir, uint32_t shard_index, const std::vector<std::string> &sample_ids,
+                         const ck_result *results, size_t n, std::string *path_out, size_t *bytes_written) {
+  try {
+    std::error_code ec;
+    fs::create_directories(dir, ec);
+    if (ec) return "Cannot create output directory " + dir + ": " + ec.message();
+    char name[64];
+    snprintf(name, sizeof(name), "part-%05u.snappy.parquet", shard_index);  // cuking.cu:868-870
+    const std::string path = (fs::path(dir) / name).string();
+    const std::string tmp = path + ".tmp";
+
+    using parquet::schema::PrimitiveNode;
+    parquet::schema::NodeVector fields;  // cuking.cu:770-788
+    fields.push_back(PrimitiveNode::Make("i", parquet::Repetition::REQUIRED, parquet::LogicalType::String(), parquet::Type::BYTE_ARRAY));
+    fields.push_back(PrimitiveNode::Make("j", parquet::Repetition::REQUIRED, parquet::LogicalType::String(), parquet::Type::BYTE_ARRAY));
+    fields.push_back(PrimitiveNode::Make("kin", parquet::Repetition::REQUIRED, parquet::LogicalType::None(), parquet::Type::FLOAT));
+    fields.push_back(PrimitiveNode::Make("ibs0", parquet::Repetition::REQUIRED, parquet::LogicalType::None(), parquet::Type::INT32));
+    fields.push_back(PrimitiveNode::Make("ibs1", parquet::Repetition::REQUIRED, parquet::LogicalType::None(), parquet::Type::INT32));
+    fields.push_back(PrimitiveNode::Make("ibs2", parquet::Repetition::REQUIRED, parquet::LogicalType::None(), parquet::Type::INT32));
+    auto schema = std::static_pointer_cast<parquet::schema::GroupNode>(
+        parquet::schema::GroupNode::Make("schema", parquet::Repetition::REQUIRED, fields));  // cuking.cu:789-791
+
+    auto sink_result = arrow::io::FileOutputStream::Open(tmp);
+    if (!sink_result.ok()) return "Cannot open " + tmp + ": " + sink_result.status().ToString();
+    std::shared_ptr<arrow::io::FileOutputStream> sink = *sink_result;
+    parquet::WriterProperties::Builder props;
+    props.compression(parquet::Compression::SNAPPY);  // Hail's libhadoop has no ZSTD, cuking.cu:797-798
+    props.max_row_group_length(int64_t(1) << 62);
+    std::shared_ptr<parquet::ParquetFileWriter> writer = parquet::ParquetFileWriter::Open(sink, schema, props.build());
+    parquet::RowGroupWriter *rg = writer->AppendRowGroup();  // single row group, cuking.cu:804-805
+
+    constexpr size_t kBatch = 1 << 16;  // the reference writes one value per WriteBatch call (:810-859); batch instead
+    for (int which = 0; which < 2; ++which) {  // i, j
+      auto *col = static_cast<parquet::ByteArrayWriter *>(rg->NextColumn());
+      std::vector<parquet::ByteArray> batch(std::min(kBatch, std::max<size_t>(n, 1)));
+      for (size_t base = 0; base < n; base += kBatch) {
+        const size_t m = std::min(kBatch, n - base);
+        for (size_t q = 0; q < m; ++q) {
+          const uint32_t s = which == 0 ? results[base + q].sample_i : results[base + q].sample_j;
+          if (s >= sample_ids.size()) return "Result refers to sample " + std::to_string(s) + " beyond metadata.json";
+          batch[q] = parquet::ByteArray(uint32_t(sample_ids[s].size()), reinterpret_cast<const uint8_t *>(sample_ids[s].data()));
+        }
+        col->WriteBatch(int64_t(m), nullptr, nullptr, batch.data());
+      }
+    }
+    {  // kin
+      auto *col = static_cast<parquet::FloatWriter *>(rg->NextColumn());
+      std::vector<float> batch(std::min(kBatch, std::max<size_t>(n, 1)));
+      for (size_t base = 0; base < n; base += kBatch) {
+        const size_t m = std::min(kBatch, n - base);
+        for (size_t q = 0; q < m; ++q) batch[q] = results[base + q].kin;
+        col->WriteBatch(int64_t(m), nullptr, nullptr, batch.data());
+      }
+    }
+    for (int which = 0; which < 3; ++which) {  // ibs0, ibs1, ibs2
+      auto *col = static_cast<parquet::Int32Writer *>(rg->NextColumn());
+      std::vector<int32_t> batch(std::min(kBatch, std::max<size_t>(n, 1)));
+      for (size_t base = 0; base < n; base += kBatch) {
+        const size_t m = std::min(kBatch, n - base);
+        for (size_t q = 0; q < m; ++q) {
+          const ck_result &r = results[base + q];
+          batch[q] = int32_t(which == 0 ? r.ibs0 : which == 1 ? r.ibs1 : r.ibs2);
+        }
+        col->WriteBatch(int64_t(m), nullptr, nullptr, batch.data());
+      }
+    }
+    writer->Close();
+    auto st = sink->Close();
+    if (!st.ok()) return "Cannot close " + tmp + ": " + st.ToString();
+    fs::rename(tmp, path, ec);  // readers never see a partial part file
+    if (ec) return "Cannot rename " + tmp + ": " + ec.message();
+    if (path_out) *path_out = path;
+    if (bytes_written) *bytes_written = size_t(fs::file_size(path, ec));
+  } catch (const std::exception &e) {
+    return std::string("Error writing results: ") + e.what();
+  }
+  return "";
+}
+
+}  // namespace cuking
