@@ -111,11 +111,16 @@ Status ReadMetadata(const std::string &dir, Metadata *md) {  // cuking.cu:475-50
   return Ok();
 }
 
+// One GPU of the box.  Calls on one ck_ctx are not thread-safe, so the decode threads serialise on `mu`.
+struct Gpu {
+  ck_ctx *ctx = nullptr;
+  std::mutex mu;
+};
+
 // Planes of one shard on one GPU.
 struct ShardOnGpu {
-  ck_ctx *ctx = nullptr;
+  Gpu *gpu = nullptr;
   ck_planes *planes = nullptr;
-  std::mutex mu;  // ck calls on one ctx are not thread-safe; decode threads serialise their pack calls here
 };
 
 struct ShardJob {
@@ -150,15 +155,15 @@ Status Run(const Flags &flags) {
   if (device_count <= 0) return Internal("No CUDA device found (this program has no CPU fallback)");
   if (flags.device + int(flags.num_gpus) > device_count)
     return InvalidArgument("--device/--num_gpus exceed the " + std::to_string(device_count) + " visible CUDA devices");
-  std::vector<ck_ctx *> ctxs(flags.num_gpus, nullptr);
+  std::vector<Gpu> gpus(flags.num_gpus);
   struct CtxCloser {
-    std::vector<ck_ctx *> *v;
+    std::vector<Gpu> *v;
     ~CtxCloser() {
-      for (ck_ctx *c : *v) ck_ctx_destroy(c);
+      for (Gpu &g : *v) ck_ctx_destroy(g.ctx);
     }
-  } ctx_closer{&ctxs};
+  } ctx_closer{&gpus};
   for (uint32_t g = 0; g < flags.num_gpus; ++g)
-    if (int rc = ck_ctx_create(flags.device + int(g), &ctxs[g]); rc != CK_OK) return FromCk(rc);
+    if (int rc = ck_ctx_create(flags.device + int(g), &gpus[g].ctx); rc != CK_OK) return FromCk(rc);
 
   // ---- shard planning (cuking.cu:505) and plane allocation (:513-523) ----
   // One shard: all GPUs hold its planes and split its tile grid.  --all_shards: shards are dealt round-robin to the
@@ -185,8 +190,8 @@ Status Run(const Flags &flags) {
     const uint32_t g_end = flags.all_shards ? g_begin + 1 : flags.num_gpus;
     for (uint32_t g = g_begin; g < g_end; ++g) {
       auto rep = std::make_unique<ShardOnGpu>();
-      rep->ctx = ctxs[g];
-      if (int rc = ck_planes_create(ctxs[g], &job.sm, md.num_sites, &rep->planes); rc != CK_OK) return FromCk(rc);
+      rep->gpu = &gpus[g];
+      if (int rc = ck_planes_create(gpus[g].ctx, &job.sm, md.num_sites, &rep->planes); rc != CK_OK) return FromCk(rc);
       uint64_t b = 0;
       ck_planes_device_bytes(rep->planes, &b);
       plane_bytes += b;
@@ -229,7 +234,7 @@ Status Run(const Flags &flags) {
           total_triples += t.row_idx.size();
           for (ShardJob &job : jobs) {
             for (ShardOnGpu *rep : job.replicas) {
-              std::lock_guard<std::mutex> l(rep->mu);
+              std::lock_guard<std::mutex> l(rep->gpu->mu);
               const int rc = ck_pack_triples(rep->planes, t.row_idx.data(), t.col_idx.data(), t.n_alt_alleles.data(),
                                              t.row_idx.size(), /*on_device=*/0);
               if (rc != CK_OK) {
@@ -314,7 +319,7 @@ Status Run(const Flags &flags) {
       num_results = uint32_t(total);
     }
     ck_timings tm{};
-    ck_ctx_get_timings(job.replicas[0]->ctx, &tm);
+    ck_ctx_get_timings(job.replicas[0]->gpu->ctx, &tm);
     std::cout << " (" << stop_watch.ElapsedAndReset() << "; kernel " << tm.king_ms << " ms on GPU " << flags.device << ")"
               << std::endl;
 
