@@ -156,7 +156,7 @@ int ck_ctx_set_stream(ck_ctx *ctx, void *cuda_stream) {
 
 int ck_ctx_set_king_variant(ck_ctx *ctx, int variant) {
   if (!ctx) return fail(CK_ERR_INVALID_ARGUMENT, "ctx is NULL");
-  if (variant < -1 || variant > 1) return fail(CK_ERR_INVALID_ARGUMENT, "unknown pairwise kernel variant");
+  if (variant < -1 || variant > 2) return fail(CK_ERR_INVALID_ARGUMENT, "unknown pairwise kernel variant");
   ctx->king_variant = variant;
   return CK_OK;
 }
@@ -450,6 +450,19 @@ static int sort_results(ck_ctx *ctx, const ck_result *in, uint32_t n, ck_result 
   return CK_OK;
 }
 
+static int active_variant(const ck_ctx *ctx) { return ctx->king_variant >= 0 ? ctx->king_variant : g_default_variant; }
+
+static uint64_t variant_num_tiles(const ck_planes *pl, const KingLaunch &k) {
+  if (active_variant(pl->ctx) == 2) return king_umma_num_tiles(k);
+  return king_num_tiles(k.num_row_blocks, k.num_col_blocks, k.triangular != 0);
+}
+
+static cudaError_t dispatch_king(const ck_planes *pl, const KingLaunch &k, cudaStream_t s, uint32_t *launches) {
+  const int variant = active_variant(pl->ctx);
+  if (variant == 2) return launch_king_umma(k, pl->map.num_blocks, s, launches);
+  return launch_king(k, variant, s, launches);
+}
+
 static KingLaunch base_launch(const ck_planes *pl) {
   const ck_submatrix &sm = pl->map.sm;
   KingLaunch k{};
@@ -470,7 +483,7 @@ static KingLaunch base_launch(const ck_planes *pl) {
 int ck_king_num_tiles(const ck_planes *pl, uint64_t *num_tiles) {
   if (!pl || !num_tiles) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
   const KingLaunch k = base_launch(pl);
-  *num_tiles = king_num_tiles(k.num_row_blocks, k.num_col_blocks, k.triangular != 0);
+  *num_tiles = variant_num_tiles(pl, k);
   return CK_OK;
 }
 
@@ -483,7 +496,7 @@ int ck_king_tiles(ck_planes *pl, uint64_t tile_begin, uint64_t tile_end, float k
   DeviceGuard guard(ctx->device);
   cudaStream_t s = ctx->stream;
   KingLaunch k = base_launch(pl);
-  const uint64_t total = king_num_tiles(k.num_row_blocks, k.num_col_blocks, k.triangular != 0);
+  const uint64_t total = variant_num_tiles(pl, k);
   if (tile_begin > tile_end || tile_end > total) return fail(CK_ERR_INVALID_ARGUMENT, "tile range outside the tile grid");
   int rc = ensure_compute(pl);
   if (rc != CK_OK) return rc;
@@ -513,10 +526,7 @@ int ck_king_tiles(ck_planes *pl, uint64_t tile_begin, uint64_t tile_end, float k
   auto tp0 = now();
   CK_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), s));
   CK_CUDA(cudaEventRecord(ctx->ev[0], s));
-  if (tile_end > tile_begin) {
-    const int variant = ctx->king_variant >= 0 ? ctx->king_variant : g_default_variant;
-    CK_CUDA(launch_king(k, variant, s, &ctx->timings.king_launches));
-  }
+  if (tile_end > tile_begin) CK_CUDA(dispatch_king(pl, k, s, &ctx->timings.king_launches));
   CK_CUDA(cudaEventRecord(ctx->ev[1], s));
   unsigned long long count = 0;
   CK_CUDA(cudaMemcpyAsync(&count, ctx->d_counter, sizeof(count), cudaMemcpyDeviceToHost, s));
@@ -598,7 +608,7 @@ int ck_king_counts(ck_planes *pl, const uint32_t *sample_i, const uint32_t *samp
   CK_CUDA(cudaMemsetAsync(d_kin.p, 0, rows * cols * sizeof(float), s));
   KingLaunch k = base_launch(pl);
   k.tile_begin = 0;
-  k.tile_end = king_num_tiles(k.num_row_blocks, k.num_col_blocks, k.triangular != 0);
+  k.tile_end = variant_num_tiles(pl, k);
   k.kin_threshold = 2.f;  // nothing is emitted: kin <= 0.5
   k.max_results = 0;
   k.results = nullptr;
@@ -606,8 +616,7 @@ int ck_king_counts(ck_planes *pl, const uint32_t *sample_i, const uint32_t *samp
   k.dump_counts = d_counts.as<ck_counts>();
   k.dump_kin = d_kin.as<float>();
   CK_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), s));
-  const int variant = ctx->king_variant >= 0 ? ctx->king_variant : g_default_variant;
-  CK_CUDA(launch_king(k, variant, s, nullptr));
+  CK_CUDA(dispatch_king(pl, k, s, nullptr));
   std::vector<ck_counts> h_counts(rows * cols);
   std::vector<float> h_kin(rows * cols);
   CK_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, rows * cols * sizeof(ck_counts), cudaMemcpyDeviceToHost, s));

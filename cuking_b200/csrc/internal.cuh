@@ -101,4 +101,8 @@ struct KingLaunch {
 uint64_t king_num_tiles(uint32_t num_row_blocks, uint32_t num_col_blocks, bool triangular);
 cudaError_t launch_king(const KingLaunch &k, int variant, cudaStream_t s, uint32_t *launches);
 
+// ---- king_umma_kernel.cu (variant 2: tcgen05 int8 tensor-core formulation, 128 x 96 tiles) ----
+uint64_t king_umma_num_tiles(const KingLaunch &k);
+cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, cudaStream_t s, uint32_t *launches);
+
 }  // namespace ck

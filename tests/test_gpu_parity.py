@@ -113,7 +113,7 @@ def load_kats():
         return json.load(f)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("kat", load_kats(), ids=lambda k: k["id"])
 def test_known_answer_vectors_on_gpu(ctx, kat, variant):
     ctx.set_king_variant(variant)
@@ -143,7 +143,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("n,s,k,shard,thr", CASES)
 def test_king_matches_oracle(ctx, n, s, k, shard, thr, variant):
     ctx.set_king_variant(variant)
@@ -201,10 +201,12 @@ def test_overflow_reports_resource_exhausted(ctx):
         assert len(pl.king(-1.0, count)) == count           # exactly enough room works
 
 
-def test_tile_slices_union_equals_full(ctx):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_tile_slices_union_equals_full(ctx, variant):
     # the multi-GPU partition: contiguous slices of the tile grid, no exchange between slices
     rng = np.random.default_rng(23)
-    for n, k, shard in [(333, 1, 0), (333, 2, 1)]:
+    ctx.set_king_variant(variant)
+    for n, k, shard in [(333, 1, 0), (333, 2, 1), (700, 1, 0)]:
         g = random_genotypes(rng, n, 500)
         sm = ck.submatrix(n, k, shard)
         with device_planes(ctx, g, sm) as pl:
@@ -215,6 +217,7 @@ def test_tile_slices_union_equals_full(ctx):
                 got = np.concatenate([pl.king(0.02, 1 << 18, tiles=(cuts[p], cuts[p + 1])) for p in range(parts)])
                 got = np.sort(got, order=["sample_i", "sample_j"])
                 assert_results_equal(got, full)
+    ctx.set_king_variant(-1)
 
 
 def test_host_bitset_seam_matches_oracle(ctx):
@@ -280,7 +283,7 @@ def test_three_way_reference_kernel_oracle_product(ctx, n, s, k, shard, thr):
     ref, ref_count, ref_ovf, _ = ref_kernel.king(bs, n, k, shard, ko.words_per_sample(s), thr, cap)
     assert ref_count == count and not ref_ovf
     assert_results_equal(ref, want)           # oracle == the reference's own kernel
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         ctx.set_king_variant(variant)
         with ctx.planes(sm, s) as pl:
             pl.import_bitset(bs)
