@@ -317,10 +317,13 @@ def main():
             hbm_peak = json.load(f).get("hbm_gbs")
     except OSError:
         pass
-    # algorithmic HBM bytes per launch: each 64x64 tile streams its row block and its column block once
-    tile_bytes = 2 * 64 * (planes.device_bytes() / (5.0 / 3.0) / max(1, -(-n_samples // 64) * 64))
+    # algorithmic HBM bytes per launch: each tile streams its row samples and its column samples once
+    # (tcgen05 variant: 128 x 80 tiles of 4-bit genotype codes; LOP3+POPC variants: 64 x 64 tiles of 3 bit planes)
+    words = -(-(-(-n_sites // 32)) // 16) * 16
+    umma = args.variant in (-1, 2)
+    tile_bytes = (128 + 80) * words * 16 if umma else 2 * 64 * words * 12
     roofline = {
-        "bound": "popc", "kernel": "king_tile_kernel",
+        "bound": "popc", "kernel": "king_umma_kernel" if umma else "king_tile_kernel",
         "achieved": achieved / 1e9, "peak": peaks["popc_lane_ops_per_s"] / 1e9, "unit": "G POPC.32 lane-ops/s",
         "frac": achieved / peaks["popc_lane_ops_per_s"], "traffic": None,
         "peak_source": "measured live on this GPU by ck_measure_int_peaks (16 lanes/clk/SM x 148 SM x SM clock); "
@@ -328,6 +331,10 @@ def main():
         "algorithmic_per_unit": "0.1875 POPC.32 lane-ops per pair·site (reference formulation, 6 popcounts per site-bit)",
         "kernel_ms": kernel_ms, "units_per_launch": my_units,
         "lop3_peak": peaks["lop3_lane_ops_per_s"] / 1e9,
+        "tensor": ({"achieved_int8_tops": my_units * 10.0 / (kernel_ms * 1e-3) / 1e12, "peak_int8_tops": 8192 * 2 * 148 * 1.965e9 / 1e12,
+                    "frac": my_units * 10.0 / (kernel_ms * 1e-3) / (8192 * 2 * 148 * 1.965e9),
+                    "note": "5 int8 MACs (10 ops) per pair-site; peak = 8192 MAC/clk/SM measured by tools/umma_i8_probe.cu x 148 SM x 1965 MHz"}
+                   if umma else None),
         "hbm": {"algorithmic_gbs": (t_end - t_begin) * tile_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "note": "tile operand streaming; L2 absorbs most of it - the kernel is not HBM-bound"},
     }
@@ -381,7 +388,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 bit planes (LOP3+POPC), fp32 kinship", "data": "synthetic",
+            "dtype": "int8 indicator GEMMs with s32 accumulation (tcgen05), fp32 kinship" if args.variant in (-1, 2) else "u32 bit planes (LOP3+POPC), fp32 kinship", "data": "synthetic",
             "config": {
                 "workload": f"{args.workload}: {n_samples} samples x {n_sites} sites, missing {missing}, "
                             f"kin_threshold {thr}, max_results {max_results}"

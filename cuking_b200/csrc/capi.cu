@@ -85,8 +85,10 @@ int king_variant_from_env() {
 
 using namespace ck;
 
-// default pairwise kernel variant: 0 = 5 POPC per pair-word, 1 = carry-save (2.5 POPC + 5 more LOP3)
-static int g_default_variant = 1;
+// default pairwise kernel variant: 0 = 5 POPC per pair-word, 1 = carry-save (2.5 POPC + 5 more LOP3),
+// 2 = tcgen05 int8 tensor-core formulation
+static int g_default_variant = 2;
+static int active_variant(const ck_ctx *ctx) { return ctx->king_variant >= 0 ? ctx->king_variant : g_default_variant; }
 
 extern "C" {
 
@@ -190,6 +192,8 @@ int ck_ctx_destroy(ck_ctx *ctx) {
   if (ctx->syn_col) cudaFree(ctx->syn_col);
   if (ctx->syn_alt) cudaFree(ctx->syn_alt);
   if (ctx->result_buf) cudaFree(ctx->result_buf);
+  if (ctx->tile_table) cudaFree(ctx->tile_table);
+  if (ctx->sort_scratch) cudaFree(ctx->sort_scratch);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -230,7 +234,7 @@ int ck_planes_reset(ck_planes *pl) {
   if (!pl) return fail(CK_ERR_INVALID_ARGUMENT, "planes is NULL");
   DeviceGuard guard(pl->ctx->device);
   if (pl->raw_words()) CK_CUDA(launch_fill_missing(pl->raw, pl->raw_words(), pl->ctx->stream));
-  pl->compute_stale = true;
+  pl->mark_stale();
   CK_CUDA(cudaStreamSynchronize(pl->ctx->stream));
   return CK_OK;
 }
@@ -241,6 +245,7 @@ int ck_planes_destroy(ck_planes *pl) {
   cudaStreamSynchronize(pl->ctx->stream);
   if (pl->raw) cudaFree(pl->raw);
   if (pl->compute) cudaFree(pl->compute);
+  if (pl->codes) cudaFree(pl->codes);
   delete pl;
   return CK_OK;
 }
@@ -253,19 +258,24 @@ int ck_planes_num_sites(const ck_planes *pl, uint32_t *num_sites) {
 
 int ck_planes_device_bytes(const ck_planes *pl, uint64_t *bytes) {
   if (!pl || !bytes) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
-  *bytes = uint64_t(pl->raw_words() + pl->compute_words()) * 4;
+  *bytes = uint64_t(pl->raw_words() + pl->compute_words() + (pl->codes ? pl->codes_words() : 0)) * 4;
   return CK_OK;
 }
 
+// Derives what the active pairwise kernel reads from the raw planes: the H/D/A compute planes (variants 0, 1) or the
+// nibble-coded genotypes (variant 2, allocated on first use).
 static int ensure_compute(ck_planes *pl) {
-  if (!pl->compute_stale) return CK_OK;
   ck_ctx *ctx = pl->ctx;
+  const bool want_codes = active_variant(ctx) == 2;
+  if (want_codes ? !pl->codes_stale : !pl->compute_stale) return CK_OK;
+  if (want_codes && pl->codes == nullptr)
+    CK_CUDA(cudaMalloc(&pl->codes, std::max<size_t>(pl->codes_words(), 1) * 4));
   CK_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  if (pl->raw_words()) CK_CUDA(launch_finalize(*pl, ctx->stream));
+  if (pl->raw_words()) CK_CUDA(want_codes ? launch_finalize_codes(*pl, ctx->stream) : launch_finalize(*pl, ctx->stream));
   CK_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   CK_CUDA(cudaEventSynchronize(ctx->ev[1]));
   ctx->timings.finalize_ms = elapsed(ctx->ev[0], ctx->ev[1]);
-  pl->compute_stale = false;
+  (want_codes ? pl->codes_stale : pl->compute_stale) = false;
   return CK_OK;
 }
 
@@ -301,7 +311,7 @@ int ck_pack_triples(ck_planes *pl, const int64_t *row_idx, const int64_t *col_id
   DeviceGuard guard(ctx->device);
   cudaStream_t s = ctx->stream;
   CK_CUDA(cudaMemsetAsync(ctx->d_pack_err, 0xff, 2 * sizeof(uint32_t), s));
-  pl->compute_stale = true;
+  pl->mark_stale();
   CK_CUDA(cudaEventRecord(ctx->ev[0], s));
   if (on_device) {
     CK_CUDA(launch_pack(*pl, row_idx, col_idx, n_alt_alleles, n, 0, ctx->d_pack_err, s));
@@ -376,7 +386,7 @@ int ck_planes_import_bitset(ck_planes *pl, const uint64_t *bit_set, int on_devic
   ctx->timings.import_ms = elapsed(ctx->ev[1], ev2);
   cudaEventDestroy(ev2);
   CK_CUDA(e);
-  pl->compute_stale = true;
+  pl->mark_stale();
   return CK_OK;
 }
 
@@ -407,7 +417,7 @@ int ck_planes_synthesize(ck_planes *pl, const ck_synth_params *params) {
     CK_CUDA(launch_fill_missing(pl->raw, pl->raw_words(), ctx->stream));
     CK_CUDA(launch_synth_planes(*pl, params->seed, missing_threshold(params->missing_rate), ctx->stream));
   }
-  pl->compute_stale = true;
+  pl->mark_stale();
   CK_CUDA(cudaStreamSynchronize(ctx->stream));
   return CK_OK;
 }
@@ -424,33 +434,47 @@ static int ensure_result_buf(ck_ctx *ctx, size_t records) {
   return CK_OK;
 }
 
-// Sorts n device records by (sample_i, sample_j) — the pair is unique, so this equals the reference's
-// (sample_i, sample_j, kin) order (cuking.cu:761-765) — into `out` (device).
-static int sort_results(ck_ctx *ctx, const ck_result *in, uint32_t n, ck_result *out) {
-  cudaStream_t s = ctx->stream;
-  DevBuf keys_a, keys_b, idx_a, idx_b, tmp;
-  CK_CUDA(keys_a.alloc(size_t(n) * 8));
-  CK_CUDA(keys_b.alloc(size_t(n) * 8));
-  CK_CUDA(idx_a.alloc(size_t(n) * 4));
-  CK_CUDA(idx_b.alloc(size_t(n) * 4));
-  const unsigned grid = (n + 255) / 256;
-  make_sort_keys_kernel<<<grid, 256, 0, s>>>(in, n, keys_a.as<unsigned long long>(), idx_a.as<uint32_t>());
-  CK_CUDA(cudaGetLastError());
-  size_t tmp_bytes = 0;
-  CK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a.as<unsigned long long>(),
-                                          keys_b.as<unsigned long long>(), idx_a.as<uint32_t>(), idx_b.as<uint32_t>(),
-                                          int(n), 0, 64, s));
-  CK_CUDA(tmp.alloc(tmp_bytes));
-  CK_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_a.as<unsigned long long>(),
-                                          keys_b.as<unsigned long long>(), idx_a.as<uint32_t>(), idx_b.as<uint32_t>(),
-                                          int(n), 0, 64, s));
-  gather_results_kernel<<<grid, 256, 0, s>>>(in, idx_b.as<uint32_t>(), n, out);
-  CK_CUDA(cudaGetLastError());
-  CK_CUDA(cudaStreamSynchronize(s));
+static int ensure_sort_scratch(ck_ctx *ctx, size_t bytes) {
+  if (ctx->sort_scratch_bytes >= bytes) return CK_OK;
+  if (ctx->sort_scratch) cudaFree(ctx->sort_scratch);
+  ctx->sort_scratch = nullptr;
+  ctx->sort_scratch_bytes = 0;
+  const size_t want = bytes + bytes / 4;  // head-room so that slightly larger result sets do not reallocate
+  CK_CUDA(cudaMalloc(&ctx->sort_scratch, want));
+  ctx->sort_scratch_bytes = want;
   return CK_OK;
 }
 
-static int active_variant(const ck_ctx *ctx) { return ctx->king_variant >= 0 ? ctx->king_variant : g_default_variant; }
+// Sorts n device records by (sample_i, sample_j) — the pair is unique, so this equals the reference's
+// (sample_i, sample_j, kin) order (cuking.cu:761-765).  `out` (device) receives the sorted records; when it is NULL
+// they stay in the ctx scratch and *sorted points at them.
+static int sort_results(ck_ctx *ctx, const ck_result *in, uint32_t n, ck_result *out, const ck_result **sorted) {
+  cudaStream_t s = ctx->stream;
+  auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+  size_t tmp_bytes = 0;
+  CK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, static_cast<unsigned long long *>(nullptr),
+                                          static_cast<unsigned long long *>(nullptr), static_cast<uint32_t *>(nullptr),
+                                          static_cast<uint32_t *>(nullptr), int(n), 0, 64, s));
+  const size_t keys_b = align(size_t(n) * 8), idx_b = align(size_t(n) * 4), tmp_b = align(tmp_bytes),
+               rec_b = out ? 0 : align(size_t(n) * sizeof(ck_result));
+  int rc = ensure_sort_scratch(ctx, 2 * keys_b + 2 * idx_b + tmp_b + rec_b);
+  if (rc != CK_OK) return rc;
+  char *base = static_cast<char *>(ctx->sort_scratch);
+  auto *keys_a = reinterpret_cast<unsigned long long *>(base);
+  auto *keys_o = reinterpret_cast<unsigned long long *>(base + keys_b);
+  auto *idx_a = reinterpret_cast<uint32_t *>(base + 2 * keys_b);
+  auto *idx_o = reinterpret_cast<uint32_t *>(base + 2 * keys_b + idx_b);
+  void *tmp = base + 2 * keys_b + 2 * idx_b;
+  ck_result *dst = out ? out : reinterpret_cast<ck_result *>(base + 2 * keys_b + 2 * idx_b + tmp_b);
+  const unsigned grid = (n + 255) / 256;
+  make_sort_keys_kernel<<<grid, 256, 0, s>>>(in, n, keys_a, idx_a);
+  CK_CUDA(cudaGetLastError());
+  CK_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_a, keys_o, idx_a, idx_o, int(n), 0, 64, s));
+  gather_results_kernel<<<grid, 256, 0, s>>>(in, idx_o, n, dst);
+  CK_CUDA(cudaGetLastError());
+  if (sorted) *sorted = dst;
+  return CK_OK;
+}
 
 static uint64_t variant_num_tiles(const ck_planes *pl, const KingLaunch &k) {
   if (active_variant(pl->ctx) == 2) return king_umma_num_tiles(k);
@@ -459,7 +483,7 @@ static uint64_t variant_num_tiles(const ck_planes *pl, const KingLaunch &k) {
 
 static cudaError_t dispatch_king(const ck_planes *pl, const KingLaunch &k, cudaStream_t s, uint32_t *launches) {
   const int variant = active_variant(pl->ctx);
-  if (variant == 2) return launch_king_umma(k, pl->map.num_blocks, s, launches);
+  if (variant == 2) return launch_king_umma(k, pl->map.num_blocks, pl->ctx, s, launches);
   return launch_king(k, variant, s, launches);
 }
 
@@ -467,6 +491,7 @@ static KingLaunch base_launch(const ck_planes *pl) {
   const ck_submatrix &sm = pl->map.sm;
   KingLaunch k{};
   k.compute = pl->compute;
+  k.codes = pl->codes;
   k.words = pl->words;
   k.row_block0 = 0;
   k.num_row_blocks = ceil_div(sm_rows(sm), kTileSamples);
@@ -495,11 +520,11 @@ int ck_king_tiles(ck_planes *pl, uint64_t tile_begin, uint64_t tile_end, float k
   ck_ctx *ctx = pl->ctx;
   DeviceGuard guard(ctx->device);
   cudaStream_t s = ctx->stream;
+  int rc = ensure_compute(pl);  // may allocate the buffer base_launch() points at
+  if (rc != CK_OK) return rc;
   KingLaunch k = base_launch(pl);
   const uint64_t total = variant_num_tiles(pl, k);
   if (tile_begin > tile_end || tile_end > total) return fail(CK_ERR_INVALID_ARGUMENT, "tile range outside the tile grid");
-  int rc = ensure_compute(pl);
-  if (rc != CK_OK) return rc;
 
   // Pairs are appended to a device buffer: the caller's when it is device memory and no sort is needed, else ours.
   ck_result *d_emit = nullptr;
@@ -546,20 +571,10 @@ int ck_king_tiles(ck_planes *pl, uint64_t tile_begin, uint64_t tile_end, float k
   CK_CUDA(cudaEventCreate(&t2));
   cudaEventRecord(t0, s);
   const ck_result *d_final = d_emit;
-  DevBuf sorted;
   if (sort) {
-    ck_result *d_sorted = nullptr;
-    if (results_on_device) {
-      d_sorted = results;
-    } else {
-      cudaError_t e = sorted.alloc(size_t(n) * sizeof(ck_result));
-      if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(sorted results)", __FILE__, __LINE__);
-      d_sorted = sorted.as<ck_result>();
-    }
-    rc = sort_results(ctx, d_emit, n, d_sorted);
+    rc = sort_results(ctx, d_emit, n, results_on_device ? results : nullptr, &d_final);
     if (rc != CK_OK) return rc;
     ctx->timings.king_launches += 3;  // key build, radix sort (one logical launch), gather
-    d_final = d_sorted;
   }
   if (dbg) fprintf(stderr, "[ck] sort: host %.2f ms\n", ms_since(tp1));
   cudaEventRecord(t1, s);

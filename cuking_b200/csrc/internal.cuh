@@ -50,6 +50,13 @@ struct ck_ctx {
   ck_result *result_buf = nullptr;
   size_t result_cap = 0;
   int king_variant = -1;  // -1 = library default
+  // alive-tile table of the tcgen05 kernel (grow-only device scratch)
+  void *tile_table = nullptr;
+  size_t tile_table_bytes = 0;
+  // grow-only scratch for the result sort (keys, indices, CUB temporaries, sorted records): no cudaMalloc/cudaFree
+  // on the steady-state path
+  void *sort_scratch = nullptr;
+  size_t sort_scratch_bytes = 0;
 };
 
 struct ck_planes {
@@ -58,10 +65,14 @@ struct ck_planes {
   uint32_t num_sites = 0;
   uint32_t words = 0;          // padded 32-bit words per plane (multiple of kChunkWords)
   uint32_t *raw = nullptr;     // [num_blocks][words][2][64]
-  uint32_t *compute = nullptr; // [num_blocks][words][3][64]
-  bool compute_stale = true;   // raw changed since the last finalize
+  uint32_t *compute = nullptr; // [num_blocks][words][3][64]   (LOP3+POPC kernels)
+  uint32_t *codes = nullptr;   // [num_blocks][words][64][4]   (tcgen05 kernel; allocated on first use)
+  bool compute_stale = true;   // raw changed since the last finalize into `compute`
+  bool codes_stale = true;     // raw changed since the last finalize into `codes`
   size_t raw_words() const { return size_t(map.num_blocks) * words * ck::kRawPlanes * ck::kTileSamples; }
   size_t compute_words() const { return size_t(map.num_blocks) * words * ck::kComputePlanes * ck::kTileSamples; }
+  size_t codes_words() const { return size_t(map.num_blocks) * words * ck::kTileSamples * 4; }
+  void mark_stale() { compute_stale = codes_stale = true; }
 };
 
 namespace ck {
@@ -71,6 +82,7 @@ cudaError_t launch_fill_missing(uint32_t *raw, size_t num_words, cudaStream_t s)
 cudaError_t launch_pack(const ck_planes &pl, const int64_t *row, const int64_t *col, const int32_t *alt, size_t n,
                         size_t index_base, uint32_t *d_err, cudaStream_t s);
 cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s);
+cudaError_t launch_finalize_codes(const ck_planes &pl, cudaStream_t s);
 cudaError_t launch_import_ref(const ck_planes &pl, const uint64_t *d_bit_set, cudaStream_t s);
 cudaError_t launch_export_ref(const ck_planes &pl, uint64_t *d_bit_set, cudaStream_t s);
 cudaError_t launch_synth_planes(const ck_planes &pl, uint64_t seed, uint32_t miss_thr, cudaStream_t s);
@@ -83,7 +95,8 @@ cudaError_t launch_synth_emit(uint64_t seed, uint32_t miss_thr, uint32_t sample_
 
 // ---- king_kernel.cu ----
 struct KingLaunch {
-  const uint32_t *compute;  // compute planes
+  const uint32_t *compute;  // compute planes (LOP3+POPC kernels)
+  const uint32_t *codes;    // nibble-coded genotypes (tcgen05 kernel)
   uint32_t words;           // padded words per plane
   uint32_t row_block0, num_row_blocks;
   uint32_t col_block0, num_col_blocks;
@@ -103,6 +116,6 @@ cudaError_t launch_king(const KingLaunch &k, int variant, cudaStream_t s, uint32
 
 // ---- king_umma_kernel.cu (variant 2: tcgen05 int8 tensor-core formulation, 128 x 96 tiles) ----
 uint64_t king_umma_num_tiles(const KingLaunch &k);
-cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, cudaStream_t s, uint32_t *launches);
+cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches);
 
 }  // namespace ck

@@ -7,22 +7,26 @@
 //     h_i.y_j = (i het, j hom) y_i.h_j = (i hom, j het)
 //     het_i = hh + hy,  het_j = hh + yh,  shared = yy + yh + hy + hh,  conc = (yy + xx)/2,  opp = (yy - xx)/2
 // i.e. five int8 GEMMs with exact s32 accumulation (counts <= num_sites < 2^31), issued as three MMAs per 32 sites:
-//     D_xx[128 x 96]        += x_i  . x_j^T
-//     D_y [128 x (96|96)]   += y_i  . [y_j ; h_j]^T        -> (yy | yh)
-//     D_h [128 x (96|96)]   += h_i  . [y_j ; h_j]^T        -> (hy | hh)
-// which fills 480 of the 512 TMEM columns of the SM.  One CTA owns a 128 (rows, TMEM lanes) x 96 (columns) tile of
-// sample pairs.  The int8 operands are never stored in HBM (they would be 8x the bit planes and the kernel would turn
-// L2-bound): warps 0-6 expand the compute bit planes (H, D, A; csrc/layout.cuh) into K-major no-swizzle canonical
-// shared-memory tiles each stage, one thread per sample, and hand them to the single MMA-issuing thread through
-// mbarriers; tcgen05.commit releases a stage when the tensor core has consumed it.
+//     D_xx[128 x 80]        += x_i  . x_j^T
+//     D_y [128 x (80|80)]   += y_i  . [y_j ; h_j]^T        -> (yy | yh)
+//     D_h [128 x (80|80)]   += h_i  . [y_j ; h_j]^T        -> (hy | hh)
+// (h and y are stored as -1 instead of +1: every product pairs two of them, so the sign cancels.)
+// One CTA owns a 128 (rows = TMEM lanes) x 80 (columns) tile of sample pairs: 400 TMEM columns of accumulators plus
+// a 4-deep ring of A operands (3 x 8 columns per 32-site step) = 496 of the SM's 512 columns.
 //
-// Measured on B200 (tools/umma_i8_probe.cu): kind::i8 peaks at 8192 MAC/clk/SM, but an M=128 MMA with both operands
-// in shared memory takes >= ~91-112 clk whatever N is (A-operand read), so MMAs must be wide: N = 192 for the two
-// stacked products; only the x.x product (N = 96) runs below peak.
-//
-// The site order inside a 32-site K step is permuted (site 8b+j of the word -> K byte 4j+b) identically for both
-// operands, which leaves every dot product unchanged and makes the expansion 2 ALU ops per 4 bytes:
-// (word >> j) & 0x01010101.
+// The int8 operands are never stored in HBM (8x the packed genotypes; the kernel would turn L2-bound).  They are
+// expanded on the fly from the 4-bit genotype codes (csrc/layout.cuh): a code nibble is used directly as a PRMT byte
+// selector into an 8-byte value table, so 4 genotypes become 4 operand bytes in ONE instruction per operand.
+//   * warps 0-7   A operands: one thread per row sample, the two groups of four warps take alternate 32-site steps,
+//                 and write straight into TMEM with tcgen05.st (thread = TMEM lane = row) — no shared-memory traffic;
+//   * warps 8-12  B operands: two threads per column sample write K-major no-swizzle canonical shared-memory tiles,
+//                 four 32-site steps per stage so that the proxy fence and barrier round trip are amortised;
+//   * one lane of each of warps 13-15 issues one of the three MMAs (A from TMEM, B from shared memory) and releases
+//                 the A slot / B stage with tcgen05.commit.
+// Measured on B200 (tools/umma_i8_probe.cu, profiles/r01_umma_probe.txt): kind::i8 peaks at 8192 MAC/clk/SM; one
+// issuing thread sustains only one M=128 MMA per 100-160 clk whatever N is, three issuers reach the peak — hence three
+// issuers.  The first version of this kernel (both operands in shared memory, bit planes expanded with shifts) ran at
+// 81 % of the shared-memory pipe and 50 % tensor-pipe activity (profiles/r01_king_umma_v1_ncu.txt).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -35,20 +39,27 @@ namespace ck {
 
 namespace {
 
-constexpr uint32_t kUM = 128, kUN = 96;            // tile rows (A operand, TMEM lanes) x tile columns (B operand)
-constexpr uint32_t kStageWords = 2;                // 32-site words per pipeline stage
-constexpr uint32_t kStageK = 32 * kStageWords;     // K bytes per stage
-constexpr uint32_t kUStages = 4;
+constexpr uint32_t kUM = 128, kUN = 80;            // tile rows (A operand, TMEM lanes) x tile columns (B operand)
+constexpr uint32_t kASlots = 4;                    // A-operand ring in TMEM: one 32-site step per slot
+constexpr uint32_t kAStageSteps = 2;               // steps per A stage; the two groups of A warps own one stage each
+constexpr uint32_t kBStageSteps = 4;               // 32-site steps per shared-memory B stage
+constexpr uint32_t kBStages = 3;
 constexpr uint32_t kLBO = 128;                     // bytes between K-adjacent 8x16-byte core matrices
-constexpr uint32_t kSBO = (kStageK / 16) * 128;    // bytes between 8-row groups
-constexpr uint32_t kATile = (kUM / 8) * kSBO;      // one A operand plane of one stage
-constexpr uint32_t kBTile = (kUN / 8) * kSBO;
-constexpr uint32_t kStageBytes = 3 * kATile + 3 * kBTile;
-constexpr size_t kUmmaSmem = size_t(kUStages) * kStageBytes + 1024;  // + alignment slack
-constexpr uint32_t kUThreads = 256;                // warps 0-3: A expanders + epilogue, 4-6: B expanders, 7: MMA issuer
-constexpr uint32_t kExpanderWarps = 7;
+constexpr uint32_t kSBO = kBStageSteps * 2 * kLBO; // bytes between 8-row groups (a stage holds 32*kBStageSteps K bytes)
+constexpr uint32_t kBTile = (kUN / 8) * kSBO;      // one B operand plane of one stage
+constexpr uint32_t kBStageBytes = 3 * kBTile;
+constexpr size_t kUmmaSmem = size_t(kBStages) * kBStageBytes + 1024;  // + alignment slack
+constexpr uint32_t kUThreads = 512;
+constexpr uint32_t kAWarps = 8, kBWarps = (2 * kUN) / 32, kExpanderWarps = kAWarps + kBWarps;  // 8 + 5
+constexpr uint32_t kIssuers = 3;                   // warps 13, 14, 15: x, y and h MMAs
+constexpr uint32_t kAPrefetch = 2, kBPrefetch = 2; // register prefetch depth in stages
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColXX = 0, kColY = kUN, kColH = 3 * kUN;  // accumulator column bases: xx | (yy|yh) | (hy|hh)
+constexpr uint32_t kColXX = 0, kColY = kUN, kColH = 3 * kUN;  // accumulators: xx | (yy|yh) | (hy|hh)
+constexpr uint32_t kColA = 5 * kUN;                // A ring: slot s at kColA + 24 s: x, y, h (8 columns each)
+static_assert(kBWarps * 32 == 2 * kUN, "two threads per column sample must fill whole warps");
+static_assert(kColA + 24 * kASlots <= kTmemCols, "TMEM budget");
+static_assert(kASlots == 2 * kAStageSteps && kBStageSteps == 2 * kAStageSteps, "stage geometry");
+static_assert(kChunkWords % (2 * kAStageSteps * kAPrefetch) == 0 && kChunkWords % (kBStageSteps * kBPrefetch) == 0, "loop unrolling");
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   // K-major, no swizzle: ((8,n),2):((16 B, SBO), LBO); version 1 (Blackwell)
@@ -58,14 +69,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t M, uint32_t N, bool a_signed, bool b_signed) {
   return (2u << 4) /* D = s32 */ | (uint32_t(a_signed) << 7) | (uint32_t(b_signed) << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
       "}\n" ::"r"(tmem_d),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
@@ -78,6 +90,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+#ifdef CK_UMMA_PROFILE
+__device__ unsigned long long g_umma_prof[16];
+#define PROF_T() clock64()
+#define PROF_ADD(slot, dt) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_umma_prof[slot], (unsigned long long)(dt)); } while (0)
+#else
+#define PROF_T() 0ull
+#define PROF_ADD(slot, dt) do { (void)(dt); } while (0)
+#endif
 
 struct UmmaTiles {  // alive-tile enumeration (tiles with at least one i < j pair), built on the host per launch
   const unsigned long long *row_prefix;  // [num_row_tiles + 1] alive tiles before row tile t
@@ -86,34 +112,31 @@ struct UmmaTiles {  // alive-tile enumeration (tiles with at least one i < j pai
   uint32_t total_blocks;                 // 64-sample plane blocks allocated (reads beyond are treated as missing)
 };
 
-// Expands one 32-site word of one sample into the three int8 operand rows (32 K bytes each) of the canonical tile.
-//   out byte 4j+b  <-  site 8b+j
-__device__ __forceinline__ void expand_store(uint32_t H, uint32_t D, uint32_t A, uint8_t *op_x, uint8_t *op_y,
-                                             uint8_t *op_h, uint32_t row_off, uint32_t word_in_stage, uint32_t tile_bytes) {
-  (void)tile_bytes;
-  const uint32_t R = D & ~H & ~A;  // hom-ref
-  uint32_t x[8], y[8], h[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint32_t hj = (H >> j) & 0x01010101u;
-    const uint32_t aj = (A >> j) & 0x01010101u;
-    const uint32_t rj = (R >> j) & 0x01010101u;
-    h[j] = hj;
-    y[j] = aj | rj;
-    x[j] = rj * 255u + aj;  // bytes: +1 hom-alt, 0xFF = -1 hom-ref (disjoint, no inter-byte carry)
-  }
-  const uint32_t off = row_off + word_in_stage * 2 * kLBO;  // a word = 32 K bytes = two core matrices along K
-  *reinterpret_cast<uint4 *>(op_x + off) = make_uint4(x[0], x[1], x[2], x[3]);
-  *reinterpret_cast<uint4 *>(op_x + off + kLBO) = make_uint4(x[4], x[5], x[6], x[7]);
-  *reinterpret_cast<uint4 *>(op_y + off) = make_uint4(y[0], y[1], y[2], y[3]);
-  *reinterpret_cast<uint4 *>(op_y + off + kLBO) = make_uint4(y[4], y[5], y[6], y[7]);
-  *reinterpret_cast<uint4 *>(op_h + off) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4 *>(op_h + off + kLBO) = make_uint4(h[4], h[5], h[6], h[7]);
+// One code word = 8 genotypes (nibbles: 1 het, 2 hom-alt, 4 hom-ref, 0 missing) -> 8 bytes of each operand row.
+// PRMT picks, per output byte, the table byte indexed by the nibble: tables hold the operand value of each code.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ void expand_codes(uint32_t z, uint32_t &x_lo, uint32_t &x_hi, uint32_t &y_lo, uint32_t &y_hi,
+                                             uint32_t &h_lo, uint32_t &h_hi) {
+  const uint32_t zh = z >> 16;  // PRMT reads its four selector nibbles from bits 0-15
+  //            code:  0     1     2     3 | 4     (5-7 unused)
+  // x = alt - ref     0     0    +1     . | -1
+  // y = -[hom]        0     0    -1     . | -1
+  // h = -[het]        0    -1     0     . |  0
+  x_lo = prmt(0x00010000u, 0x000000ffu, z);
+  x_hi = prmt(0x00010000u, 0x000000ffu, zh);
+  y_lo = prmt(0x00ff0000u, 0x000000ffu, z);
+  y_hi = prmt(0x00ff0000u, 0x000000ffu, zh);
+  h_lo = prmt(0x0000ff00u, 0x00000000u, z);
+  h_hi = prmt(0x0000ff00u, 0x00000000u, zh);
 }
 
 __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunch p, const UmmaTiles tiles) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kUStages], empty_bar[kUStages], acc_bar;
+  __shared__ __align__(8) uint64_t full_a[2], empty_a[2], full_b[kBStages], empty_b[kBStages], acc_bar;
   __shared__ uint32_t tmem_base_smem;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -131,99 +154,177 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
   const uint32_t rows_here = min(kUM, p.num_rows - row0), cols_here = min(kUN, p.num_cols - col0);
   const uint32_t i0 = p.row_global0 + row0, j0 = p.col_global0 + col0;
 
-  if (warp == 7) {
+  if (warp == kExpanderWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (uint32_t s = 0; s < kUStages; ++s) {
-      mbar_init(&full_bar[s], kExpanderWarps);
-      mbar_init(&empty_bar[s], 1);
+    for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(&full_a[s], kAWarps / 2);  // the four warps of the group that owns the stage
+      mbar_init(&empty_a[s], kIssuers);
     }
-    mbar_init(&acc_bar, 1);
+    for (uint32_t s = 0; s < kBStages; ++s) {
+      mbar_init(&full_b[s], kBWarps);
+      mbar_init(&empty_b[s], kIssuers);
+    }
+    mbar_init(&acc_bar, kIssuers);
     mbar_fence_init();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t num_stages_total = p.words / kStageWords;  // p.words is a multiple of 16
+  const uint32_t num_steps = p.words;  // one 32-site word per step; p.words is a multiple of kChunkWords = 16
 
-  if (warp < kExpanderWarps) {
-    // ================= expanders: one thread per sample =================
-    const bool is_a = warp < 4;
-    const uint32_t srow = is_a ? tid : tid - 128;                                   // row of the A tile / of the B tile
-    const uint32_t slot = is_a ? p.row_block0 * kTileSamples + row0 + srow : p.col_block0 * kTileSamples + col0 + srow;
+  if (warp < kAWarps) {
+    // ===== A expanders: one thread per row; group g (4 warps) owns A stage g = TMEM slots 2g, 2g+1 and fills it with
+    // the steps {4n + 2g, 4n + 2g + 1}, n = 0, 1, ...  =====
+    const uint32_t group = warp >> 2, srow = (warp & 3) * 32 + lane;
+    const uint32_t slot = p.row_block0 * kTileSamples + row0 + srow;
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
-    const bool in_range = blk < tiles.total_blocks && (is_a ? srow < rows_here : srow < cols_here);
-    const uint32_t *src = p.compute + (size_t(blk) * p.words * kComputePlanes) * kTileSamples + ln;
-    const uint32_t op_base = is_a ? 0u : 3 * kATile;
-    const uint32_t tile_bytes = is_a ? kATile : kBTile;
-    const uint32_t row_off = (srow >> 3) * kSBO + (srow & 7) * 16;
-
-    auto load_stage = [&](uint32_t st, uint32_t (&w)[kStageWords][3]) {
+    const bool in_range = blk < tiles.total_blocks && srow < rows_here;
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.codes) + size_t(blk) * p.words * kTileSamples + ln;
+    const uint32_t ta = tmem_base + ((uint32_t(warp & 3) * 32u) << 16) + kColA + group * (kAStageSteps * 24);
+    const uint32_t num_fills = num_steps / kASlots;  // fills of this group's stage
+    uint4 z[kAPrefetch][kAStageSteps];
+    auto load_fill = [&](uint32_t n, uint4 (&dst)[kAStageSteps]) {
 #pragma unroll
-      for (uint32_t q = 0; q < kStageWords; ++q)
-#pragma unroll
-        for (uint32_t pl = 0; pl < 3; ++pl)
-          w[q][pl] = (in_range && st < num_stages_total)
-                         ? __ldg(src + (size_t(st * kStageWords + q) * kComputePlanes + pl) * kTileSamples)
-                         : 0u;  // out-of-range samples / stages: everything missing
+      for (uint32_t q = 0; q < kAStageSteps; ++q)
+        dst[q] = (in_range && n < num_fills) ? __ldg(src + size_t(n * kASlots + group * kAStageSteps + q) * kTileSamples)
+                                             : make_uint4(0, 0, 0, 0);
     };
-    uint32_t w0[kStageWords][3], w1[kStageWords][3], w2[kStageWords][3];
-    load_stage(0, w0);
-    load_stage(1, w1);
-    for (uint32_t st = 0; st < num_stages_total; ++st) {
-      load_stage(st + 2, w2);  // prefetch two stages ahead (covers L2/HBM latency)
-      const uint32_t s = st % kUStages, fill = st / kUStages;
-      if (fill > 0) mbar_wait(&empty_bar[s], (fill - 1) & 1u);  // the tensor core has consumed the previous fill
-      uint8_t *stage = smem + size_t(s) * kStageBytes + op_base;
 #pragma unroll
-      for (uint32_t q = 0; q < kStageWords; ++q)
-        expand_store(w0[q][kPlaneH], w0[q][kPlaneD], w0[q][kPlaneA], stage, stage + tile_bytes, stage + 2 * tile_bytes,
-                     row_off, q, tile_bytes);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (tensor core)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
+    for (uint32_t u = 0; u < kAPrefetch; ++u) load_fill(u, z[u]);
+    for (uint32_t n0 = 0; n0 < num_fills; n0 += kAPrefetch) {
 #pragma unroll
-      for (uint32_t q = 0; q < kStageWords; ++q)
+      for (uint32_t u = 0; u < kAPrefetch; ++u) {
+        const uint32_t n = n0 + u;
+        uint32_t x[kAStageSteps][8], y[kAStageSteps][8], h[kAStageSteps][8];
+        const unsigned long long p0 = PROF_T();
 #pragma unroll
-        for (uint32_t pl = 0; pl < 3; ++pl) {
-          w0[q][pl] = w1[q][pl];
-          w1[q][pl] = w2[q][pl];
+        for (uint32_t q = 0; q < kAStageSteps; ++q) {
+          expand_codes(z[u][q].x, x[q][0], x[q][1], y[q][0], y[q][1], h[q][0], h[q][1]);
+          expand_codes(z[u][q].y, x[q][2], x[q][3], y[q][2], y[q][3], h[q][2], h[q][3]);
+          expand_codes(z[u][q].z, x[q][4], x[q][5], y[q][4], y[q][5], h[q][4], h[q][5]);
+          expand_codes(z[u][q].w, x[q][6], x[q][7], y[q][6], y[q][7], h[q][6], h[q][7]);
         }
+        load_fill(n + kAPrefetch, z[u]);  // refill the registers just consumed
+        const unsigned long long p1 = PROF_T();
+        if (n > 0) mbar_wait(&empty_a[group], (n - 1) & 1u);  // the MMAs that read the previous fill have completed
+        __syncwarp();  // tcgen05.st is warp-collective; the polling loop may leave the lanes diverged
+        const unsigned long long p2 = PROF_T();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (uint32_t q = 0; q < kAStageSteps; ++q) {
+          tmem_st8(ta + q * 24, x[q]);
+          tmem_st8(ta + q * 24 + 8, y[q]);
+          tmem_st8(ta + q * 24 + 16, h[q]);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          // The issuers wait on full_a only.  Group 0's fill n starts B stage n, so it is group 0 that makes sure the
+          // B operands are in shared memory before it announces the A stage (acquire on full_b, release on full_a).
+          if (group == 0) mbar_wait(&full_b[n % kBStages], (n / kBStages) & 1u);
+          mbar_arrive(&full_a[group]);
+        }
+        const unsigned long long p3 = PROF_T();
+        PROF_ADD(0, p1 - p0);
+        PROF_ADD(1, p2 - p1);
+        PROF_ADD(2, p3 - p2);
+        PROF_ADD(3, 1);
+      }
+    }
+  } else if (warp < kExpanderWarps) {
+    // ================= B expanders: two threads per column sample, kBStageSteps steps per stage =================
+    const uint32_t idx = tid - kAWarps * 32;
+    const uint32_t half = idx / kUN, srow = idx % kUN;  // half: K bytes 16*half .. 16*half+15 of every step
+    const uint32_t slot = p.col_block0 * kTileSamples + col0 + srow;
+    const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
+    const bool in_range = blk < tiles.total_blocks && srow < cols_here;
+    const uint2 *src = reinterpret_cast<const uint2 *>(p.codes) + (size_t(blk) * p.words * kTileSamples + ln) * 2 + half;
+    const uint32_t b_off = (srow >> 3) * kSBO + (srow & 7) * 16 + half * kLBO;
+    const uint32_t num_bstages = num_steps / kBStageSteps;
+    uint2 z[kBPrefetch][kBStageSteps];
+    auto load_stage = [&](uint32_t m, uint2 (&dst)[kBStageSteps]) {
+#pragma unroll
+      for (uint32_t q = 0; q < kBStageSteps; ++q)
+        dst[q] = (in_range && m < num_bstages) ? __ldg(src + size_t(m * kBStageSteps + q) * kTileSamples * 2) : make_uint2(0, 0);
+    };
+#pragma unroll
+    for (uint32_t u = 0; u < kBPrefetch; ++u) load_stage(u, z[u]);
+    for (uint32_t m0 = 0; m0 < num_bstages; m0 += kBPrefetch) {
+#pragma unroll
+      for (uint32_t u = 0; u < kBPrefetch; ++u) {
+        const uint32_t m = m0 + u;
+        const uint32_t s = m % kBStages, fill = m / kBStages;
+        uint32_t x[kBStageSteps][4], y[kBStageSteps][4], h[kBStageSteps][4];
+        const unsigned long long p0 = PROF_T();
+#pragma unroll
+        for (uint32_t q = 0; q < kBStageSteps; ++q) {
+          expand_codes(z[u][q].x, x[q][0], x[q][1], y[q][0], y[q][1], h[q][0], h[q][1]);
+          expand_codes(z[u][q].y, x[q][2], x[q][3], y[q][2], y[q][3], h[q][2], h[q][3]);
+        }
+        load_stage(m + kBPrefetch, z[u]);
+        const unsigned long long p1 = PROF_T();
+        if (fill > 0) mbar_wait(&empty_b[s], (fill - 1) & 1u);  // the MMAs that read this stage have completed
+        const unsigned long long p2 = PROF_T();
+        uint8_t *stage = smem + size_t(s) * kBStageBytes + b_off;
+#pragma unroll
+        for (uint32_t q = 0; q < kBStageSteps; ++q) {
+          *reinterpret_cast<uint4 *>(stage + q * 2 * kLBO) = make_uint4(x[q][0], x[q][1], x[q][2], x[q][3]);
+          *reinterpret_cast<uint4 *>(stage + kBTile + q * 2 * kLBO) = make_uint4(y[q][0], y[q][1], y[q][2], y[q][3]);
+          *reinterpret_cast<uint4 *>(stage + 2 * kBTile + q * 2 * kLBO) = make_uint4(h[q][0], h[q][1], h[q][2], h[q][3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (tensor core)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_b[s]);
+        const unsigned long long p3 = PROF_T();
+        PROF_ADD(4, p1 - p0);
+        PROF_ADD(5, p2 - p1);
+        PROF_ADD(6, p3 - p2);
+        PROF_ADD(7, 1);
+      }
     }
   } else if (lane == 0) {
-    // ================= MMA issuer: one thread =================
-    constexpr uint32_t idesc_xx = make_idesc_i8(kUM, kUN, true, true);
-    constexpr uint32_t idesc_yh = make_idesc_i8(kUM, 2 * kUN, false, false);
-    const uint32_t smem_base = smem_u32(smem);
-    for (uint32_t st = 0; st < num_stages_total; ++st) {
-      const uint32_t s = st % kUStages, fill = st / kUStages;
-      mbar_wait(&full_bar[s], fill & 1u);
+    // ================= MMA issuers: one thread of each of warps 13 (x.x), 14 (y.[y;h]), 15 (h.[y;h]) =================
+    const uint32_t which = warp - kExpanderWarps;
+    const uint32_t idesc = which == 0 ? make_idesc_i8(kUM, kUN, true, true) : make_idesc_i8(kUM, 2 * kUN, true, true);
+    const uint32_t d_addr = tmem_base + (which == 0 ? kColXX : which == 1 ? kColY : kColH);
+    const uint32_t a_addr = tmem_base + kColA + which * 8;
+    const uint32_t b_addr = smem_u32(smem) + (which == 0 ? 0u : kBTile);  // x tile, or the stacked [y ; h] tiles
+    const uint32_t num_astages = num_steps / kAStageSteps;
+    for (uint32_t ma = 0; ma < num_astages; ++ma) {
+      const uint32_t g = ma & 1u, mb = ma >> 1, sb = mb % kBStages;  // A stage g, B stage mb (4 steps = 2 A stages)
+      const unsigned long long q0 = PROF_T();
+      mbar_wait(&full_a[g], (ma >> 1) & 1u);  // covers the B stage too (see the A expanders)
+      const unsigned long long q1 = PROF_T();
+      PROF_ADD(8 + which, q1 - q0);
+      PROF_ADD(11, which == 0 ? 1 : 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a0 = smem_base + s * kStageBytes, b0 = a0 + 3 * kATile;
 #pragma unroll
-      for (uint32_t q = 0; q < kStageWords; ++q) {
-        const uint32_t koff = q * 2 * kLBO;
-        const uint32_t acc = (st > 0 || q > 0) ? 1u : 0u;
-        umma_i8(tmem_base + kColXX, make_smem_desc(a0 + koff), make_smem_desc(b0 + koff), idesc_xx, acc);
-        umma_i8(tmem_base + kColY, make_smem_desc(a0 + kATile + koff), make_smem_desc(b0 + kBTile + koff), idesc_yh, acc);
-        umma_i8(tmem_base + kColH, make_smem_desc(a0 + 2 * kATile + koff), make_smem_desc(b0 + kBTile + koff), idesc_yh, acc);
+      for (uint32_t q = 0; q < kAStageSteps; ++q) {
+        const uint32_t step_in_b = g * kAStageSteps + q;
+        umma_i8_ts(d_addr, a_addr + (g * kAStageSteps + q) * 24,
+                   make_smem_desc(b_addr + sb * kBStageBytes + step_in_b * 2 * kLBO), idesc, (ma > 0 || q > 0) ? 1u : 0u);
       }
-      umma_commit(&empty_bar[s]);  // arrives when the MMAs above have finished reading this stage
+      umma_commit(&empty_a[g]);                 // arrives when this thread's MMAs so far have completed
+      if (g == 1) umma_commit(&empty_b[sb]);    // second half of the B stage done
     }
-    umma_commit(&acc_bar);  // all accumulators final
+    umma_commit(&acc_bar);  // this issuer's accumulator is final
   }
 
-  // ================= epilogue: warps 0-3, thread = row (TMEM lane) =================
-  if (warp < 4) {
+  // ================= epilogue: all 16 warps; thread = row (TMEM lane quadrant warp % 4), column chunks by warp / 4 ====
+  {
+    __syncwarp();
     mbar_wait(&acc_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t r = tid;
+    const uint32_t quad = warp & 3, group = warp >> 2;
+    const uint32_t r = quad * 32 + lane;
     const uint32_t gi = i0 + r;
-    const uint32_t lane_base = tmem_base + ((warp * 32u) << 16);
-    for (uint32_t c0 = 0; c0 < kUN; c0 += 16) {
+    const uint32_t lane_base = tmem_base + ((quad * 32u) << 16);
+    for (uint32_t c0 = group * 16; c0 < kUN; c0 += 64) {
       uint32_t xx[16], yy[16], yh[16], hy[16], hh[16];
       tmem_ld16(lane_base + kColXX + c0, xx);
       tmem_ld16(lane_base + kColY + c0, yy);
@@ -257,7 +358,7 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   __syncwarp();
-  if (warp == 7) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  if (warp == kExpanderWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
 }
 
 // ---- host side: alive-tile table ---------------------------------------------------------------------------------
@@ -295,12 +396,20 @@ TileTable build_tile_table(const KingLaunch &k) {
 
 }  // namespace
 
+#ifdef CK_UMMA_PROFILE
+extern "C" void ck_debug_umma_prof(unsigned long long *out) {
+  cudaMemcpyFromSymbol(out, g_umma_prof, sizeof(g_umma_prof));
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_umma_prof, z, sizeof(z));
+}
+#endif
+
 uint64_t king_umma_num_tiles(const KingLaunch &k) {
   if (k.num_rows == 0 || k.num_cols == 0) return 0;
   return build_tile_table(k).row_prefix.back();
 }
 
-cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, cudaStream_t s, uint32_t *launches) {
+cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(king_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUmmaSmem));
@@ -309,14 +418,19 @@ cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, cudaStr
   }
   if (k.tile_end <= k.tile_begin) return cudaSuccess;
   const TileTable tt = build_tile_table(k);
-  unsigned long long *d_prefix = nullptr;
-  uint32_t *d_first = nullptr;
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&d_prefix), tt.row_prefix.size() * 8, s);
-  if (e != cudaSuccess) return e;
-  e = cudaMallocAsync(reinterpret_cast<void **>(&d_first), tt.first_col.size() * 4, s);
-  if (e != cudaSuccess) return e;
-  e = cudaMemcpyAsync(d_prefix, tt.row_prefix.data(), tt.row_prefix.size() * 8, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_first, tt.first_col.data(), tt.first_col.size() * 4, cudaMemcpyHostToDevice, s);
+  const size_t prefix_bytes = (tt.row_prefix.size() * 8 + 255) & ~size_t(255), first_bytes = tt.first_col.size() * 4;
+  if (ctx->tile_table_bytes < prefix_bytes + first_bytes) {  // grow-only scratch owned by the ctx
+    if (ctx->tile_table) cudaFree(ctx->tile_table);
+    ctx->tile_table = nullptr;
+    ctx->tile_table_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->tile_table, prefix_bytes + first_bytes);
+    if (e != cudaSuccess) return e;
+    ctx->tile_table_bytes = prefix_bytes + first_bytes;
+  }
+  auto *d_prefix = static_cast<unsigned long long *>(ctx->tile_table);
+  auto *d_first = reinterpret_cast<uint32_t *>(static_cast<char *>(ctx->tile_table) + prefix_bytes);
+  cudaError_t e = cudaMemcpyAsync(d_prefix, tt.row_prefix.data(), tt.row_prefix.size() * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_first, tt.first_col.data(), first_bytes, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the host vectors die with this frame
   UmmaTiles tiles{d_prefix, d_first, tt.num_row_tiles, tt.num_col_tiles, total_blocks};
   constexpr uint64_t kMaxGrid = 1ull << 30;
@@ -328,8 +442,6 @@ cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, cudaStr
     if (launches) ++*launches;
     e = cudaGetLastError();
   }
-  cudaFreeAsync(d_prefix, s);
-  cudaFreeAsync(d_first, s);
   return e;
 }
 

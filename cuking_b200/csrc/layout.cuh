@@ -16,6 +16,11 @@
 //                  exactly like cuking.cu:675-703;
 //   compute planes P = 3: H = het & ~alt (true het), D = ~(het & alt) (defined), A = alt & ~het (true hom-alt),
 //                  derived once per pack by finalize_planes_kernel so the pair loop needs no per-sample decode.
+//   genotype codes (tcgen05 kernel only): 4 bits per genotype — bit 0 het, bit 1 hom-alt, bit 2 hom-ref, 0 = missing —
+//                  eight sites per uint32 (site 8t+u of a 32-site word in nibble u of code word t), laid out
+//                  codes[((b * Wp + k) * 64 + s) * 4 + t] so that one thread fetches a sample's 32 sites with one
+//                  16-byte load and a warp's loads are contiguous.  A nibble is directly a PRMT byte selector, which
+//                  turns 4 genotypes into 4 int8 operand bytes in one instruction (king_umma_kernel.cu).
 #pragma once
 #include <cstddef>
 #include <cstdint>

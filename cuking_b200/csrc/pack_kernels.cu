@@ -92,6 +92,32 @@ __global__ void __launch_bounds__(256) finalize_kernel(const uint4 *__restrict__
   }
 }
 
+// ---- finalize for the tensor-core kernel: raw (het, alt) -> nibble-coded genotypes ---------------------------------
+// spread8: bit i of the low byte -> bit 4i
+__device__ __forceinline__ uint32_t spread8(uint32_t b) {
+  b &= 0xffu;
+  b = (b | (b << 12)) & 0x000f000fu;
+  b = (b | (b << 6)) & 0x03030303u;
+  b = (b | (b << 3)) & 0x11111111u;
+  return b;
+}
+__global__ void __launch_bounds__(256) finalize_codes_kernel(const uint32_t *__restrict__ raw, uint4 *__restrict__ codes,
+                                                             size_t num_rows /* blocks * words */) {
+  const size_t total = num_rows * kTileSamples;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / kTileSamples, lane = i % kTileSamples;
+    const uint32_t het = raw[(r * kRawPlanes + 0) * kTileSamples + lane];
+    const uint32_t alt = raw[(r * kRawPlanes + 1) * kTileSamples + lane];
+    const uint32_t H = het & ~alt, A = alt & ~het, R = ~het & ~alt;  // (1,1) = missing -> code 0
+    uint32_t z[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      z[t] = spread8(H >> (8 * t)) | (spread8(A >> (8 * t)) << 1) | (spread8(R >> (8 * t)) << 2);
+    codes[i] = make_uint4(z[0], z[1], z[2], z[3]);
+  }
+}
+
 // ---- reference layout <-> raw planes ----------------------------------------------------------------------------
 // The reference bit set is sample-major (cuking.cu:204-212): slot o, plane p, 64-bit word q at
 // bit_set[o*W + p*W/2 + q]; as little-endian uint32 the 32-site word k sits at index 2*(o*W + p*W/2) + k.
@@ -252,6 +278,12 @@ cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s) {
   const size_t rows = size_t(pl.map.num_blocks) * pl.words;
   finalize_kernel<<<grid_for(rows * (kTileSamples / 4), 256), 256, 0, s>>>(
       reinterpret_cast<const uint4 *>(pl.raw), reinterpret_cast<uint4 *>(pl.compute), rows);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finalize_codes(const ck_planes &pl, cudaStream_t s) {
+  const size_t rows = size_t(pl.map.num_blocks) * pl.words;
+  finalize_codes_kernel<<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(pl.raw, reinterpret_cast<uint4 *>(pl.codes), rows);
   return cudaGetLastError();
 }
 

@@ -106,8 +106,9 @@ int ck_ctx_create(int device, ck_ctx **out);
 /* Run all later work of this ctx on an existing cudaStream_t (e.g. torch's current stream).  NULL restores the
  * ctx-owned stream. */
 int ck_ctx_set_stream(ck_ctx *ctx, void *cuda_stream);
-/* Pairwise kernel variant: 0 = 5 POPC per pair and 32 sites, 1 = carry-save (2.5 POPC + 5 more LOP3), -1 = library
- * default (also settable with the CUKING_KING_VARIANT environment variable).  Results are identical. */
+/* Pairwise kernel variant: 0 = LOP3 + 5 POPC per pair and 32 sites, 1 = carry-save (2.5 POPC + 5 more LOP3),
+ * 2 = tcgen05 int8 tensor-core formulation (five exact s32 GEMMs of indicator vectors), -1 = library default (= 2;
+ * also settable with the CUKING_KING_VARIANT environment variable).  Results are bit-identical across variants. */
 int ck_ctx_set_king_variant(ck_ctx *ctx, int variant);
 int ck_ctx_synchronize(ck_ctx *ctx);
 int ck_ctx_get_timings(ck_ctx *ctx, ck_timings *out);
@@ -160,8 +161,9 @@ int ck_planes_synthesize(ck_planes *planes, const ck_synth_params *params);
 int ck_king(ck_planes *planes, float kin_threshold, uint32_t max_results, ck_result *results, int results_on_device,
             uint32_t *num_results, int sort);
 
-/* Same, restricted to the linear range [tile_begin, tile_end) of the sub-matrix's 64x64-sample tile grid (row-major
- * over the tiles that contain at least one i < j pair).  This is how one shard is split across the GPUs of a box:
+/* Same, restricted to the linear range [tile_begin, tile_end) of the sub-matrix's tile grid (row-major over the tiles
+ * that can contain an i < j pair; the tile shape belongs to the active kernel variant, so tile counts are only
+ * comparable under one variant).  This is how one shard is split across the GPUs of a box:
  * each GPU holds the planes and takes a contiguous slice of ck_king_num_tiles().  Results of all slices together
  * equal ck_king's. */
 int ck_king_num_tiles(const ck_planes *planes, uint64_t *num_tiles);
