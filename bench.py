@@ -219,6 +219,29 @@ def run_reference_gpu_kernel(ctx, n_sites: int, missing: float, thr: float):
     return out
 
 
+# ---- pack stage (HBM-bound): triples -> bit planes on the GPU --------------------------------------------------------
+
+
+def run_pack_bench(ctx, n_samples: int, missing: float, hbm_peak_gbs):
+    """Times the GPU pack kernel (cuking.cu:675-703 moved to the device) on a slab of the workload's triples generated on
+    the device in Hail's order: all samples x 2048 sites.  Algorithmic traffic: 20 B read per triple (int64, int64, int32)."""
+    import cuking_b200 as ck
+
+    sites = 2048
+    r, c, a, n = ctx.synth_triples_device(SEED, missing, 0, n_samples, 0, sites)
+    best = None
+    with ctx.planes(ck.submatrix(n_samples), sites) as pl:
+        for _ in range(4):
+            pl.pack_device_ptrs(r, c, a, n)
+            ms = ctx.timings()["pack_ms"]
+            best = ms if best is None else min(best, ms)
+    gbs = n * 20.0 / (best * 1e-3) / 1e9
+    return {"kernel": "pack_kernel", "triples": int(n), "ms": best, "triples_per_s": n / (best * 1e-3), "achieved_gbs": gbs,
+            "peak_gbs": hbm_peak_gbs, "frac": (gbs / hbm_peak_gbs) if hbm_peak_gbs else None, "bound": "hbm",
+            "algorithmic_per_unit": "20 B read per triple (row_idx int64, col_idx int64, n_alt_alleles int32); plane writes are 2 bits per genotype",
+            "sample": f"{n_samples} samples x {sites} sites of the workload cohort, Hail order"}
+
+
 # ---- our arm ------------------------------------------------------------------------------------------------------
 
 
@@ -322,22 +345,38 @@ def main():
     words = -(-(-(-n_sites // 32)) // 16) * 16
     umma = args.variant in (-1, 2)
     tile_bytes = (128 + 80) * words * 16 if umma else 2 * 64 * words * 12
-    roofline = {
-        "bound": "popc", "kernel": "king_umma_kernel" if umma else "king_tile_kernel",
+    popc_view = {
         "achieved": achieved / 1e9, "peak": peaks["popc_lane_ops_per_s"] / 1e9, "unit": "G POPC.32 lane-ops/s",
-        "frac": achieved / peaks["popc_lane_ops_per_s"], "traffic": None,
-        "peak_source": "measured live on this GPU by ck_measure_int_peaks (16 lanes/clk/SM x 148 SM x SM clock); "
-                       "MEASURED_PEAKS.json has no integer-pipe figure",
-        "algorithmic_per_unit": "0.1875 POPC.32 lane-ops per pair·site (reference formulation, 6 popcounts per site-bit)",
-        "kernel_ms": kernel_ms, "units_per_launch": my_units,
+        "frac": achieved / peaks["popc_lane_ops_per_s"],
+        "algorithmic_per_unit": "0.1875 POPC.32 lane-ops per pair-site (reference formulation: 6 popcounts per site-bit, cuking.cu:232-239)",
+        "peak_source": "POPC.32 issue rate measured live on this GPU by ck_measure_int_peaks (16 lanes/clk/SM)",
         "lop3_peak": peaks["lop3_lane_ops_per_s"] / 1e9,
-        "tensor": ({"achieved_int8_tops": my_units * 10.0 / (kernel_ms * 1e-3) / 1e12, "peak_int8_tops": 8192 * 2 * 148 * 1.965e9 / 1e12,
-                    "frac": my_units * 10.0 / (kernel_ms * 1e-3) / (8192 * 2 * 148 * 1.965e9),
-                    "note": "5 int8 MACs (10 ops) per pair-site; peak = 8192 MAC/clk/SM measured by tools/umma_i8_probe.cu x 148 SM x 1965 MHz"}
-                   if umma else None),
-        "hbm": {"algorithmic_gbs": (t_end - t_begin) * tile_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                "note": "tile operand streaming; L2 absorbs most of it - the kernel is not HBM-bound"},
     }
+    hbm_view = {"algorithmic_gbs": (t_end - t_begin) * tile_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "note": "tile operand streaming (each tile reads its row and column samples once); mostly L2 hits"}
+    if umma:
+        # 5 exact int8 MACs = 10 ops per pair-site (xx, yy, yh, hy, hh); peak = dense int8 tcgen05 rate measured on this
+        # pool's B200 by tools/umma_i8_probe.cu (8190 MAC/clk/SM, 4075 TOP/s burst at N=256) - MEASURED_PEAKS.json only
+        # holds bf16 (int8 is nominally 2x bf16: 2 x 1390 sustained = 2781, 2 x 1657 burst = 3313 TOP/s)
+        tops = my_units * 10.0 / (kernel_ms * 1e-3) / 1e12
+        bf16 = None
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                bf16 = json.load(f)
+        except OSError:
+            pass
+        roofline = {
+            "bound": "tensor", "kernel": "king_umma_kernel", "achieved": tops, "peak": 4075.0, "unit": "TOP/s (int8, dense)",
+            "frac": tops / 4075.0, "traffic": None, "kernel_ms": kernel_ms, "units_per_launch": my_units,
+            "algorithmic_per_unit": "10 int8 ops (5 MACs: xx, yy, yh, hy, hh) per pair-site, s32 accumulation",
+            "peak_source": "measured: tools/umma_i8_probe.cu on this pool's B200 (profiles/r01_umma_probe.txt), "
+                           "kind::i8 M=128 N=256, 8190 MAC/clk/SM = 4075 TOP/s at the burst clock",
+            "vs_2x_measured_bf16_sustained": (tops / (2 * bf16["bf16_tflops_sustained"])) if bf16 else None,
+            "popc_equivalent": popc_view, "hbm": hbm_view,
+        }
+    else:
+        roofline = dict(popc_view, bound="popc", kernel="king_tile_kernel", traffic=None, kernel_ms=kernel_ms,
+                        units_per_launch=my_units, hbm=hbm_view)
 
     # ---- e2e: host buffers through the reference-facing C-ABI call (rank-local slice is the whole shard at N=1) ----
     e2e = None
@@ -373,8 +412,12 @@ def main():
                "api": "ck_king_host_bitset (pinned host bit set in the reference layout -> sorted KingResult[] on the host)"}
         del host_bits
 
-    cpu_baseline, ref_gpu = None, None
+    cpu_baseline, ref_gpu, pack = None, None, None
     if rank == 0 and n_gpus == 1:
+        try:
+            pack = run_pack_bench(ctx, n_samples, missing, hbm_peak)
+        except Exception as exc:
+            pack = {"error": repr(exc)}
         if not args.skip_ref_gpu:
             try:
                 ref_gpu = run_reference_gpu_kernel(ctx, n_sites, missing, thr)
@@ -398,7 +441,7 @@ def main():
                 "input_synthesis_s": round(synth_s, 3),
             },
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "reference_gpu_kernel": ref_gpu,
+            "reference_gpu_kernel": ref_gpu, "pack": pack,
         }
         print(json.dumps(line), flush=True)
     planes.close()

@@ -287,13 +287,17 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
         PROF_ADD(7, 1);
       }
     }
-  } else if (lane == 0) {
-    // ================= MMA issuers: one thread of each of warps 13 (x.x), 14 (y.[y;h]), 15 (h.[y;h]) =================
+  } else {
+    // ================= MMA issuers: warps 13 (x.x), 14 (y.[y;h]), 15 (h.[y;h]) =================
+    // The whole warp runs the loop (warp-uniform control flow keeps the descriptor arithmetic in the uniform
+    // datapath); one elected lane issues the MMAs and commits.
     const uint32_t which = warp - kExpanderWarps;
     const uint32_t idesc = which == 0 ? make_idesc_i8(kUM, kUN, true, true) : make_idesc_i8(kUM, 2 * kUN, true, true);
     const uint32_t d_addr = tmem_base + (which == 0 ? kColXX : which == 1 ? kColY : kColH);
     const uint32_t a_addr = tmem_base + kColA + which * 8;
-    const uint32_t b_addr = smem_u32(smem) + (which == 0 ? 0u : kBTile);  // x tile, or the stacked [y ; h] tiles
+    const uint64_t b_desc0 = make_smem_desc(smem_u32(smem) + (which == 0 ? 0u : kBTile));  // x tile, or stacked [y ; h]
+    uint32_t elected;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(elected));
     const uint32_t num_astages = num_steps / kAStageSteps;
     for (uint32_t ma = 0; ma < num_astages; ++ma) {
       const uint32_t g = ma & 1u, mb = ma >> 1, sb = mb % kBStages;  // A stage g, B stage mb (4 steps = 2 A stages)
@@ -303,16 +307,19 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
       PROF_ADD(8 + which, q1 - q0);
       PROF_ADD(11, which == 0 ? 1 : 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elected) {
 #pragma unroll
-      for (uint32_t q = 0; q < kAStageSteps; ++q) {
-        const uint32_t step_in_b = g * kAStageSteps + q;
-        umma_i8_ts(d_addr, a_addr + (g * kAStageSteps + q) * 24,
-                   make_smem_desc(b_addr + sb * kBStageBytes + step_in_b * 2 * kLBO), idesc, (ma > 0 || q > 0) ? 1u : 0u);
+        for (uint32_t q = 0; q < kAStageSteps; ++q) {
+          const uint32_t b_bytes = sb * kBStageBytes + (g * kAStageSteps + q) * 2 * kLBO;
+          umma_i8_ts(d_addr, a_addr + (g * kAStageSteps + q) * 24, b_desc0 + uint64_t(b_bytes >> 4), idesc,
+                     (ma > 0 || q > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_a[g]);                 // arrives when this thread's MMAs so far have completed
+        if (g == 1) umma_commit(&empty_b[sb]);    // second half of the B stage done
       }
-      umma_commit(&empty_a[g]);                 // arrives when this thread's MMAs so far have completed
-      if (g == 1) umma_commit(&empty_b[sb]);    // second half of the B stage done
+      __syncwarp();
     }
-    umma_commit(&acc_bar);  // this issuer's accumulator is final
+    if (elected) umma_commit(&acc_bar);  // this issuer's accumulator is final
   }
 
   // ================= epilogue: all 16 warps; thread = row (TMEM lane quadrant warp % 4), column chunks by warp / 4 ====
