@@ -40,6 +40,7 @@ struct DeviceGuard {  // every entry point runs on the ctx's device and restores
   explicit DeviceGuard(int dev) {
     cudaGetDevice(&prev);
     if (prev != dev) cudaSetDevice(dev);
+    (void)cudaGetLastError();  // a stale non-sticky error of an earlier (successful) call must not be blamed on ours
   }
   ~DeviceGuard() {
     if (prev >= 0) cudaSetDevice(prev);
@@ -73,6 +74,67 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
   cudaEventElapsedTime(&ms, a, b);
   return ms;
 }
+
+}  // namespace
+
+static bool dbg_alloc() {
+  static const bool on = getenv("CUKING_DEBUG_ALLOC") != nullptr;
+  return on;
+}
+
+cudaError_t ctx_alloc(ck_ctx *ctx, void **ptr, size_t bytes) {
+  bytes = bytes ? bytes : 1;
+  for (int i = 0; i < ck_ctx::kCacheSlots; ++i)
+    if (ctx->cache_ptr[i] && ctx->cache_bytes[i] == bytes) {
+      *ptr = ctx->cache_ptr[i];
+      ctx->cache_ptr[i] = nullptr;
+      ctx->cache_bytes[i] = 0;
+      if (dbg_alloc()) fprintf(stderr, "[ck] ctx_alloc %zu -> cached %p\n", bytes, *ptr);
+      return cudaSuccess;
+    }
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // make room: drop everything cached and retry once
+    cudaGetLastError();
+    for (int i = 0; i < ck_ctx::kCacheSlots; ++i)
+      if (ctx->cache_ptr[i]) {
+        cudaFree(ctx->cache_ptr[i]);
+        ctx->cache_ptr[i] = nullptr;
+        ctx->cache_bytes[i] = 0;
+      }
+    e = cudaMalloc(ptr, bytes);
+  }
+  if (dbg_alloc()) fprintf(stderr, "[ck] ctx_alloc %zu -> new %p\n", bytes, *ptr);
+  return e;
+}
+
+void ctx_release(ck_ctx *ctx, void *ptr, size_t bytes) {
+  if (!ptr) return;
+  static const bool no_cache = getenv("CUKING_NO_CACHE") != nullptr;
+  if (no_cache) {
+    cudaFree(ptr);
+    return;
+  }
+  bytes = bytes ? bytes : 1;
+  int slot = -1;
+  for (int i = 0; i < ck_ctx::kCacheSlots; ++i)
+    if (!ctx->cache_ptr[i]) { slot = i; break; }
+  if (slot < 0) {  // full: evict the smallest entry if it is smaller than the newcomer
+    int smallest = 0;
+    for (int i = 1; i < ck_ctx::kCacheSlots; ++i)
+      if (ctx->cache_bytes[i] < ctx->cache_bytes[smallest]) smallest = i;
+    if (ctx->cache_bytes[smallest] >= bytes) {
+      cudaFree(ptr);
+      return;
+    }
+    cudaFree(ctx->cache_ptr[smallest]);
+    slot = smallest;
+  }
+  ctx->cache_ptr[slot] = ptr;
+  ctx->cache_bytes[slot] = bytes;
+  if (dbg_alloc()) fprintf(stderr, "[ck] ctx_release %p %zu -> slot %d\n", ptr, bytes, slot);
+}
+
+namespace {
 
 int king_variant_from_env() {
   const char *v = getenv("CUKING_KING_VARIANT");
@@ -194,6 +256,8 @@ int ck_ctx_destroy(ck_ctx *ctx) {
   if (ctx->result_buf) cudaFree(ctx->result_buf);
   if (ctx->tile_table) cudaFree(ctx->tile_table);
   if (ctx->sort_scratch) cudaFree(ctx->sort_scratch);
+  for (int i = 0; i < ck_ctx::kCacheSlots; ++i)
+    if (ctx->cache_ptr[i]) cudaFree(ctx->cache_ptr[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -220,9 +284,9 @@ int ck_planes_create(ck_ctx *ctx, const ck_submatrix *sm, uint32_t num_sites, ck
     delete pl;
     return fail(CK_ERR_INVALID_ARGUMENT, "more than 65535 x 64 samples in one shard; raise --split_factor");
   }
-  cudaError_t e;
-  if ((e = cudaMalloc(&pl->raw, std::max<size_t>(pl->raw_words(), 1) * 4)) != cudaSuccess ||
-      (e = cudaMalloc(&pl->compute, std::max<size_t>(pl->compute_words(), 1) * 4)) != cudaSuccess) {
+  pl->raw_bytes = std::max<size_t>(pl->raw_words(), 1) * 4;
+  cudaError_t e = ctx_alloc(ctx, reinterpret_cast<void **>(&pl->raw), pl->raw_bytes);
+  if (e != cudaSuccess) {  // the derived buffers (compute planes / genotype codes) are allocated on first use
     ck_planes_destroy(pl);
     return fail_cuda(e, "cudaMalloc(planes)", __FILE__, __LINE__);
   }
@@ -243,9 +307,9 @@ int ck_planes_destroy(ck_planes *pl) {
   if (!pl) return CK_OK;
   DeviceGuard guard(pl->ctx->device);
   cudaStreamSynchronize(pl->ctx->stream);
-  if (pl->raw) cudaFree(pl->raw);
-  if (pl->compute) cudaFree(pl->compute);
-  if (pl->codes) cudaFree(pl->codes);
+  ctx_release(pl->ctx, pl->raw, pl->raw_bytes);
+  ctx_release(pl->ctx, pl->compute, pl->compute_bytes);
+  ctx_release(pl->ctx, pl->codes, pl->codes_bytes);
   delete pl;
   return CK_OK;
 }
@@ -258,7 +322,7 @@ int ck_planes_num_sites(const ck_planes *pl, uint32_t *num_sites) {
 
 int ck_planes_device_bytes(const ck_planes *pl, uint64_t *bytes) {
   if (!pl || !bytes) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
-  *bytes = uint64_t(pl->raw_words() + pl->compute_words() + (pl->codes ? pl->codes_words() : 0)) * 4;
+  *bytes = uint64_t(pl->raw_words() + (pl->compute ? pl->compute_words() : 0) + (pl->codes ? pl->codes_words() : 0)) * 4;
   return CK_OK;
 }
 
@@ -268,8 +332,14 @@ static int ensure_compute(ck_planes *pl) {
   ck_ctx *ctx = pl->ctx;
   const bool want_codes = active_variant(ctx) == 2;
   if (want_codes ? !pl->codes_stale : !pl->compute_stale) return CK_OK;
-  if (want_codes && pl->codes == nullptr)
-    CK_CUDA(cudaMalloc(&pl->codes, std::max<size_t>(pl->codes_words(), 1) * 4));
+  if (want_codes && pl->codes == nullptr) {
+    pl->codes_bytes = std::max<size_t>(pl->codes_words(), 1) * 4;
+    CK_CUDA(ctx_alloc(ctx, reinterpret_cast<void **>(&pl->codes), pl->codes_bytes));
+  }
+  if (!want_codes && pl->compute == nullptr) {
+    pl->compute_bytes = std::max<size_t>(pl->compute_words(), 1) * 4;
+    CK_CUDA(ctx_alloc(ctx, reinterpret_cast<void **>(&pl->compute), pl->compute_bytes));
+  }
   CK_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   if (pl->raw_words()) CK_CUDA(want_codes ? launch_finalize_codes(*pl, ctx->stream) : launch_finalize(*pl, ctx->stream));
   CK_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -365,13 +435,19 @@ int ck_planes_import_bitset(ck_planes *pl, const uint64_t *bit_set, int on_devic
   DeviceGuard guard(ctx->device);
   cudaStream_t s = ctx->stream;
   const size_t bytes = size_t(ref_words_per_sample(pl->num_sites)) * sm_samples(pl->map.sm) * 8;
-  DevBuf tmp;
+  struct Staging {  // device copy of a host bit set, returned to the ctx cache on scope exit
+    ck_ctx *ctx;
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~Staging() { ctx_release(ctx, p, bytes); }
+  } tmp{ctx};
   const uint64_t *d_src = bit_set;
   CK_CUDA(cudaEventRecord(ctx->ev[0], s));
   if (!on_device) {
-    CK_CUDA(tmp.alloc(bytes));
+    CK_CUDA(ctx_alloc(ctx, &tmp.p, bytes));
+    tmp.bytes = bytes;
     CK_CUDA(cudaMemcpyAsync(tmp.p, bit_set, bytes, cudaMemcpyHostToDevice, s));
-    d_src = tmp.as<uint64_t>();
+    d_src = static_cast<const uint64_t *>(tmp.p);
   }
   CK_CUDA(cudaEventRecord(ctx->ev[1], s));
   if (pl->raw_words()) {
@@ -452,9 +528,11 @@ static int sort_results(ck_ctx *ctx, const ck_result *in, uint32_t n, ck_result 
   cudaStream_t s = ctx->stream;
   auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
   size_t tmp_bytes = 0;
-  CK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, static_cast<unsigned long long *>(nullptr),
-                                          static_cast<unsigned long long *>(nullptr), static_cast<uint32_t *>(nullptr),
-                                          static_cast<uint32_t *>(nullptr), int(n), 0, 64, s));
+  {  // size query only (no work is launched); any valid device address serves as the pointer arguments
+    auto *k64 = reinterpret_cast<unsigned long long *>(ctx->d_counter);
+    auto *v32 = reinterpret_cast<uint32_t *>(ctx->d_counter);
+    CK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k64, k64, v32, v32, int(n), 0, 64, s));
+  }
   const size_t keys_b = align(size_t(n) * 8), idx_b = align(size_t(n) * 4), tmp_b = align(tmp_bytes),
                rec_b = out ? 0 : align(size_t(n) * sizeof(ck_result));
   int rc = ensure_sort_scratch(ctx, 2 * keys_b + 2 * idx_b + tmp_b + rec_b);

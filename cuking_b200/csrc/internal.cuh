@@ -57,10 +57,22 @@ struct ck_ctx {
   // on the steady-state path
   void *sort_scratch = nullptr;
   size_t sort_scratch_bytes = 0;
+  // small cache of released device buffers (planes, staging) so that a create / destroy cycle per call - the
+  // host-buffer entry point ck_king_host_bitset - does not pay cudaMalloc / cudaFree of gigabytes every time
+  static constexpr int kCacheSlots = 8;
+  void *cache_ptr[kCacheSlots] = {};
+  size_t cache_bytes[kCacheSlots] = {};
 };
+
+namespace ck {
+cudaError_t ctx_alloc(ck_ctx *ctx, void **ptr, size_t bytes);  // exact-size reuse from the cache, else cudaMalloc
+void ctx_release(ck_ctx *ctx, void *ptr, size_t bytes);        // into the cache (evicting the smallest entry) or cudaFree
+}  // namespace ck
+
 
 struct ck_planes {
   ck_ctx *ctx = nullptr;
+  size_t raw_bytes = 0, compute_bytes = 0, codes_bytes = 0;  // sizes of the three buffers as allocated
   ck::SlotMap map{};
   uint32_t num_sites = 0;
   uint32_t words = 0;          // padded 32-bit words per plane (multiple of kChunkWords)
