@@ -44,6 +44,7 @@ WORKLOADS = {
     "cfg1": (1_000, 10_000, 0.02, 0.05),        # configs[0] (parity-test case; selectable for quick runs)
     "mid": (20_000, 100_000, 0.01, 0.0884),     # quick smoke of the bench itself
     "prof": (8_192, 100_000, 0.01, 0.0884),     # short kernel for ncu captures (profiles/)
+    "cfg5": (50_000, 1_000_000, 0.01, -1.0),    # BASELINE.json configs[4]: dense output, every finite-kin pair is emitted
 }
 
 
@@ -273,6 +274,8 @@ def main():
     n1, n_sites, missing, thr = WORKLOADS[args.workload]
     n_samples = int(round(n1 * (n_gpus ** 0.5) / 64.0)) * 64 if n_gpus > 1 else n1  # weak scaling: pairs ~ N
     max_results = 10 << 20  # the reference's default --max_results (cuking.cu:40)
+    if thr < 0:  # dense-output stress: room for every pair of this rank's slice
+        max_results = int(n_samples * (n_samples - 1) // 2 // max(1, n_gpus) * 1.02) + 1024
 
     # a dedicated stream: the library launches on it and the timing events are recorded on it
     stream = torch.cuda.Stream(dev)

@@ -289,3 +289,70 @@ def test_three_way_reference_kernel_oracle_product(ctx, n, s, k, shard, thr):
             pl.import_bitset(bs)
             assert_results_equal(pl.king(thr, cap), ref)  # product == the reference's own kernel
     ctx.set_king_variant(-1)
+
+
+# ---- scale: dense output and the BASELINE single-GPU shape, checked through size-independent properties ---------------
+
+
+def test_dense_output_every_pair_matches_oracle(ctx):
+    # BASELINE.json configs[4] in miniature: threshold -1 emits every pair with a finite kinship
+    n, s = 3000, 5000
+    g = ck.synth_genotypes_host(42, 0.01, 0, n, 0, s)
+    sm = ck.submatrix(n)
+    osm = ko_sm(sm)
+    want, count, ovf = ko.king(oracle_bitset(g, osm), s, osm, -1.0, n * (n - 1) // 2)
+    assert not ovf and count == n * (n - 1) // 2
+    with ctx.planes(sm, s) as pl:
+        pl.synthesize(42, 0.01)
+        got = pl.king(-1.0, count)
+        assert_results_equal(got, want)
+        with pytest.raises(ck.CukingError):
+            pl.king(-1.0, count - 1)  # one slot short -> ResourceExhausted
+
+
+def test_baseline_shape_properties(ctx):
+    # BASELINE.json configs[1]: 100,000 samples x 100,000 sites, threshold 0.0884 — too large for the oracle as a
+    # whole, so: structural properties of the full result + exact oracle values for a sample of retained pairs and
+    # for one whole 256 x 256 block of the matrix.
+    n, s, thr, seed, miss = 100_000, 100_000, 0.0884, 42, 0.01
+    with ctx.planes(ck.submatrix(n), s) as pl:
+        pl.synthesize(seed, miss)
+        res = pl.king(thr, 10 << 20)
+    key = res["sample_i"].astype(np.int64) * n + res["sample_j"]
+    assert np.all(np.diff(key) > 0)                                  # sorted by (i, j), no duplicates
+    assert np.all(res["sample_i"] < res["sample_j"]) and np.all(res["kin"] > np.float32(thr))
+    assert np.all(res["sample_i"] // 8 == res["sample_j"] // 8)      # only planted pedigrees are related
+    pairs = set(zip(res["sample_i"].tolist(), res["sample_j"].tolist()))
+    first_degree = [(0, 2), (0, 3), (1, 2), (1, 3), (2, 3), (2, 5), (4, 5), (5, 7), (6, 7)]
+    for b in (0, 1, 777, n // 8 - 1):
+        for a, c in first_degree:
+            assert (8 * b + a, 8 * b + c) in pairs
+    assert 12 * (n // 8) <= len(res) <= 16 * (n // 8)
+
+    def oracle_pairs(samples_i, samples_j):
+        ids = sorted(set(samples_i) | set(samples_j))
+        pos = {x: q for q, x in enumerate(ids)}
+        g = np.stack([ck.synth_genotypes_host(seed, miss, x, x + 1, 0, s)[0] for x in ids])
+        bs, _ = ko.pack_dense(g)
+        return [ko.pair_counts(bs, s, pos[a], pos[b]) for a, b in zip(samples_i, samples_j)]
+
+    rng = np.random.default_rng(0)
+    pick = rng.choice(len(res), 48, replace=False)
+    for q, (c, kin) in zip(pick, oracle_pairs(res["sample_i"][pick].tolist(), res["sample_j"][pick].tolist())):
+        r = res[q]
+        assert (int(r["ibs0"]), int(r["ibs2"])) == (c["opposing_hom"], c["concordant_hom"] + c["both_het"])
+        assert int(r["ibs1"]) == c["shared_sites"] - int(r["ibs0"]) - int(r["ibs2"])
+        assert bits_equal_f32([r["kin"]], [kin])
+
+    # one whole off-diagonal 256 x 256 block, far from the origin: exact retained set vs the oracle
+    i0, j0, w = 40_000, 40_192, 256  # overlaps the diagonal band so that related pairs exist in it
+    ids = list(range(i0, i0 + w)) + list(range(j0, j0 + w))
+    ids = sorted(set(ids))
+    g = ck.synth_genotypes_host(seed, miss, ids[0], ids[-1] + 1, 0, s)
+    osm = ko.submatrix(g.shape[0])
+    want, _, _ = ko.king(oracle_bitset(g, osm), s, osm, thr, 1 << 20)
+    sel = (res["sample_i"] >= ids[0]) & (res["sample_j"] <= ids[-1])
+    got = res[sel].copy()
+    got["sample_i"] -= ids[0]
+    got["sample_j"] -= ids[0]
+    assert_results_equal(got, want)
