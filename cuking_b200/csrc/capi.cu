@@ -383,7 +383,18 @@ int ck_pack_triples(ck_planes *pl, const int64_t *row_idx, const int64_t *col_id
   CK_CUDA(cudaMemsetAsync(ctx->d_pack_err, 0xff, 2 * sizeof(uint32_t), s));
   pl->mark_stale();
   CK_CUDA(cudaEventRecord(ctx->ev[0], s));
+  auto is_pinned = [](const void *p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return false;
+    }
+    return at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
+  };
   if (on_device) {
+    CK_CUDA(launch_pack(*pl, row_idx, col_idx, n_alt_alleles, n, 0, ctx->d_pack_err, s));
+  } else if (is_pinned(row_idx) && is_pinned(col_idx) && is_pinned(n_alt_alleles)) {
+    // Page-locked host arrays are addressable from the device (UVA): the kernel streams them over PCIe in place.
     CK_CUDA(launch_pack(*pl, row_idx, col_idx, n_alt_alleles, n, 0, ctx->d_pack_err, s));
   } else {
     // Host arrays: memcpy into one of two pinned buffers while the GPU consumes the other (H2D + pack kernel).
@@ -426,6 +437,18 @@ int ck_pack_triples(ck_planes *pl, const int64_t *row_idx, const int64_t *col_id
   }
   if (err[1] != 0xffffffffu)
     return fail(CK_ERR_OUT_OF_RANGE, "row_idx out of range [0, num_sites) at triple " + std::to_string(size_t(err[1]) - 1));
+  return CK_OK;
+}
+
+int ck_host_alloc(size_t bytes, void **out) {
+  if (!out) return fail(CK_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  CK_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return CK_OK;
+}
+
+int ck_host_free(void *ptr) {
+  if (ptr) CK_CUDA(cudaFreeHost(ptr));
   return CK_OK;
 }
 

@@ -150,6 +150,8 @@ Status Run(const Flags &flags) {
   std::cout << " (" << stop_watch.ElapsedAndReset() << ")" << std::endl;
 
   // ---- devices ----
+  std::cout << "Initializing CUDA...";
+  std::cout.flush();
   int device_count = 0;
   if (int rc = ck_device_count(&device_count); rc != CK_OK) return FromCk(rc);
   if (device_count <= 0) return Internal("No CUDA device found (this program has no CPU fallback)");
@@ -164,6 +166,7 @@ Status Run(const Flags &flags) {
   } ctx_closer{&gpus};
   for (uint32_t g = 0; g < flags.num_gpus; ++g)
     if (int rc = ck_ctx_create(flags.device + int(g), &gpus[g].ctx); rc != CK_OK) return FromCk(rc);
+  std::cout << " " << flags.num_gpus << " GPU(s) (" << stop_watch.ElapsedAndReset() << ")" << std::endl;
 
   // ---- shard planning (cuking.cu:505) and plane allocation (:513-523) ----
   // One shard: all GPUs hold its planes and split its tile grid.  --all_shards: shards are dealt round-robin to the
@@ -218,6 +221,7 @@ Status Run(const Flags &flags) {
     std::atomic<size_t> next(0), processed(0), total_triples(0);
     std::mutex err_mu;
     Status first_error;  // first error wins, like ParallelFor (cuking.cu:415-433)
+    constexpr size_t kChunkRows = size_t(1) << 20;  // 20 MiB of page-locked memory per reader thread
     auto worker = [&]() {
       cuking::Triples t;
       for (;;) {
@@ -228,24 +232,26 @@ Status Run(const Flags &flags) {
           if (!first_error.ok()) return;
         }
         Status st;
-        if (std::string e = cuking::ReadTriples(files[f], &t); !e.empty()) {
-          st = (e.rfind("Error reading", 0) == 0) ? Unknown(e) : FailedPrecondition(e);
-        } else {
-          total_triples += t.row_idx.size();
+        // Stream the file through this thread's page-locked chunk buffer: decode a chunk, let every shard that needs it
+        // pack it on its GPU (the kernel reads the pinned chunk in place), decode the next chunk.
+        auto consume = [&](size_t first_row) -> std::string {
           for (ShardJob &job : jobs) {
             for (ShardOnGpu *rep : job.replicas) {
               std::lock_guard<std::mutex> l(rep->gpu->mu);
-              const int rc = ck_pack_triples(rep->planes, t.row_idx.data(), t.col_idx.data(), t.n_alt_alleles.data(),
-                                             t.row_idx.size(), /*on_device=*/0);
+              const int rc = ck_pack_triples(rep->planes, t.row_idx, t.col_idx, t.n_alt_alleles, t.size, /*on_device=*/0);
               if (rc != CK_OK) {
                 st = FromCk(rc);
-                st.message += " in " + files[f];
-                break;
+                st.message += " (chunk starting at row " + std::to_string(first_row) + ") in " + files[f];
+                return st.message;
               }
             }
-            if (!st.ok()) break;
           }
-        }
+          return "";
+        };
+        size_t rows = 0;
+        if (std::string e = cuking::ReadTriples(files[f], kChunkRows, &t, consume, &rows); !e.empty() && st.ok())
+          st = (e.rfind("Error reading", 0) == 0) ? Unknown(e) : FailedPrecondition(e);
+        total_triples += rows;
         if (!st.ok()) {
           std::lock_guard<std::mutex> l(err_mu);
           if (first_error.ok()) first_error = st;

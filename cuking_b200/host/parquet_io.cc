@@ -11,6 +11,25 @@
 namespace cuking {
 namespace fs = std::filesystem;
 
+Triples::~Triples() { ck_host_free(block_); }
+
+std::string Triples::Reserve(size_t n) {
+  size = n;
+  if (n <= capacity_) return "";
+  ck_host_free(block_);
+  block_ = nullptr;
+  capacity_ = 0;
+  const size_t cap = std::max<size_t>(n, size_t(1) << 12);  // column starts stay 16-byte aligned
+  const size_t cap_pad = (cap + 1) & ~size_t(1);
+  if (ck_host_alloc(cap_pad * (8 + 8 + 4), &block_) != CK_OK) return std::string("Cannot allocate pinned host memory: ") + ck_last_error();
+  capacity_ = cap_pad;
+  char *base = static_cast<char *>(block_);
+  row_idx = reinterpret_cast<int64_t *>(base);
+  col_idx = reinterpret_cast<int64_t *>(base + cap_pad * 8);
+  n_alt_alleles = reinterpret_cast<int32_t *>(base + cap_pad * 16);
+  return "";
+}
+
 std::string ListParquetFiles(const std::string &dir, std::vector<std::string> *files) {
   std::error_code ec;
   if (!fs::is_directory(dir, ec)) return "Input is not a directory: " + dir;
@@ -27,66 +46,80 @@ std::string ListParquetFiles(const std::string &dir, std::vector<std::string> *f
 
 namespace {
 
+// Reads exactly `want` values (fewer only at the end of the column chunk) from one typed column reader.
 template <typename ReaderT, typename T>
-std::string ReadColumn(parquet::ColumnReader *column, parquet::Type::type want, const std::string &path, T *dst,
-                       size_t capacity, size_t *offset, std::vector<int16_t> *def_scratch) {
-  if (column->type() != want)  // cuking.cu:608-612, :630-634, :652-656
-    return "Expected " + parquet::TypeToString(want) + " type, found " + parquet::TypeToString(column->type()) + " in " + path;
-  if (column->descr()->max_repetition_level() > 0) return "Repeated column in " + path;
-  const bool optional = column->descr()->max_definition_level() > 0;
-  auto *reader = static_cast<ReaderT *>(column);
-  while (reader->HasNext()) {
-    const int64_t room = int64_t(capacity - *offset);
-    if (room <= 0) return "More values than rows in " + path;
+std::string ReadValues(ReaderT *reader, bool optional, const std::string &path, T *dst, size_t want, size_t *got,
+                       std::vector<int16_t> *def_scratch) {
+  *got = 0;
+  while (*got < want && reader->HasNext()) {
+    const int64_t room = int64_t(want - *got);
     int64_t values_read = 0, levels_read = 0;
     if (optional) {
       // Spark writes these columns OPTIONAL; the reference passes null def-levels because there are no nulls
       // (cuking.cu:617-623).  Read the levels and insist on that.
-      const int64_t batch = std::min<int64_t>(room, 1 << 20);
-      def_scratch->resize(size_t(batch));
-      levels_read = reader->ReadBatch(batch, def_scratch->data(), nullptr, dst + *offset, &values_read);
+      def_scratch->resize(size_t(room));
+      levels_read = reader->ReadBatch(room, def_scratch->data(), nullptr, dst + *got, &values_read);
       if (values_read != levels_read) return "Null values in " + path;
     } else {
-      levels_read = reader->ReadBatch(room, nullptr, nullptr, dst + *offset, &values_read);
+      levels_read = reader->ReadBatch(room, nullptr, nullptr, dst + *got, &values_read);
     }
     if (values_read == 0 && levels_read == 0) break;
-    *offset += size_t(values_read);
+    *got += size_t(values_read);
   }
+  return "";
+}
+
+std::string CheckColumn(parquet::ColumnReader *column, parquet::Type::type want, const std::string &path) {
+  if (column->type() != want)  // cuking.cu:608-612, :630-634, :652-656
+    return "Expected " + parquet::TypeToString(want) + " type, found " + parquet::TypeToString(column->type()) + " in " + path;
+  if (column->descr()->max_repetition_level() > 0) return "Repeated column in " + path;
   return "";
 }
 
 }  // namespace
 
-std::string ReadTriples(const std::string &path, Triples *out) {
+std::string ReadTriples(const std::string &path, size_t chunk_rows, Triples *buf,
+                        const std::function<std::string(size_t)> &consume, size_t *rows_out) {
+  size_t delivered = 0;
   try {
     std::unique_ptr<parquet::ParquetFileReader> reader = parquet::ParquetFileReader::OpenFile(path, /*memory_map=*/false);
     const auto md = reader->metadata();
     constexpr int kNumColumns = 3;
     if (md->num_columns() != kNumColumns)  // cuking.cu:585-590
       return "Expected 3 columns, found " + std::to_string(md->num_columns()) + " in " + path;
-    const size_t num_rows = size_t(md->num_rows());
-    out->row_idx.resize(num_rows);
-    out->col_idx.resize(num_rows);
-    out->n_alt_alleles.resize(num_rows);
-    size_t o0 = 0, o1 = 0, o2 = 0;
+    if (std::string e = buf->Reserve(chunk_rows); !e.empty()) return e;
     std::vector<int16_t> def_scratch;
     for (int rg = 0; rg < md->num_row_groups(); ++rg) {
       auto group = reader->RowGroup(rg);
+      auto c0 = group->Column(0), c1 = group->Column(1), c2 = group->Column(2);
       std::string err;
-      auto c0 = group->Column(0);
-      err = ReadColumn<parquet::Int64Reader>(c0.get(), parquet::Type::INT64, path, out->row_idx.data(), num_rows, &o0, &def_scratch);
-      if (!err.empty()) return err;
-      auto c1 = group->Column(1);
-      err = ReadColumn<parquet::Int64Reader>(c1.get(), parquet::Type::INT64, path, out->col_idx.data(), num_rows, &o1, &def_scratch);
-      if (!err.empty()) return err;
-      auto c2 = group->Column(2);
-      err = ReadColumn<parquet::Int32Reader>(c2.get(), parquet::Type::INT32, path, out->n_alt_alleles.data(), num_rows, &o2, &def_scratch);
-      if (!err.empty()) return err;
+      if (!(err = CheckColumn(c0.get(), parquet::Type::INT64, path)).empty()) return err;
+      if (!(err = CheckColumn(c1.get(), parquet::Type::INT64, path)).empty()) return err;
+      if (!(err = CheckColumn(c2.get(), parquet::Type::INT32, path)).empty()) return err;
+      auto *r0 = static_cast<parquet::Int64Reader *>(c0.get());
+      auto *r1 = static_cast<parquet::Int64Reader *>(c1.get());
+      auto *r2 = static_cast<parquet::Int32Reader *>(c2.get());
+      const bool o0 = c0->descr()->max_definition_level() > 0, o1 = c1->descr()->max_definition_level() > 0,
+                 o2 = c2->descr()->max_definition_level() > 0;
+      size_t remaining = size_t(md->RowGroup(rg)->num_rows());
+      while (remaining > 0) {
+        const size_t want = std::min(chunk_rows, remaining);
+        size_t g0 = 0, g1 = 0, g2 = 0;
+        if (!(err = ReadValues(r0, o0, path, buf->row_idx, want, &g0, &def_scratch)).empty()) return err;
+        if (!(err = ReadValues(r1, o1, path, buf->col_idx, want, &g1, &def_scratch)).empty()) return err;
+        if (!(err = ReadValues(r2, o2, path, buf->n_alt_alleles, want, &g2, &def_scratch)).empty()) return err;
+        if (g0 != want || g1 != want || g2 != want) return "Column lengths differ from the row count in " + path;
+        buf->size = want;
+        if (!(err = consume(delivered)).empty()) return err;
+        delivered += want;
+        remaining -= want;
+      }
     }
-    if (o0 != num_rows || o1 != num_rows || o2 != num_rows) return "Column lengths differ from the row count in " + path;
+    if (delivered != size_t(md->num_rows())) return "Column lengths differ from the row count in " + path;
   } catch (const std::exception &e) {  // parquet::ParquetException, cuking.cu:580-583
     return "Error reading " + path + ": " + e.what();
   }
+  if (rows_out) *rows_out = delivered;
   return "";
 }
 

@@ -3,6 +3,7 @@
 //   output: /root/reference/cuking.cu:770-862 (schema, Snappy, one row group), file name :868-870
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -10,9 +11,23 @@
 
 namespace cuking {
 
-struct Triples {
-  std::vector<int64_t> row_idx, col_idx;
-  std::vector<int32_t> n_alt_alleles;
+// Decoded columns of one file.  The arrays live in page-locked host memory (ck_host_alloc) that grows geometrically
+// and is reused from file to file by the owning reader thread, so the GPU pack kernel can read them in place.
+class Triples {
+ public:
+  Triples() = default;
+  Triples(const Triples &) = delete;
+  Triples &operator=(const Triples &) = delete;
+  ~Triples();
+  // Makes room for n rows (contents are not preserved).  Returns "" or an error message.
+  std::string Reserve(size_t n);
+  int64_t *row_idx = nullptr, *col_idx = nullptr;
+  int32_t *n_alt_alleles = nullptr;
+  size_t size = 0;
+
+ private:
+  void *block_ = nullptr;
+  size_t capacity_ = 0;
 };
 
 // Non-recursive listing of <dir>/*.parquet, sorted; everything else is skipped (cuking.cu:530-540).
@@ -20,8 +35,12 @@ std::string ListParquetFiles(const std::string &dir, std::vector<std::string> *f
 
 // Decodes one file: exactly 3 columns INT64, INT64, INT32 in that order (cuking.cu:585-590, :608, :630, :652), any
 // number of row groups, any codec Arrow was built with.  OPTIONAL columns are accepted as long as they hold no nulls.
-// Returns "" or an error message.
-std::string ReadTriples(const std::string &path, Triples *out);
+// The file is streamed in chunks of at most `chunk_rows` rows through `buf` (page-locked, reused): after each chunk
+// `consume(first_row_of_chunk)` is called with buf->size rows valid; a non-empty return value aborts the read.
+// (The reference decodes the whole file into three vectors first, cuking.cu:596-672; the rows are the same.)
+// Returns "" or an error message; *rows_out = rows delivered.
+std::string ReadTriples(const std::string &path, size_t chunk_rows, Triples *buf,
+                        const std::function<std::string(size_t)> &consume, size_t *rows_out);
 
 // Writes <dir>/part-<%05d shard>.snappy.parquet with the reference schema (all REQUIRED): i, j BYTE_ARRAY/String,
 // kin FLOAT, ibs0, ibs1, ibs2 INT32; Snappy; one row group.  Returns "" or an error; *bytes_written = file size.

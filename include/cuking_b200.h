@@ -136,9 +136,16 @@ int ck_planes_device_bytes(const ck_planes *planes, uint64_t *bytes);
  * duplicate or conflicting triples combine exactly as in the reference and order never matters).  row_idx and
  * col_idx are truncated to 32 bits like cuking.cu:676,:680.  Any other n_alt_alleles value fails the call with
  * CK_ERR_INVALID_GENOTYPE (cuking.cu:698-701); row_idx >= num_sites fails with CK_ERR_OUT_OF_RANGE.
- * The three arrays are host pointers (on_device == 0; staged through pinned memory) or device pointers. */
+ * The three arrays are host pointers (on_device == 0) or device pointers.  Pageable host arrays are staged through
+ * pinned memory chunk by chunk; page-locked host arrays (ck_host_alloc) are read by the kernel in place. */
 int ck_pack_triples(ck_planes *planes, const int64_t *row_idx, const int64_t *col_idx, const int32_t *n_alt_alleles,
                     size_t num_triples, int on_device);
+
+/* Page-locked host memory for triple buffers.  ck_pack_triples recognises it (and any other cudaHostAlloc /
+ * cudaHostRegister memory) and lets the pack kernel stream the triples straight over PCIe, skipping the staging copy;
+ * decode threads should read their Parquet columns directly into buffers from here. */
+int ck_host_alloc(size_t bytes, void **out);
+int ck_host_free(void *ptr);
 
 /* Exchange with the reference bit-set layout (cuking.cu:204-212, :507-523): sample-major uint64 words, slot o at
  * [o*W, (o+1)*W), het plane first, hom-alt plane second, W = ck_words_per_sample(num_sites); site r is bit r&63 of

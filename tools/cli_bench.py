@@ -1,0 +1,58 @@
+#!/usr/bin/env python3
+"""End-to-end timing of bin/cuking through real Parquet files (decode -> pack -> pairwise -> write).
+
+  python tools/cli_bench.py [--samples 2000] [--sites 100000] [--files 32] [--threads 16]
+
+Writes a synthetic cohort (SURVEY.md §8d generator) as zstd Parquet part files in Hail's layout, runs the binary, checks
+the output row count against the library called directly, and prints one JSON line with the phase times the binary logs.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+import cuking_b200 as ck  # noqa: E402
+from cuking_b200 import io as ckio  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--samples", type=int, default=2000)
+ap.add_argument("--sites", type=int, default=100_000)
+ap.add_argument("--files", type=int, default=32)
+ap.add_argument("--threads", type=int, default=16)
+ap.add_argument("--threshold", type=float, default=0.0884)
+args = ap.parse_args()
+
+with tempfile.TemporaryDirectory() as tmp:
+    t0 = time.perf_counter()
+    g = ck.synth_genotypes_host(42, 0.01, 0, args.samples, 0, args.sites)
+    info = ckio.write_input_dir(os.path.join(tmp, "in"), g, num_files=args.files)
+    gen_s = time.perf_counter() - t0
+    in_bytes = sum(os.path.getsize(os.path.join(tmp, "in", f)) for f in os.listdir(os.path.join(tmp, "in"))
+                   if f.endswith(".parquet"))
+    t0 = time.perf_counter()
+    p = subprocess.run([os.path.join(ROOT, "bin", "cuking"), f"--input_uri={tmp}/in", f"--output_uri={tmp}/out",
+                        f"--kin_threshold={args.threshold}", f"--num_reader_threads={args.threads}"],
+                       capture_output=True, text=True)
+    wall = time.perf_counter() - t0
+    if p.returncode != 0:
+        sys.exit(p.stderr)
+    phases = dict(re.findall(r"^(Reading metadata|Initializing CUDA|Allocating memory for bit set|Listing input files|Processing Parquet tables|"
+                             r"Running KING CUDA kernel[^.]*|Processing \d+ results)\.\.\..*\(([^;)]+)", p.stdout, re.M))
+    rows = ckio.read_output_dir(os.path.join(tmp, "out")).num_rows
+    with ck.Context(0) as ctx, ctx.planes(ck.submatrix(args.samples), args.sites) as pl:
+        pl.synthesize(42, 0.01)
+        want = len(pl.king(args.threshold, 10 << 20))
+    assert rows == want, (rows, want)
+    print(json.dumps({"tool": "cli_bench", "samples": args.samples, "sites": args.sites, "triples": info["num_triples"],
+                      "parquet_bytes": in_bytes, "files": args.files, "reader_threads": args.threads,
+                      "generate_input_s": round(gen_s, 2), "cuking_wall_s": round(wall, 3), "phases": phases,
+                      "triples_per_s_end_to_end": info["num_triples"] / wall, "retained_pairs": rows}))
