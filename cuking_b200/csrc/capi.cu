@@ -148,9 +148,15 @@ int king_variant_from_env() {
 using namespace ck;
 
 // default pairwise kernel variant: 0 = 5 POPC per pair-word, 1 = carry-save (2.5 POPC + 5 more LOP3),
-// 2 = tcgen05 int8 tensor-core formulation
-static int g_default_variant = 2;
+// 2 = tcgen05 int8 tensor-core formulation, 3 = tcgen05 mxf4 (E2M1, fp32 accumulation) formulation
+static int g_default_variant = 3;
 static int active_variant(const ck_ctx *ctx) { return ctx->king_variant >= 0 ? ctx->king_variant : g_default_variant; }
+// The variant that actually runs on these planes: the fp32 accumulators of the mxf4 kernel are exact only up to the
+// site count the probe verified (kFp4MaxSites); longer genotype vectors take the int8 kernel (s32 accumulators).
+static int planes_variant(const ck_planes *pl) {
+  const int v = active_variant(pl->ctx);
+  return (v == 3 && pl->num_sites > kFp4MaxSites) ? 2 : v;
+}
 
 extern "C" {
 
@@ -220,7 +226,7 @@ int ck_ctx_set_stream(ck_ctx *ctx, void *cuda_stream) {
 
 int ck_ctx_set_king_variant(ck_ctx *ctx, int variant) {
   if (!ctx) return fail(CK_ERR_INVALID_ARGUMENT, "ctx is NULL");
-  if (variant < -1 || variant > 2) return fail(CK_ERR_INVALID_ARGUMENT, "unknown pairwise kernel variant");
+  if (variant < -1 || variant > 3) return fail(CK_ERR_INVALID_ARGUMENT, "unknown pairwise kernel variant");
   ctx->king_variant = variant;
   return CK_OK;
 }
@@ -327,11 +333,12 @@ int ck_planes_device_bytes(const ck_planes *pl, uint64_t *bytes) {
 }
 
 // Derives what the active pairwise kernel reads from the raw planes: the H/D/A compute planes (variants 0, 1) or the
-// nibble-coded genotypes (variant 2, allocated on first use).
+// nibble-coded genotypes (variants 2 and 3 — different nibble values —, allocated on first use).
 static int ensure_compute(ck_planes *pl) {
   ck_ctx *ctx = pl->ctx;
-  const bool want_codes = active_variant(ctx) == 2;
-  if (want_codes ? !pl->codes_stale : !pl->compute_stale) return CK_OK;
+  const int variant = planes_variant(pl);
+  const bool want_codes = variant >= 2;
+  if (want_codes ? (!pl->codes_stale && pl->codes_kind == variant) : !pl->compute_stale) return CK_OK;
   if (want_codes && pl->codes == nullptr) {
     pl->codes_bytes = std::max<size_t>(pl->codes_words(), 1) * 4;
     CK_CUDA(ctx_alloc(ctx, reinterpret_cast<void **>(&pl->codes), pl->codes_bytes));
@@ -341,11 +348,12 @@ static int ensure_compute(ck_planes *pl) {
     CK_CUDA(ctx_alloc(ctx, reinterpret_cast<void **>(&pl->compute), pl->compute_bytes));
   }
   CK_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  if (pl->raw_words()) CK_CUDA(want_codes ? launch_finalize_codes(*pl, ctx->stream) : launch_finalize(*pl, ctx->stream));
+  if (pl->raw_words()) CK_CUDA(want_codes ? launch_finalize_codes(*pl, variant, ctx->stream) : launch_finalize(*pl, ctx->stream));
   CK_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   CK_CUDA(cudaEventSynchronize(ctx->ev[1]));
   ctx->timings.finalize_ms = elapsed(ctx->ev[0], ctx->ev[1]);
   (want_codes ? pl->codes_stale : pl->compute_stale) = false;
+  if (want_codes) pl->codes_kind = variant;
   return CK_OK;
 }
 
@@ -578,12 +586,15 @@ static int sort_results(ck_ctx *ctx, const ck_result *in, uint32_t n, ck_result 
 }
 
 static uint64_t variant_num_tiles(const ck_planes *pl, const KingLaunch &k) {
-  if (active_variant(pl->ctx) == 2) return king_umma_num_tiles(k);
+  const int variant = planes_variant(pl);
+  if (variant == 3) return king_fp4_num_tiles(k);
+  if (variant == 2) return king_umma_num_tiles(k);
   return king_num_tiles(k.num_row_blocks, k.num_col_blocks, k.triangular != 0);
 }
 
 static cudaError_t dispatch_king(const ck_planes *pl, const KingLaunch &k, cudaStream_t s, uint32_t *launches) {
-  const int variant = active_variant(pl->ctx);
+  const int variant = planes_variant(pl);
+  if (variant == 3) return launch_king_fp4(k, pl->map.num_blocks, pl->ctx, s, launches);
   if (variant == 2) return launch_king_umma(k, pl->map.num_blocks, pl->ctx, s, launches);
   return launch_king(k, variant, s, launches);
 }

@@ -81,6 +81,7 @@ struct ck_planes {
   uint32_t *codes = nullptr;   // [num_blocks][words][64][4]   (tcgen05 kernel; allocated on first use)
   bool compute_stale = true;   // raw changed since the last finalize into `compute`
   bool codes_stale = true;     // raw changed since the last finalize into `codes`
+  int codes_kind = 0;          // which kernel variant `codes` was last derived for (2: int8 selectors, 3: E2M1 nibbles)
   size_t raw_words() const { return size_t(map.num_blocks) * words * ck::kRawPlanes * ck::kTileSamples; }
   size_t compute_words() const { return size_t(map.num_blocks) * words * ck::kComputePlanes * ck::kTileSamples; }
   size_t codes_words() const { return size_t(map.num_blocks) * words * ck::kTileSamples * 4; }
@@ -94,7 +95,7 @@ cudaError_t launch_fill_missing(uint32_t *raw, size_t num_words, cudaStream_t s)
 cudaError_t launch_pack(const ck_planes &pl, const int64_t *row, const int64_t *col, const int32_t *alt, size_t n,
                         size_t index_base, uint32_t *d_err, cudaStream_t s);
 cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s);
-cudaError_t launch_finalize_codes(const ck_planes &pl, cudaStream_t s);
+cudaError_t launch_finalize_codes(const ck_planes &pl, int kind, cudaStream_t s);
 cudaError_t launch_import_ref(const ck_planes &pl, const uint64_t *d_bit_set, cudaStream_t s);
 cudaError_t launch_export_ref(const ck_planes &pl, uint64_t *d_bit_set, cudaStream_t s);
 cudaError_t launch_synth_planes(const ck_planes &pl, uint64_t seed, uint32_t miss_thr, cudaStream_t s);
@@ -129,5 +130,10 @@ cudaError_t launch_king(const KingLaunch &k, int variant, cudaStream_t s, uint32
 // ---- king_umma_kernel.cu (variant 2: tcgen05 int8 tensor-core formulation, 128 x 96 tiles) ----
 uint64_t king_umma_num_tiles(const KingLaunch &k);
 cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches);
+
+// ---- king_fp4_kernel.cu (variant 3: tcgen05 kind::mxf4 formulation, 128 x 80 tiles, band-ordered tile enumeration) ----
+uint64_t king_fp4_num_tiles(const KingLaunch &k);
+cudaError_t launch_king_fp4(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches);
+constexpr uint32_t kFp4MaxSites = 1u << 21;  // exactness of the tensor core's fp32 accumulation was measured up to this count
 
 }  // namespace ck

@@ -101,6 +101,9 @@ __device__ __forceinline__ uint32_t spread8(uint32_t b) {
   b = (b | (b << 3)) & 0x11111111u;
   return b;
 }
+// kFp4 = false: bit 0 het, bit 1 hom-alt, bit 2 hom-ref (PRMT selectors of the int8 kernel);
+// kFp4 = true:  the nibble IS the E2M1 operand superposition of the mxf4 kernel: 1 het (0.5), 2 hom-alt (+1), 0xA hom-ref (-1)
+template <bool kFp4>
 __global__ void __launch_bounds__(256) finalize_codes_kernel(const uint32_t *__restrict__ raw, uint4 *__restrict__ codes,
                                                              size_t num_rows /* blocks * words */) {
   const size_t total = num_rows * kTileSamples;
@@ -113,7 +116,8 @@ __global__ void __launch_bounds__(256) finalize_codes_kernel(const uint32_t *__r
     uint32_t z[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t)
-      z[t] = spread8(H >> (8 * t)) | (spread8(A >> (8 * t)) << 1) | (spread8(R >> (8 * t)) << 2);
+      z[t] = kFp4 ? spread8(H >> (8 * t)) | (spread8((A | R) >> (8 * t)) << 1) | (spread8(R >> (8 * t)) << 3)
+                  : spread8(H >> (8 * t)) | (spread8(A >> (8 * t)) << 1) | (spread8(R >> (8 * t)) << 2);
     codes[i] = make_uint4(z[0], z[1], z[2], z[3]);
   }
 }
@@ -281,9 +285,12 @@ cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_finalize_codes(const ck_planes &pl, cudaStream_t s) {
+cudaError_t launch_finalize_codes(const ck_planes &pl, int kind, cudaStream_t s) {
   const size_t rows = size_t(pl.map.num_blocks) * pl.words;
-  finalize_codes_kernel<<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(pl.raw, reinterpret_cast<uint4 *>(pl.codes), rows);
+  if (kind == 3)
+    finalize_codes_kernel<true><<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(pl.raw, reinterpret_cast<uint4 *>(pl.codes), rows);
+  else
+    finalize_codes_kernel<false><<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(pl.raw, reinterpret_cast<uint4 *>(pl.codes), rows);
   return cudaGetLastError();
 }
 

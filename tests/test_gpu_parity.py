@@ -113,7 +113,7 @@ def load_kats():
         return json.load(f)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("kat", load_kats(), ids=lambda k: k["id"])
 def test_known_answer_vectors_on_gpu(ctx, kat, variant):
     ctx.set_king_variant(variant)
@@ -143,7 +143,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("n,s,k,shard,thr", CASES)
 def test_king_matches_oracle(ctx, n, s, k, shard, thr, variant):
     ctx.set_king_variant(variant)
@@ -201,7 +201,7 @@ def test_overflow_reports_resource_exhausted(ctx):
         assert len(pl.king(-1.0, count)) == count           # exactly enough room works
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_tile_slices_union_equals_full(ctx, variant):
     # the multi-GPU partition: contiguous slices of the tile grid, no exchange between slices
     rng = np.random.default_rng(23)
@@ -283,7 +283,7 @@ def test_three_way_reference_kernel_oracle_product(ctx, n, s, k, shard, thr):
     ref, ref_count, ref_ovf, _ = ref_kernel.king(bs, n, k, shard, ko.words_per_sample(s), thr, cap)
     assert ref_count == count and not ref_ovf
     assert_results_equal(ref, want)           # oracle == the reference's own kernel
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         ctx.set_king_variant(variant)
         with ctx.planes(sm, s) as pl:
             pl.import_bitset(bs)

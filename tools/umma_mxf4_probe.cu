@@ -1,0 +1,312 @@
+// Probe: tcgen05.mma.kind::mxf4.block_scale (E2M1 operands, UE8M0 block-32 scales, fp32 accumulation) as an EXACT
+// integer engine for the pairwise KING counters, at twice the MAC rate of kind::i8 (K = 64 per instruction).
+// Questions answered on the GPU (nothing here is taken from documentation we cannot read offline):
+//   1. descriptor / scale-factor plumbing: SS mode (both operands in shared memory) against a CPU dot product;
+//   2. the TMEM layout of a 4-bit A operand (TS mode), tried under several hypotheses;
+//   3. exactness of the fp32 accumulation for counts up to 2^21 (operands in {-1, 0, +1}, scales 2^0): every partial
+//      sum is an integer below 2^24, so an IEEE fp32 accumulator is exact — is the tensor core's?
+//   4. the sustained rate with the KING issue pattern: three issuers, N = 80 / 160 / 160, A from TMEM.
+// All scale factors are the constant 1.0 (0x7F), so the scale-factor TMEM layout does not matter: the whole region is
+// filled with 0x7F7F7F7F.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/umma_mxf4_probe tools/umma_mxf4_probe.cu
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); exit(1);} } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return uint64_t((smem_addr >> 4) & 0x3fff) | (uint64_t((lbo_bytes >> 4) & 0x3fff) << 16) |
+         (uint64_t((sbo_bytes >> 4) & 0x3fff) << 32) | (uint64_t(1) << 46);
+}
+// block-scaled instruction descriptor: E2M1 x E2M1 (format code 1 for kind::mxf4), UE8M0 scales, K-major, dense K=64
+__host__ __device__ constexpr uint32_t make_idesc_mxf4(uint32_t M, uint32_t N) {
+  return (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_mxf4_ss(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t sfa, uint32_t sfb, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+      : "memory");
+}
+__device__ __forceinline__ void umma_mxf4_ts(uint32_t d, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t sfa, uint32_t sfb, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], [%1], %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t canon_off(uint32_t row, uint32_t kbyte, uint32_t lbo, uint32_t sbo) {
+  return (row >> 3) * sbo + (kbyte >> 4) * lbo + (row & 7) * 16 + (kbyte & 15);
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+
+constexpr uint32_t kSfCol = 480;  // columns [480, 512): scale factors, all 1.0
+constexpr uint32_t kACol = 416;   // columns [416, 480): A operand (up to 64 columns)
+
+// A/B: packed E2M1 nibbles, row-major [rows][kbytes], element k of a row = nibble (k & 1) of byte k >> 1.
+// a_mode: 0 = A in shared memory (SS); 1 = A in TMEM packed (8 elements per 32-bit column);
+//         2 = A in TMEM, one element per byte (low nibble); 3 = A in TMEM, one element per byte (high nibble)
+template <int N>
+__global__ void __launch_bounds__(128) probe_kernel(const uint8_t *A, const uint8_t *B, float *D, int kbytes, int reps, int a_mode,
+                                                    unsigned long long *cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_smem;
+  constexpr int M = 128;
+  const uint32_t LBO = 128, SBO = (kbytes / 16) * 128;
+  uint8_t *sB = smem, *sA = smem + N * kbytes;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (uint32_t e = tid; e < uint32_t(N * kbytes); e += blockDim.x) sB[canon_off(e / kbytes, e % kbytes, LBO, SBO)] = B[e];
+  if (a_mode == 0)
+    for (uint32_t e = tid; e < uint32_t(M * kbytes); e += blockDim.x) sA[canon_off(e / kbytes, e % kbytes, LBO, SBO)] = A[e];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t lane_base = tmem_base + (uint32_t(warp * 32) << 16);
+  for (uint32_t c = 0; c < 32; ++c) tmem_st1(lane_base + kSfCol + c, 0x7f7f7f7fu);
+  uint32_t a_cols_per_mma = 8;
+  if (a_mode == 1) {
+    for (uint32_t c = 0; c < uint32_t(kbytes) / 4; ++c) {
+      uint32_t w = 0;
+      for (int b = 0; b < 4; ++b) w |= uint32_t(A[tid * kbytes + c * 4 + b]) << (8 * b);
+      tmem_st1(lane_base + kACol + c, w);
+    }
+  } else if (a_mode >= 2) {
+    a_cols_per_mma = 16;
+    for (uint32_t c = 0; c < uint32_t(kbytes) / 2; ++c) {  // 4 elements per column
+      uint32_t w = 0;
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t k = c * 4 + e;
+        const uint32_t nib = (A[tid * kbytes + (k >> 1)] >> (4 * (k & 1))) & 0xf;
+        w |= (a_mode == 2 ? nib : nib << 4) << (8 * e);
+      }
+      tmem_st1(lane_base + kACol + c, w);
+    }
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  unsigned long long t0 = clock64();
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_mxf4(M, N);
+    for (int rep = 0; rep < reps; ++rep)
+      for (uint32_t ks = 0; ks < uint32_t(kbytes) / 32; ++ks) {
+        const uint64_t db = make_smem_desc(smem_u32(sB) + ks * 2 * LBO, LBO, SBO);
+        const uint32_t acc = (rep > 0 || ks > 0) ? 1u : 0u;
+        if (a_mode == 0)
+          umma_mxf4_ss(tmem_base, make_smem_desc(smem_u32(sA) + ks * 2 * LBO, LBO, SBO), db, idesc, tmem_base + kSfCol, tmem_base + kSfCol + 16, acc);
+        else
+          umma_mxf4_ts(tmem_base, tmem_base + kACol + ks * a_cols_per_mma, db, idesc, tmem_base + kSfCol, tmem_base + kSfCol + 16, acc);
+      }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  unsigned long long t1 = clock64();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid == 0 && cycles) cycles[blockIdx.x] = t1 - t0;
+  for (int n0 = 0; n0 < N; n0 += 8) {
+    uint32_t v[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(lane_base + n0));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (blockIdx.x == 0)
+      for (int q = 0; q < 8; ++q) D[tid * N + n0 + q] = __uint_as_float(v[q]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+}
+
+static int e2m1_value(uint32_t nib) {  // only the codes the probe uses
+  return nib == 0x2 ? 1 : nib == 0xA ? -1 : 0;
+}
+
+// fill: 0 = random {-1,0,+1}; 1 = all +1 (largest possible count); 2 = random {0,+1} (monotone partial sums)
+template <int N>
+static int run(int kbytes, int reps, int a_mode, int fill, const char *label) {
+  constexpr int M = 128;
+  std::vector<uint8_t> hA(size_t(M) * kbytes), hB(size_t(N) * kbytes);
+  uint32_t s = 4242u + N + fill;
+  auto nib = [&]() -> uint8_t {
+    s = s * 1664525u + 1013904223u;
+    const uint32_t r = (s >> 24) % 3;
+    if (fill == 1) return 0x2;
+    if (fill == 2) return r ? 0x2 : 0x0;
+    return r == 0 ? 0x0 : r == 1 ? 0x2 : 0xA;
+  };
+  for (auto &x : hA) { uint8_t lo = nib(), hi = nib(); x = uint8_t(lo | (hi << 4)); }
+  for (auto &x : hB) { uint8_t lo = nib(), hi = nib(); x = uint8_t(lo | (hi << 4)); }
+  uint8_t *dA, *dB; float *dD; unsigned long long *dC;
+  CK(cudaMalloc(&dA, hA.size())); CK(cudaMalloc(&dB, hB.size())); CK(cudaMalloc(&dD, M * N * 4)); CK(cudaMalloc(&dC, 8 * 1024));
+  CK(cudaMemcpy(dA, hA.data(), hA.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size(), cudaMemcpyHostToDevice));
+  const size_t smem = size_t(M + N) * kbytes;
+  CK(cudaFuncSetAttribute(probe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  probe_kernel<N><<<1, 128, smem>>>(dA, dB, dD, kbytes, reps, a_mode, dC);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  std::vector<float> hD(M * N);
+  CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+  unsigned long long cyc; CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  long long max_abs = 0;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      long long ref = 0;
+      for (int k = 0; k < 2 * kbytes; ++k)
+        ref += e2m1_value((hA[size_t(m) * kbytes + (k >> 1)] >> (4 * (k & 1))) & 0xf) * e2m1_value((hB[size_t(n) * kbytes + (k >> 1)] >> (4 * (k & 1))) & 0xf);
+      ref *= reps;
+      if (llabs(ref) > max_abs) max_abs = llabs(ref);
+      if (double(ref) != double(hD[m * N + n]) && bad++ < 4)
+        printf("  %s mismatch (m=%d,n=%d): got %.1f want %lld\n", label, m, n, hD[m * N + n], ref);
+    }
+  printf("{\"probe\": \"umma_mxf4\", \"test\": \"%s\", \"a_mode\": %d, \"fill\": %d, \"N\": %d, \"K\": %d, \"reps\": %d, \"total_sites\": %lld, \"max_abs_count\": %lld, \"mismatches\": %d, \"clk_per_mma\": %.1f}\n",
+         label, a_mode, fill, N, 2 * kbytes, reps, (long long)2 * kbytes * reps, max_abs, bad, double(cyc) / (double(reps) * kbytes / 32));
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dC);
+  return bad;
+}
+
+// ---- throughput with the KING pattern: issuers 0,1,2 (one lane of warps 0-2) each own an accumulator; issuer 0 uses
+// N = n0, the others N = n1; A from TMEM (packed) or shared memory, B from shared memory; per "step" each issuer issues
+// one MMA.  Reports clocks per step.
+__global__ void __launch_bounds__(128) rate_kernel(int n0, int n1, int issuers, int steps, int a_in_tmem, unsigned long long *cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_smem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t kbytes = 128, LBO = 128, SBO = (kbytes / 16) * 128;  // 4 K-steps of data, reused
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&bar, issuers);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (uint32_t e = tid; e < (256 + 128) * kbytes / 4; e += blockDim.x) reinterpret_cast<uint32_t *>(smem)[e] = 0x22222222u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t lane_base = tmem_base + (uint32_t(warp * 32) << 16);
+  for (uint32_t c = 0; c < 32; ++c) tmem_st1(lane_base + kSfCol + c, 0x7f7f7f7fu);
+  for (uint32_t c = 0; c < 64; ++c) tmem_st1(lane_base + kACol + c, 0x22222222u);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  unsigned long long t0 = clock64();
+  if ((tid & 31) == 0 && warp < issuers) {
+    const uint32_t n = warp == 0 ? n0 : n1;
+    const uint32_t idesc = make_idesc_mxf4(128, n);
+    const uint32_t d = tmem_base + (warp == 0 ? 0 : n0 + (warp - 1) * n1);
+    for (int st = 0; st < steps; ++st) {
+      const uint32_t ks = st & 3;
+      const uint64_t db = make_smem_desc(smem_u32(smem) + ks * 2 * LBO, LBO, SBO);
+      if (a_in_tmem)
+        umma_mxf4_ts(d, tmem_base + kACol + ks * 8 + warp * 8, db, idesc, tmem_base + kSfCol, tmem_base + kSfCol + 16, st > 0);
+      else
+        umma_mxf4_ss(d, make_smem_desc(smem_u32(smem) + 256 * kbytes + ks * 2 * LBO, LBO, SBO), db, idesc, tmem_base + kSfCol, tmem_base + kSfCol + 16, st > 0);
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  unsigned long long t1 = clock64();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid == 0 && cycles) cycles[blockIdx.x] = t1 - t0;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+}
+
+static void run_rate(int n0, int n1, int issuers, int a_in_tmem) {
+  unsigned long long *dC;
+  CK(cudaMalloc(&dC, 8 * 1024));
+  const size_t smem = (256 + 128) * 128;
+  CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int steps = 20000;
+  rate_kernel<<<148, 128, smem>>>(n0, n1, issuers, steps, a_in_tmem, dC);
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  rate_kernel<<<148, 128, smem>>>(n0, n1, issuers, steps, a_in_tmem, dC);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  CK(cudaGetLastError());
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  unsigned long long cyc; CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+  const double macs_per_step = 128.0 * 64 * (n0 + double(issuers - 1) * n1);
+  printf("{\"probe\": \"umma_mxf4_rate\", \"a_in_tmem\": %d, \"issuers\": %d, \"N0\": %d, \"N1\": %d, \"clk_per_step\": %.1f, \"macs_per_clk_per_sm\": %.1f, \"chip_tops\": %.1f, \"ms\": %.3f}\n",
+         a_in_tmem, issuers, n0, n1, double(cyc) / steps, macs_per_step * steps / double(cyc), 2.0 * macs_per_step * steps * 148 / (ms * 1e-3) / 1e12, ms);
+  cudaFree(dC);
+}
+
+int main(int argc, char **argv) {
+  int bad_ss = 0;
+  // 1. plumbing, SS mode (the layout CUTLASS uses): small K, random signs
+  bad_ss += run<80>(128, 1, 0, 0, "ss_small");
+  bad_ss += run<160>(128, 1, 0, 0, "ss_small");
+  // 2. A in TMEM under the three layout hypotheses
+  int bad_ts[4] = {0, 0, 0, 0};
+  for (int mode = 1; mode <= 3; ++mode) bad_ts[mode] = run<80>(64, 1, mode, 0, "ts_layout");
+  int ts_mode = 0;
+  for (int mode = 1; mode <= 3; ++mode) if (bad_ts[mode] == 0) { ts_mode = mode; break; }
+  printf("{\"probe\": \"umma_mxf4\", \"ts_layout_mode\": %d}\n", ts_mode);
+  // 3. exactness of long accumulations (total sites = K * reps)
+  const int amode = (bad_ss == 0) ? (ts_mode ? ts_mode : 0) : 0;
+  int bad_exact = 0;
+  for (int reps : {64, 1024, 8192, 16384}) {          // 2^13 ... 2^21 sites
+    bad_exact += run<160>(64, reps, amode, 1, "exact_all_ones");
+    bad_exact += run<160>(64, reps, amode, 2, "exact_random_01");
+    bad_exact += run<160>(64, reps, amode, 0, "exact_random_pm1");
+  }
+  // 4. sustained rate, KING issue pattern
+  run_rate(80, 160, 3, 1);
+  run_rate(80, 160, 3, 0);
+  run_rate(80, 160, 1, 1);
+  run_rate(256, 256, 1, 1);
+  run_rate(192, 192, 2, 1);
+  run_rate(208, 208, 2, 1);
+  run_rate(128, 128, 3, 1);
+  const bool ok = bad_ss == 0 && ts_mode != 0 && bad_exact == 0;
+  printf("{\"probe\": \"umma_mxf4\", \"ss_ok\": %s, \"ts_mode\": %d, \"exact\": %s}\n", bad_ss ? "false" : "true", ts_mode, bad_exact ? "false" : "true");
+  printf(ok ? "PROBE OK\n" : "PROBE FAILED\n");
+  return 0;
+}
