@@ -346,7 +346,8 @@ def main():
     # algorithmic HBM bytes per launch: each tile streams its row samples and its column samples once
     # (tcgen05 variant: 128 x 80 tiles of 4-bit genotype codes; LOP3+POPC variants: 64 x 64 tiles of 3 bit planes)
     words = -(-(-(-n_sites // 32)) // 16) * 16
-    umma = args.variant in (-1, 2)
+    variant = args.variant if args.variant >= 0 else (3 if n_sites <= (1 << 21) else 2)  # the library's own choice
+    umma = variant in (2, 3)
     tile_bytes = (128 + 80) * words * 16 if umma else 2 * 64 * words * 12
     popc_view = {
         "achieved": achieved / 1e9, "peak": peaks["popc_lane_ops_per_s"] / 1e9, "unit": "G POPC.32 lane-ops/s",
@@ -357,17 +358,35 @@ def main():
     }
     hbm_view = {"algorithmic_gbs": (t_end - t_begin) * tile_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "note": "tile operand streaming (each tile reads its row and column samples once); mostly L2 hits"}
-    if umma:
+    bf16 = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            bf16 = json.load(f)
+    except OSError:
+        pass
+    if variant == 3:
+        # 5 exact E2M1 MACs = 10 ops per pair-site (xx, yy, yh, hy, hh) on the FP4 tensor path (kind::mxf4, unit block
+        # scales, fp32 accumulation).  Peak = the dense FP4 rate measured on this pool's B200 by tools/umma_mxf4_probe.cu
+        # (15,595 MAC/clk/SM, 8481 TOP/s at the burst clock; nominal 9000) - MEASURED_PEAKS.json only holds bf16
+        # (FP4 is nominally 4x bf16: 4 x 1657 burst = 6626, 4 x 1390 sustained = 5562 TOP/s).
+        tops = my_units * 10.0 / (kernel_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "kernel": "king_fp4_kernel", "achieved": tops, "peak": 8481.0, "unit": "TOP/s (fp4 e2m1, dense)",
+            "frac": tops / 8481.0, "traffic": None, "kernel_ms": kernel_ms, "units_per_launch": my_units,
+            "algorithmic_per_unit": "10 fp4 ops (5 MACs: xx, yy, yh, hy, hh) per pair-site, fp32 accumulation (exact: counts < 2^21)",
+            "peak_source": "measured: tools/umma_mxf4_probe.cu on this pool's B200 (profiles/r01_mxf4_probe.txt), "
+                           "kind::mxf4 M=128 N=208, 15595 MAC/clk/SM = 8481 TOP/s at the burst clock (nominal dense fp4: 9000)",
+            "vs_4x_measured_bf16_burst": (tops / (4 * bf16["bf16_tflops"])) if bf16 else None,
+            "vs_4x_measured_bf16_sustained": (tops / (4 * bf16["bf16_tflops_sustained"])) if bf16 else None,
+            "int8_equivalent": {"peak": 4075.0, "frac": tops / 4075.0,
+                                "note": "the same 10 ops per pair-site against the measured int8 tensor peak (the round's first tensor kernel, variant 2)"},
+            "popc_equivalent": popc_view, "hbm": hbm_view,
+        }
+    elif umma:
         # 5 exact int8 MACs = 10 ops per pair-site (xx, yy, yh, hy, hh); peak = dense int8 tcgen05 rate measured on this
         # pool's B200 by tools/umma_i8_probe.cu (8190 MAC/clk/SM, 4075 TOP/s burst at N=256) - MEASURED_PEAKS.json only
         # holds bf16 (int8 is nominally 2x bf16: 2 x 1390 sustained = 2781, 2 x 1657 burst = 3313 TOP/s)
         tops = my_units * 10.0 / (kernel_ms * 1e-3) / 1e12
-        bf16 = None
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                bf16 = json.load(f)
-        except OSError:
-            pass
         roofline = {
             "bound": "tensor", "kernel": "king_umma_kernel", "achieved": tops, "peak": 4075.0, "unit": "TOP/s (int8, dense)",
             "frac": tops / 4075.0, "traffic": None, "kernel_ms": kernel_ms, "units_per_launch": my_units,
@@ -434,12 +453,13 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int8 indicator GEMMs with s32 accumulation (tcgen05), fp32 kinship" if args.variant in (-1, 2) else "u32 bit planes (LOP3+POPC), fp32 kinship", "data": "synthetic",
+            "dtype": {3: "fp4 (e2m1 indicators, exact fp32 accumulation)", 2: "int8 (indicators, s32 accumulation)"}.get(variant, "u32 (bit planes, LOP3+POPC)"),
+            "data": "synthetic",
             "config": {
                 "workload": f"{args.workload}: {n_samples} samples x {n_sites} sites, missing {missing}, "
                             f"kin_threshold {thr}, max_results {max_results}"
                             + (f" (weak scaling: {n1}*sqrt({n_gpus}) samples, tile grid split over {n_gpus} GPUs)" if n_gpus > 1 else ""),
-                "tiles": tiles, "retained_pairs": retained, "kernel_variant": args.variant,
+                "tiles": tiles, "retained_pairs": retained, "kernel_variant": variant,
                 "l2": f"inputs larger than L2: {planes.device_bytes() * 3 // 5 >> 20} MiB of compute planes streamed per step",
                 "input_synthesis_s": round(synth_s, 3),
             },

@@ -617,6 +617,12 @@ static KingLaunch base_launch(const ck_planes *pl) {
   return k;
 }
 
+int ck_planes_king_variant(const ck_planes *pl, int *variant) {
+  if (!pl || !variant) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  *variant = planes_variant(pl);
+  return CK_OK;
+}
+
 int ck_king_num_tiles(const ck_planes *pl, uint64_t *num_tiles) {
   if (!pl || !num_tiles) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
   const KingLaunch k = base_launch(pl);

@@ -143,10 +143,8 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (uint32_t s = 0; s < kAStages; ++s) {
-      mbar_init(&full_a[s], kFAWarps / kFGroups);  // the four warps of the group that fills the stage
-      mbar_init(&empty_a[s], kFIssuers);
-    }
+    for (uint32_t s = 0; s < kFSlots; ++s) mbar_init(&full_a[s], kFAWarps / kFGroups);  // per slot: the four warps of the filling group
+    for (uint32_t s = 0; s < kAStages; ++s) mbar_init(&empty_a[s], kFIssuers);             // per stage: one commit per issuer
     for (uint32_t s = 0; s < NS; ++s) {
       mbar_init(&full_b[s], kFBWarps);
       mbar_init(&empty_b[s], kFIssuers);
@@ -218,16 +216,19 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
         __syncwarp();  // tcgen05.st is warp-collective; the polling loop may leave the lanes diverged
         const unsigned long long p2 = FPROF_T();
         tcgen05_after_sync();
+        // a slot is announced as soon as it is stored (the issuers start on it while the next one is written); the
+        // stage is released as a whole (one commit per issuer per stage: commits are the issuers' expensive instruction)
 #pragma unroll
         for (uint32_t a = 0; a < AS; ++a) {
-          tmem_store8(ta + (astage * AS + a) * 24, x[a]);
-          tmem_store8(ta + (astage * AS + a) * 24 + 8, y[a]);
-          tmem_store8(ta + (astage * AS + a) * 24 + 16, h[a]);
+          const uint32_t aslot = astage * AS + a;
+          tmem_store8(ta + aslot * 24, x[a]);
+          tmem_store8(ta + aslot * 24 + 8, y[a]);
+          tmem_store8(ta + aslot * 24 + 16, h[a]);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tcgen05_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_a[aslot]);
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tcgen05_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_a[astage]);
         const unsigned long long p3 = FPROF_T();
         FPROF_ADD(0, p1 - p0);
         FPROF_ADD(1, p2 - p1);
@@ -306,22 +307,27 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
       const uint32_t stage_no = step / AS, astage = stage_no % kAStages, mb = step / BS, sb = mb % NS, q = step % BS;
       const unsigned long long q0 = FPROF_T();
       if (q == 0) mbar_wait(&full_b[sb], (mb / NS) & 1u);
-      mbar_wait(&full_a[astage], (stage_no / kAStages) & 1u);
-      const unsigned long long q1 = FPROF_T();
-      FPROF_ADD(8 + which, q1 - q0);
-      tcgen05_after_sync();
-      if (elected) {
+      unsigned long long waited = FPROF_T() - q0;
 #pragma unroll
-        for (uint32_t a = 0; a < AS; ++a) {
+      for (uint32_t a = 0; a < AS; ++a) {
+        const uint32_t aslot = astage * AS + a;
+        const unsigned long long w0 = FPROF_T();
+        mbar_wait(&full_a[aslot], (stage_no / kAStages) & 1u);
+        waited += FPROF_T() - w0;
+        tcgen05_after_sync();
+        if (elected) {
           const uint32_t b_bytes = sb * G::kStageBytes + (q + a) * 2 * kFLBO;
-          umma_mxf4_ts(d_addr, a_addr + (astage * AS + a) * 24, b_desc0 + uint64_t(b_bytes >> 4), idesc, sf_addr,
-                       (step + a) > 0 ? 1u : 0u);
+          umma_mxf4_ts(d_addr, a_addr + aslot * 24, b_desc0 + uint64_t(b_bytes >> 4), idesc, sf_addr, (step + a) > 0 ? 1u : 0u);
         }
+      }
+      if (elected) {
         umma_commit_arrive(&empty_a[astage]);                       // arrives when this thread's MMAs so far have completed
         if (q + AS == BS) umma_commit_arrive(&empty_b[sb]);         // last steps of the B stage
       }
       __syncwarp();
-      if (which == 1) FPROF_ADD(11, FPROF_T() - q1);
+      const unsigned long long q1 = FPROF_T();
+      FPROF_ADD(8 + which, waited);
+      if (which == 1) FPROF_ADD(11, q1 - q0 - waited);
     }
     if (elected) umma_commit_arrive(&acc_bar);  // this issuer's accumulator is final
   }
@@ -337,28 +343,33 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     const uint32_t r = quad * 32 + lane;
     const uint32_t gi = i0 + r;
     const uint32_t lane_base = tmem_base + ((quad * 32u) << 16);
-    // Cheap conservative screen before the exact kinship: with every count below 2^21 the numerator and denominator of
-    // cuking.cu:289-294 are exact in fp32, so kin = fl(0.5 + fl(num / den)) differs from the real value by < 2^-22
-    // relative; a pair with num <= (thr - 0.5 - margin) * den cannot pass the strict threshold test and skips the IEEE
+    // Cheap conservative screen before the exact kinship, in fp32 on the raw accumulators (no conversions).  With
+    // every count below 2^21 all the quantities below are exact in fp32:
+    //     num = 2 both_het - 4 opp - het_i - het_j = 2 (D_xx - D_yy - D_hy - D_yh)          (cuking.cu:289-292)
+    //     den = 4 min(het_i, het_j)                = 8 (2 D_hh + min(D_hy, D_yh))           (cuking.cu:293)
+    // and kin = fl(0.5 + fl(num / den)) differs from the real value by < 2^-22 relative, so a pair with
+    // num <= (thr - 0.5 - margin) den cannot pass the strict threshold test and skips the conversions and the IEEE
     // division.  den == 0 implies num <= 0 (both_het <= min_hets), i.e. -inf / NaN, which the reference never emits.
-    const float screen = p.kin_threshold - 0.5f - (1e-3f + 1e-5f * fabsf(p.kin_threshold));
+    const float screen4 = 4.f * (p.kin_threshold - 0.5f - (1e-3f + 1e-5f * fabsf(p.kin_threshold)));
     const bool dump = p.dump_counts != nullptr;
     auto finish = [&](uint32_t c, uint32_t xx, uint32_t yy, uint32_t yh, uint32_t hy, uint32_t hh) {
       const uint32_t gj = j0 + c;
+      const float fxx = __uint_as_float(xx), fyy = __uint_as_float(yy), fyh = __uint_as_float(yh), fhy = __uint_as_float(hy),
+                  fhh = __uint_as_float(hh);
+      const float half_num = (fxx - fyy) - (fhy + fyh);
+      const float eighth_den = fmaf(2.f, fhh, fminf(fhy, fyh));
+      const bool in_tile = r < rows_here && c < cols_here;
+      const bool cand = in_tile && gi < gj && half_num > screen4 * eighth_den;
+      if (__ballot_sync(0xffffffffu, cand || dump) == 0) return;
       // the accumulators hold exact multiples of 1/4 (see the header): scale back to integer counts
-      const int32_t n_xx = __float2int_rn(__uint_as_float(xx));                  // conc - opp (signed)
-      const uint32_t n_yy = uint32_t(__float2int_rn(__uint_as_float(yy)));       // conc + opp
-      const uint32_t n_yh = uint32_t(__float2int_rn(2.f * __uint_as_float(yh)));   // i hom, j het
-      const uint32_t n_hy = uint32_t(__float2int_rn(2.f * __uint_as_float(hy)));   // i het, j hom
-      const uint32_t both_het = uint32_t(__float2int_rn(4.f * __uint_as_float(hh)));
+      const int32_t n_xx = __float2int_rn(fxx);                    // conc - opp (signed)
+      const uint32_t n_yy = uint32_t(__float2int_rn(fyy));         // conc + opp
+      const uint32_t n_yh = uint32_t(__float2int_rn(2.f * fyh));   // i hom, j het
+      const uint32_t n_hy = uint32_t(__float2int_rn(2.f * fhy));   // i het, j hom
+      const uint32_t both_het = uint32_t(__float2int_rn(4.f * fhh));
       const uint32_t het_i = both_het + n_hy;  // i het where j is defined
       const uint32_t het_j = both_het + n_yh;  // j het where i is defined
       const uint32_t opp = uint32_t(int32_t(n_yy) - n_xx) >> 1;
-      const bool in_tile = r < rows_here && c < cols_here;
-      const int32_t num = int32_t(2u * both_het) - int32_t(4u * opp) - int32_t(het_i) - int32_t(het_j);
-      const float den = float(4u * min(het_i, het_j));
-      const bool cand = in_tile && gi < gj && float(num) > screen * den;
-      if (__ballot_sync(0xffffffffu, cand || dump) == 0) return;
       const uint32_t shared = n_yy + n_yh + n_hy + both_het;
       const uint32_t conc = uint32_t(int32_t(n_yy) + n_xx) >> 1;
       const float kin = kinship(het_i, het_j, both_het, opp);

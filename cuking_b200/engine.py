@@ -190,6 +190,12 @@ class Planes:
         check(self._lib.ck_king_num_tiles(self._h, C.byref(t)))
         return int(t.value)
 
+    def king_variant(self) -> int:
+        """The pairwise kernel variant ck_king* runs on these planes (3 = FP4 tensor path, 2 = int8 beyond 2^21 sites)."""
+        v = C.c_int()
+        check(self._lib.ck_planes_king_variant(self._h, C.byref(v)))
+        return int(v.value)
+
     def king(self, kin_threshold: float, max_results: int = 10 << 20, sort: bool = True,
              tiles: tuple[int, int] | None = None, out=None):
         """ComputeKingKernel + overflow check + sort (cuking.cu:713-765).  Returns the retained KingResult records

@@ -107,8 +107,10 @@ int ck_ctx_create(int device, ck_ctx **out);
  * ctx-owned stream. */
 int ck_ctx_set_stream(ck_ctx *ctx, void *cuda_stream);
 /* Pairwise kernel variant: 0 = LOP3 + 5 POPC per pair and 32 sites, 1 = carry-save (2.5 POPC + 5 more LOP3),
- * 2 = tcgen05 int8 tensor-core formulation (five exact s32 GEMMs of indicator vectors), -1 = library default (= 2;
- * also settable with the CUKING_KING_VARIANT environment variable).  Results are bit-identical across variants. */
+ * 2 = tcgen05 int8 tensor-core formulation (five exact s32 GEMMs of indicator vectors), 3 = the same five GEMMs on
+ * the FP4 tensor path (kind::mxf4 E2M1 operands, unit block scales, fp32 accumulation - exact for counts < 2^21; planes
+ * with more than 2^21 sites are routed to variant 2), -1 = library default (= 3; also settable with the
+ * CUKING_KING_VARIANT environment variable).  Results are bit-identical across variants. */
 int ck_ctx_set_king_variant(ck_ctx *ctx, int variant);
 int ck_ctx_synchronize(ck_ctx *ctx);
 int ck_ctx_get_timings(ck_ctx *ctx, ck_timings *out);
@@ -168,6 +170,9 @@ int ck_planes_synthesize(ck_planes *planes, const ck_synth_params *params);
 int ck_king(ck_planes *planes, float kin_threshold, uint32_t max_results, ck_result *results, int results_on_device,
             uint32_t *num_results, int sort);
 
+/* The pairwise kernel variant that ck_king* will run on these planes (the ctx's variant, except that variant 3 falls
+ * back to 2 beyond 2^21 sites). */
+int ck_planes_king_variant(const ck_planes *pl, int *variant);
 /* Same, restricted to the linear range [tile_begin, tile_end) of the sub-matrix's tile grid (row-major over the tiles
  * that can contain an i < j pair; the tile shape belongs to the active kernel variant, so tile counts are only
  * comparable under one variant).  This is how one shard is split across the GPUs of a box:

@@ -177,6 +177,36 @@ def test_king_matches_oracle(ctx, n, s, k, shard, thr, variant):
     ctx.set_king_variant(-1)
 
 
+def _long_vector_case(ctx, n, s, expect_variant):
+    rng = np.random.default_rng(s)
+    g = random_genotypes(rng, n, s, missing=0.03)
+    g[0] = 1; g[1] = 1          # both_het = num_sites: the largest count an accumulator can hold
+    g[2] = 2; g[3] = 0          # opposing homozygotes at every site: xx = -num_sites
+    g[4] = 2                    # concordant with 2 everywhere
+    sm = ck.submatrix(n)
+    osm = ko_sm(sm)
+    bs = oracle_bitset(g, osm)
+    want, count, _ = ko.king(bs, s, osm, -1.0, 1 << 16)
+    ctx.set_king_variant(-1)
+    with ctx.planes(sm, s) as pl:
+        pl.import_bitset(bs)
+        assert pl.king_variant() == expect_variant
+        got = pl.king(-1.0, 1 << 16)
+        assert pl.last_count == count
+        assert_results_equal(got, want)
+        counts, _ = pl.counts([0, 2, 2], [1, 3, 4])
+        assert counts[0]["both_het"] == s and counts[1]["opposing_hom"] == s and counts[2]["concordant_hom"] == s
+
+
+def test_fp4_kernel_is_exact_at_its_largest_site_count(ctx):
+    # 2^21 sites is the largest count the mxf4 probe verified the fp32 accumulation for (kFp4MaxSites)
+    _long_vector_case(ctx, 20, 1 << 21, expect_variant=3)
+
+
+def test_longer_genotype_vectors_take_the_int8_kernel(ctx):
+    _long_vector_case(ctx, 12, (1 << 21) + 37, expect_variant=2)
+
+
 def test_king_unsorted_is_a_permutation(ctx):
     rng = np.random.default_rng(21)
     g = random_genotypes(rng, 150, 400)
