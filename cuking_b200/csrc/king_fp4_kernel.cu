@@ -103,9 +103,13 @@ struct Fp4Tiles {  // band enumeration, built on the host per launch
   const unsigned long long *band_prefix;  // [num_bands + 1] tiles before band b
   const uint32_t *band_first_col;         // [num_bands] first column tile enumerated in band b
   uint32_t num_bands, num_row_tiles, num_col_tiles;
-  uint32_t total_blocks;                  // 64-sample plane blocks allocated (reads beyond are treated as missing)
 };
 
+// Pins eight values in registers at this point of the instruction stream: without it the compiler sinks the operand
+// expansion below the barrier wait that follows, i.e. onto the critical path of the A-slot refill.
+__device__ __forceinline__ void pin8(const uint32_t (&v)[8]) {
+  asm volatile("" ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
+}
 __device__ __forceinline__ void expand_fp4(uint32_t z, uint32_t &x, uint32_t &y, uint32_t &h) {
   x = z & 0xAAAAAAAAu;  // +1 hom-alt (0x2), -1 hom-ref (0xA)
   y = z & 0x22222222u;  // 1 hom
@@ -163,9 +167,10 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     // ===== A expanders: one thread per row; group g expands the steps {2n + g} into TMEM slot step % 4.  A slot is
     // refilled as soon as the three MMAs that read it have completed, while the other three keep the tensor pipe busy.
     const uint32_t group = warp >> 2, srow = (warp & 3) * 32 + lane;
-    const uint32_t slot = p.row_block0 * kTileSamples + row0 + srow;
+    // rows beyond the tile's edge re-read its first row (always allocated): their pairs are masked in the epilogue, and
+    // the loads stay unconditional
+    const uint32_t slot = p.row_block0 * kTileSamples + row0 + (srow < rows_here ? srow : 0u);
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
-    const bool in_range = blk < tiles.total_blocks && srow < rows_here;
     const uint4 *src = reinterpret_cast<const uint4 *>(p.codes) + size_t(blk) * p.words * kTileSamples + ln;
     const uint32_t lane_base = tmem_base + ((uint32_t(warp & 3) * 32u) << 16);
     const uint32_t ta = lane_base + kFColA;
@@ -183,12 +188,12 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     const uint32_t num_items = num_steps / (AS * kFGroups);
     uint4 z[kPrefetch][AS][2];
     auto load_item = [&](uint32_t n, uint4 (&dst)[AS][2]) {
-      const bool ok = in_range && n < num_items;
+      n = min(n, num_items - 1);  // the prefetch beyond the last item re-reads it
 #pragma unroll
       for (uint32_t a = 0; a < AS; ++a) {
         const uint4 *s0 = src + size_t((n * kFGroups + group) * AS + a) * (2 * kTileSamples);
-        dst[a][0] = ok ? __ldg(s0) : make_uint4(0, 0, 0, 0);
-        dst[a][1] = ok ? __ldg(s0 + kTileSamples) : make_uint4(0, 0, 0, 0);
+        dst[a][0] = __ldg(s0);
+        dst[a][1] = __ldg(s0 + kTileSamples);
       }
     };
 #pragma unroll
@@ -209,10 +214,13 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
           expand_fp4(z[u][a][1].y, x[a][5], y[a][5], h[a][5]);
           expand_fp4(z[u][a][1].z, x[a][6], y[a][6], h[a][6]);
           expand_fp4(z[u][a][1].w, x[a][7], y[a][7], h[a][7]);
+          pin8(x[a]);
+          pin8(y[a]);
+          pin8(h[a]);
         }
         load_item(n0 + u + kPrefetch, z[u]);  // refill the registers just consumed
         const unsigned long long p1 = FPROF_T();
-        if (stage_no >= kAStages) mbar_wait(&empty_a[astage], ((stage_no / kAStages) - 1) & 1u);  // previous readers done
+        if (stage_no >= kAStages) mbar_wait_suspend(&empty_a[astage], ((stage_no / kAStages) - 1) & 1u);  // previous readers done
         __syncwarp();  // tcgen05.st is warp-collective; the polling loop may leave the lanes diverged
         const unsigned long long p2 = FPROF_T();
         tcgen05_after_sync();
@@ -240,9 +248,8 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     // ===== B expanders: two threads per column sample (32 sites of every step each), BS steps per stage =====
     const uint32_t idx = tid - kFAWarps * 32;
     const uint32_t half = idx / kFN, srow = idx % kFN;  // half: K bytes 16*half .. 16*half+15 of every step
-    const uint32_t slot = p.col_block0 * kTileSamples + col0 + srow;
+    const uint32_t slot = p.col_block0 * kTileSamples + col0 + (srow < cols_here ? srow : 0u);  // see the A expanders
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
-    const bool in_range = blk < tiles.total_blocks && srow < cols_here;
     const uint4 *src = reinterpret_cast<const uint4 *>(p.codes) + (size_t(blk) * p.words + half) * kTileSamples + ln;
     const uint32_t b_off = (srow >> 3) * G::kSBO + (srow & 7) * 16 + half * kFLBO;
     const uint32_t num_subs = num_steps / kFSub;
@@ -250,8 +257,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     uint4 z[kFBPrefetch][kFSub];
     auto load_sub = [&](uint32_t m, uint4 (&dst)[kFSub]) {
 #pragma unroll
-      for (uint32_t q = 0; q < kFSub; ++q)
-        dst[q] = (in_range && m < num_subs) ? __ldg(src + size_t(m * kFSub + q) * (2 * kTileSamples)) : make_uint4(0, 0, 0, 0);
+      for (uint32_t q = 0; q < kFSub; ++q) dst[q] = __ldg(src + size_t(min(m, num_subs - 1) * kFSub + q) * (2 * kTileSamples));
     };
 #pragma unroll
     for (uint32_t u = 0; u < kFBPrefetch; ++u) load_sub(u, z[u]);
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
         }
         load_sub(m + kFBPrefetch, z[u]);
         const unsigned long long p1 = FPROF_T();
-        if (sub == 0 && fill > 0) mbar_wait(&empty_b[s], (fill - 1) & 1u);  // the MMAs that read this stage have completed
+        if (sub == 0 && fill > 0) mbar_wait_suspend(&empty_b[s], (fill - 1) & 1u);  // the MMAs that read this stage have completed
         const unsigned long long p2 = FPROF_T();
         uint8_t *stage = smem + size_t(s) * G::kStageBytes + b_off + sub * kFSub * 2 * kFLBO;
 #pragma unroll
@@ -306,13 +312,13 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     for (uint32_t step = 0; step < num_steps; step += AS) {
       const uint32_t stage_no = step / AS, astage = stage_no % kAStages, mb = step / BS, sb = mb % NS, q = step % BS;
       const unsigned long long q0 = FPROF_T();
-      if (q == 0) mbar_wait(&full_b[sb], (mb / NS) & 1u);
+      if (q == 0) mbar_wait_suspend(&full_b[sb], (mb / NS) & 1u);
       unsigned long long waited = FPROF_T() - q0;
 #pragma unroll
       for (uint32_t a = 0; a < AS; ++a) {
         const uint32_t aslot = astage * AS + a;
         const unsigned long long w0 = FPROF_T();
-        mbar_wait(&full_a[aslot], (stage_no / kAStages) & 1u);
+        mbar_wait_suspend(&full_a[aslot], (stage_no / kAStages) & 1u);
         waited += FPROF_T() - w0;
         tcgen05_after_sync();
         if (elected) {
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
   // ===== epilogue: all 16 warps; thread = row (TMEM lane quadrant warp % 4), 20 columns per warp group (16 + 4) =====
   {
     __syncwarp();
-    mbar_wait(&acc_bar, 0);
+    mbar_wait_suspend(&acc_bar, 0);
     tcgen05_after_sync();
     const unsigned long long t_main = FPROF_T();
     if (tid == 0) { FPROF_ADD(12, t_main - t_start); FPROF_ADD(13, num_steps); }
@@ -453,7 +459,7 @@ BandTable build_band_table(const KingLaunch &k) {
 struct Fp4Config { uint32_t as, bs, ns; };
 Fp4Config fp4_config() {  // stage geometry; CUKING_FP4_STAGE = "<steps per A stage>x<steps per B stage>x<B stages>" is a tuning knob
   static Fp4Config cfg = [] {
-    Fp4Config c{2, 4, 4};
+    Fp4Config c{2, 8, 3};
     if (const char *v = getenv("CUKING_FP4_STAGE")) {
       unsigned a = 0, b = 0, n = 0;
       if (sscanf(v, "%ux%ux%u", &a, &b, &n) == 3 && (a == 1 || a == 2) && ((b == 4 && n == 4) || (b == 8 && n == 3))) c = Fp4Config{a, b, n};
@@ -507,7 +513,8 @@ cudaError_t launch_king_fp4(const KingLaunch &k, uint32_t total_blocks, ck_ctx *
   cudaError_t e = cudaMemcpyAsync(d_prefix, bt.band_prefix.data(), bt.band_prefix.size() * 8, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_first, bt.band_first_col.data(), first_bytes, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the host vectors die with this frame
-  const Fp4Tiles tiles{d_prefix, d_first, bt.num_bands, bt.num_row_tiles, bt.num_col_tiles, total_blocks};
+  (void)total_blocks;  // every row / column a tile reads lies inside the shard's allocated blocks
+  const Fp4Tiles tiles{d_prefix, d_first, bt.num_bands, bt.num_row_tiles, bt.num_col_tiles};
   const Fp4Config cfg = fp4_config();
   constexpr uint64_t kMaxGrid = 1ull << 30;
   for (uint64_t t = k.tile_begin; e == cudaSuccess && t < k.tile_end; t += kMaxGrid) {

@@ -40,8 +40,8 @@ namespace ck {
 namespace {
 
 constexpr uint32_t kUM = 128, kUN = 80;            // tile rows (A operand, TMEM lanes) x tile columns (B operand)
-constexpr uint32_t kASlots = 4;                    // A-operand ring in TMEM: one 32-site step per slot, one barrier pair each
-constexpr uint32_t kAGroups = 2;                   // groups of four A warps; group g expands the steps with step % 2 == g
+constexpr uint32_t kASlots = 4;                    // A-operand ring in TMEM: one 32-site step per slot
+constexpr uint32_t kAStageSteps = 2;               // steps per A stage; the two groups of A warps own one stage each
 constexpr uint32_t kBStageSteps = 4;               // 32-site steps per shared-memory B stage
 constexpr uint32_t kBStages = 3;
 constexpr uint32_t kLBO = 128;                     // bytes between K-adjacent 8x16-byte core matrices
@@ -52,14 +52,14 @@ constexpr size_t kUmmaSmem = size_t(kBStages) * kBStageBytes + 1024;  // + align
 constexpr uint32_t kUThreads = 512;
 constexpr uint32_t kAWarps = 8, kBWarps = (2 * kUN) / 32, kExpanderWarps = kAWarps + kBWarps;  // 8 + 5
 constexpr uint32_t kIssuers = 3;                   // warps 13, 14, 15: x, y and h MMAs
-constexpr uint32_t kAPrefetch = 4, kBPrefetch = 2; // register prefetch depth: A in steps of the group, B in stages
+constexpr uint32_t kAPrefetch = 2, kBPrefetch = 2; // register prefetch depth in stages
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColXX = 0, kColY = kUN, kColH = 3 * kUN;  // accumulators: xx | (yy|yh) | (hy|hh)
 constexpr uint32_t kColA = 5 * kUN;                // A ring: slot s at kColA + 24 s: x, y, h (8 columns each)
 static_assert(kBWarps * 32 == 2 * kUN, "two threads per column sample must fill whole warps");
 static_assert(kColA + 24 * kASlots <= kTmemCols, "TMEM budget");
-static_assert(kASlots == kBStageSteps && kASlots % kAGroups == 0, "stage geometry");
-static_assert(kChunkWords % (kAGroups * kAPrefetch) == 0 && kChunkWords % (kBStageSteps * kBPrefetch) == 0, "loop unrolling");
+static_assert(kASlots == 2 * kAStageSteps && kBStageSteps == 2 * kAStageSteps, "stage geometry");
+static_assert(kChunkWords % (2 * kAStageSteps * kAPrefetch) == 0 && kChunkWords % (kBStageSteps * kBPrefetch) == 0, "loop unrolling");
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   // K-major, no swizzle: ((8,n),2):((16 B, SBO), LBO); version 1 (Blackwell)
@@ -136,7 +136,7 @@ __device__ __forceinline__ void expand_codes(uint32_t z, uint32_t &x_lo, uint32_
 
 __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunch p, const UmmaTiles tiles) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_a[kASlots], empty_a[kASlots], full_b[kBStages], empty_b[kBStages], acc_bar;
+  __shared__ __align__(8) uint64_t full_a[2], empty_a[2], full_b[kBStages], empty_b[kBStages], acc_bar;
   __shared__ uint32_t tmem_base_smem;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (uint32_t s = 0; s < kASlots; ++s) {
-      mbar_init(&full_a[s], kAWarps / kAGroups);  // the four warps of the group that fills the slot
+    for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(&full_a[s], kAWarps / 2);  // the four warps of the group that owns the stage
       mbar_init(&empty_a[s], kIssuers);
     }
     for (uint32_t s = 0; s < kBStages; ++s) {
@@ -177,45 +177,58 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
   const uint32_t num_steps = p.words;  // one 32-site word per step; p.words is a multiple of kChunkWords = 16
 
   if (warp < kAWarps) {
-    // ===== A expanders: one thread per row; group g (4 warps) expands the steps {2n + g}, n = 0, 1, ..., each into TMEM
-    // slot step % 4.  A slot is refilled as soon as the three MMAs that read it have completed, while the other three
-    // slots keep the tensor pipe busy (the store + barrier round trip is ~2 steps long).  =====
+    // ===== A expanders: one thread per row; group g (4 warps) owns A stage g = TMEM slots 2g, 2g+1 and fills it with
+    // the steps {4n + 2g, 4n + 2g + 1}, n = 0, 1, ...  =====
     const uint32_t group = warp >> 2, srow = (warp & 3) * 32 + lane;
     const uint32_t slot = p.row_block0 * kTileSamples + row0 + srow;
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
     const bool in_range = blk < tiles.total_blocks && srow < rows_here;
     const uint4 *src = reinterpret_cast<const uint4 *>(p.codes) + size_t(blk) * p.words * kTileSamples + ln;
-    const uint32_t ta = tmem_base + ((uint32_t(warp & 3) * 32u) << 16) + kColA;
-    const uint32_t num_items = num_steps / kAGroups;  // steps expanded by this group
-    uint4 z[kAPrefetch];
-    auto load_item = [&](uint32_t n) {
-      return (in_range && n < num_items) ? __ldg(src + size_t(n * kAGroups + group) * kTileSamples) : make_uint4(0, 0, 0, 0);
+    const uint32_t ta = tmem_base + ((uint32_t(warp & 3) * 32u) << 16) + kColA + group * (kAStageSteps * 24);
+    const uint32_t num_fills = num_steps / kASlots;  // fills of this group's stage
+    uint4 z[kAPrefetch][kAStageSteps];
+    auto load_fill = [&](uint32_t n, uint4 (&dst)[kAStageSteps]) {
+#pragma unroll
+      for (uint32_t q = 0; q < kAStageSteps; ++q)
+        dst[q] = (in_range && n < num_fills) ? __ldg(src + size_t(n * kASlots + group * kAStageSteps + q) * kTileSamples)
+                                             : make_uint4(0, 0, 0, 0);
     };
 #pragma unroll
-    for (uint32_t u = 0; u < kAPrefetch; ++u) z[u] = load_item(u);
-    for (uint32_t n0 = 0; n0 < num_items; n0 += kAPrefetch) {
+    for (uint32_t u = 0; u < kAPrefetch; ++u) load_fill(u, z[u]);
+    for (uint32_t n0 = 0; n0 < num_fills; n0 += kAPrefetch) {
 #pragma unroll
       for (uint32_t u = 0; u < kAPrefetch; ++u) {
-        const uint32_t step = (n0 + u) * kAGroups + group, aslot = step % kASlots;
-        uint32_t x[8], y[8], h[8];
+        const uint32_t n = n0 + u;
+        uint32_t x[kAStageSteps][8], y[kAStageSteps][8], h[kAStageSteps][8];
         const unsigned long long p0 = PROF_T();
-        expand_codes(z[u].x, x[0], x[1], y[0], y[1], h[0], h[1]);
-        expand_codes(z[u].y, x[2], x[3], y[2], y[3], h[2], h[3]);
-        expand_codes(z[u].z, x[4], x[5], y[4], y[5], h[4], h[5]);
-        expand_codes(z[u].w, x[6], x[7], y[6], y[7], h[6], h[7]);
-        z[u] = load_item(n0 + u + kAPrefetch);  // refill the registers just consumed
+#pragma unroll
+        for (uint32_t q = 0; q < kAStageSteps; ++q) {
+          expand_codes(z[u][q].x, x[q][0], x[q][1], y[q][0], y[q][1], h[q][0], h[q][1]);
+          expand_codes(z[u][q].y, x[q][2], x[q][3], y[q][2], y[q][3], h[q][2], h[q][3]);
+          expand_codes(z[u][q].z, x[q][4], x[q][5], y[q][4], y[q][5], h[q][4], h[q][5]);
+          expand_codes(z[u][q].w, x[q][6], x[q][7], y[q][6], y[q][7], h[q][6], h[q][7]);
+        }
+        load_fill(n + kAPrefetch, z[u]);  // refill the registers just consumed
         const unsigned long long p1 = PROF_T();
-        if (step >= kASlots) mbar_wait(&empty_a[aslot], ((step / kASlots) - 1) & 1u);  // previous readers of the slot done
+        if (n > 0) mbar_wait(&empty_a[group], (n - 1) & 1u);  // the MMAs that read the previous fill have completed
         __syncwarp();  // tcgen05.st is warp-collective; the polling loop may leave the lanes diverged
         const unsigned long long p2 = PROF_T();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tmem_st8(ta + aslot * 24, x);
-        tmem_st8(ta + aslot * 24 + 8, y);
-        tmem_st8(ta + aslot * 24 + 16, h);
+#pragma unroll
+        for (uint32_t q = 0; q < kAStageSteps; ++q) {
+          tmem_st8(ta + q * 24, x[q]);
+          tmem_st8(ta + q * 24 + 8, y[q]);
+          tmem_st8(ta + q * 24 + 16, h[q]);
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full_a[aslot]);
+        if (lane == 0) {
+          // The issuers wait on full_a only.  Group 0's fill n starts B stage n, so it is group 0 that makes sure the
+          // B operands are in shared memory before it announces the A stage (acquire on full_b, release on full_a).
+          if (group == 0) mbar_wait(&full_b[n % kBStages], (n / kBStages) & 1u);
+          mbar_arrive(&full_a[group]);
+        }
         const unsigned long long p3 = PROF_T();
         PROF_ADD(0, p1 - p0);
         PROF_ADD(1, p2 - p1);
@@ -285,20 +298,24 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
     const uint64_t b_desc0 = make_smem_desc(smem_u32(smem) + (which == 0 ? 0u : kBTile));  // x tile, or stacked [y ; h]
     uint32_t elected;
     asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(elected));
-    for (uint32_t step = 0; step < num_steps; ++step) {
-      const uint32_t aslot = step % kASlots, mb = step / kBStageSteps, sb = mb % kBStages, q = step % kBStageSteps;
+    const uint32_t num_astages = num_steps / kAStageSteps;
+    for (uint32_t ma = 0; ma < num_astages; ++ma) {
+      const uint32_t g = ma & 1u, mb = ma >> 1, sb = mb % kBStages;  // A stage g, B stage mb (4 steps = 2 A stages)
       const unsigned long long q0 = PROF_T();
-      if (q == 0) mbar_wait(&full_b[sb], (mb / kBStages) & 1u);
-      mbar_wait(&full_a[aslot], (step / kASlots) & 1u);
+      mbar_wait(&full_a[g], (ma >> 1) & 1u);  // covers the B stage too (see the A expanders)
       const unsigned long long q1 = PROF_T();
       PROF_ADD(8 + which, q1 - q0);
       PROF_ADD(11, which == 0 ? 1 : 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elected) {
-        const uint32_t b_bytes = sb * kBStageBytes + q * 2 * kLBO;
-        umma_i8_ts(d_addr, a_addr + aslot * 24, b_desc0 + uint64_t(b_bytes >> 4), idesc, step > 0 ? 1u : 0u);
-        umma_commit(&empty_a[aslot]);                              // arrives when this thread's MMAs so far have completed
-        if (q == kBStageSteps - 1) umma_commit(&empty_b[sb]);      // last step of the B stage
+#pragma unroll
+        for (uint32_t q = 0; q < kAStageSteps; ++q) {
+          const uint32_t b_bytes = sb * kBStageBytes + (g * kAStageSteps + q) * 2 * kLBO;
+          umma_i8_ts(d_addr, a_addr + (g * kAStageSteps + q) * 24, b_desc0 + uint64_t(b_bytes >> 4), idesc,
+                     (ma > 0 || q > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_a[g]);                 // arrives when this thread's MMAs so far have completed
+        if (g == 1) umma_commit(&empty_b[sb]);    // second half of the B stage done
       }
       __syncwarp();
     }
