@@ -630,6 +630,54 @@ int ck_king_num_tiles(const ck_planes *pl, uint64_t *num_tiles) {
   return CK_OK;
 }
 
+// Common tail of the pairwise entry points: reads the emitted-pair counter, turns an overflow into the reference's
+// error (cuking.cu:747-751), sorts on the device and copies the records out.  Expects ev[0] / ev[1] recorded around
+// the kernel launches on the ctx stream.
+static int finish_results(ck_ctx *ctx, ck_result *d_emit, uint32_t max_results, ck_result *results, int results_on_device,
+                          uint32_t *num_results, int sort) {
+  cudaStream_t s = ctx->stream;
+  static const bool dbg = getenv("CUKING_DEBUG_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+  auto tp0 = now();
+  unsigned long long count = 0;
+  CK_CUDA(cudaMemcpyAsync(&count, ctx->d_counter, sizeof(count), cudaMemcpyDeviceToHost, s));
+  CK_CUDA(cudaStreamSynchronize(s));
+  ctx->timings.king_ms = elapsed(ctx->ev[0], ctx->ev[1]);
+  if (dbg) fprintf(stderr, "[ck] king: host wait %.2f ms, kernel %.2f ms\n", ms_since(tp0), ctx->timings.king_ms);
+  auto tp1 = now();
+  *num_results = count > 0xffffffffull ? 0xffffffffu : uint32_t(count);
+  if (count > max_results)  // cuking.cu:747-751
+    return fail(CK_ERR_RESULT_OVERFLOW, "Could not store all results: try increasing the --max_results parameter.");
+  const uint32_t n = uint32_t(count);
+  if (n == 0) return CK_OK;
+
+  cudaEvent_t t0, t1, t2;
+  CK_CUDA(cudaEventCreate(&t0));
+  CK_CUDA(cudaEventCreate(&t1));
+  CK_CUDA(cudaEventCreate(&t2));
+  cudaEventRecord(t0, s);
+  const ck_result *d_final = d_emit;
+  if (sort) {
+    int rc = sort_results(ctx, d_emit, n, results_on_device ? results : nullptr, &d_final);
+    if (rc != CK_OK) return rc;
+    ctx->timings.king_launches += 3;  // key build, radix sort (one logical launch), gather
+  }
+  if (dbg) fprintf(stderr, "[ck] sort: host %.2f ms\n", ms_since(tp1));
+  cudaEventRecord(t1, s);
+  if (!results_on_device) CK_CUDA(cudaMemcpyAsync(results, d_final, size_t(n) * sizeof(ck_result), cudaMemcpyDeviceToHost, s));
+  cudaEventRecord(t2, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  ctx->timings.sort_ms = elapsed(t0, t1);
+  ctx->timings.d2h_ms = elapsed(t1, t2);
+  if (dbg) fprintf(stderr, "[ck] sort+d2h: host %.2f ms (device sort %.2f, d2h %.2f)\n", ms_since(tp1), ctx->timings.sort_ms, ctx->timings.d2h_ms);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaEventDestroy(t2);
+  CK_CUDA(e);
+  return CK_OK;
+}
+
 int ck_king_tiles(ck_planes *pl, uint64_t tile_begin, uint64_t tile_end, float kin_threshold, uint32_t max_results,
                   ck_result *results, int results_on_device, uint32_t *num_results, int sort) {
   if (!pl || !num_results) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -663,50 +711,11 @@ int ck_king_tiles(ck_planes *pl, uint64_t tile_begin, uint64_t tile_end, float k
   k.dump_counts = nullptr;
   k.dump_kin = nullptr;
   ctx->timings.king_launches = 0;
-  static const bool dbg = getenv("CUKING_DEBUG_TIMING") != nullptr;
-  auto now = [] { return std::chrono::steady_clock::now(); };
-  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
-  auto tp0 = now();
   CK_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), s));
   CK_CUDA(cudaEventRecord(ctx->ev[0], s));
   if (tile_end > tile_begin) CK_CUDA(dispatch_king(pl, k, s, &ctx->timings.king_launches));
   CK_CUDA(cudaEventRecord(ctx->ev[1], s));
-  unsigned long long count = 0;
-  CK_CUDA(cudaMemcpyAsync(&count, ctx->d_counter, sizeof(count), cudaMemcpyDeviceToHost, s));
-  CK_CUDA(cudaStreamSynchronize(s));
-  ctx->timings.king_ms = elapsed(ctx->ev[0], ctx->ev[1]);
-  if (dbg) fprintf(stderr, "[ck] king: host %.2f ms, kernel %.2f ms\n", ms_since(tp0), ctx->timings.king_ms);
-  auto tp1 = now();
-  *num_results = count > 0xffffffffull ? 0xffffffffu : uint32_t(count);
-  if (count > max_results)  // cuking.cu:747-751
-    return fail(CK_ERR_RESULT_OVERFLOW, "Could not store all results: try increasing the --max_results parameter.");
-  const uint32_t n = uint32_t(count);
-  if (n == 0) return CK_OK;
-
-  cudaEvent_t t0, t1, t2;
-  CK_CUDA(cudaEventCreate(&t0));
-  CK_CUDA(cudaEventCreate(&t1));
-  CK_CUDA(cudaEventCreate(&t2));
-  cudaEventRecord(t0, s);
-  const ck_result *d_final = d_emit;
-  if (sort) {
-    rc = sort_results(ctx, d_emit, n, results_on_device ? results : nullptr, &d_final);
-    if (rc != CK_OK) return rc;
-    ctx->timings.king_launches += 3;  // key build, radix sort (one logical launch), gather
-  }
-  if (dbg) fprintf(stderr, "[ck] sort: host %.2f ms\n", ms_since(tp1));
-  cudaEventRecord(t1, s);
-  if (!results_on_device) CK_CUDA(cudaMemcpyAsync(results, d_final, size_t(n) * sizeof(ck_result), cudaMemcpyDeviceToHost, s));
-  cudaEventRecord(t2, s);
-  cudaError_t e = cudaStreamSynchronize(s);
-  ctx->timings.sort_ms = elapsed(t0, t1);
-  ctx->timings.d2h_ms = elapsed(t1, t2);
-  if (dbg) fprintf(stderr, "[ck] sort+d2h: host %.2f ms (device sort %.2f, d2h %.2f)\n", ms_since(tp1), ctx->timings.sort_ms, ctx->timings.d2h_ms);
-  cudaEventDestroy(t0);
-  cudaEventDestroy(t1);
-  cudaEventDestroy(t2);
-  CK_CUDA(e);
-  return CK_OK;
+  return finish_results(ctx, d_emit, max_results, results, results_on_device, num_results, sort);
 }
 
 int ck_king(ck_planes *pl, float kin_threshold, uint32_t max_results, ck_result *results, int results_on_device,
@@ -763,6 +772,99 @@ int ck_king_counts(ck_planes *pl, const uint32_t *sample_i, const uint32_t *samp
   return CK_OK;
 }
 
+// ---- pipelined host-buffer path ------------------------------------------------------------------------------------
+// ck_king_host_bitset on a diagonal shard with the mxf4 kernel: the upload of the reference-layout bit set overlaps
+// the pairwise kernel instead of preceding it.  A band of the tile enumeration (kFp4BandRows rows) only needs the
+// samples at or after its first row (i < j), so the sample range is uploaded LAST CHUNK FIRST on the copy stream and
+// every chunk's bands are launched as soon as its rows have been transposed and coded - by then every column they
+// pair with is already on the device.  The bottom chunks hold few tiles, so only the first small upload is exposed.
+static bool host_bitset_can_pipeline(const ck_planes *pl) {
+  static const bool off = getenv("CUKING_NO_PIPELINE") != nullptr;
+  return !off && planes_variant(pl) == 3 && sm_diagonal(pl->map.sm) && sm_rows(pl->map.sm) >= 4 * kFp4BandRows;
+}
+
+static int king_host_bitset_pipelined(ck_planes *pl, const uint64_t *bit_set, float kin_threshold, uint32_t max_results,
+                                      ck_result *results, uint32_t *num_results) {
+  if (!num_results) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (max_results > 0 && !results) return fail(CK_ERR_INVALID_ARGUMENT, "results is NULL");
+  *num_results = 0;
+  ck_ctx *ctx = pl->ctx;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+  const uint32_t n = sm_rows(pl->map.sm);
+  const size_t words_per_sample = ref_words_per_sample(pl->num_sites);  // u64
+  const size_t bytes = words_per_sample * n * 8;
+  struct Staging {  // device copy of the host bit set, returned to the ctx cache on scope exit
+    ck_ctx *ctx;
+    void *p = nullptr;
+    size_t bytes = 0;
+    std::vector<cudaEvent_t> events;
+    ~Staging() {
+      for (cudaEvent_t e : events) cudaEventDestroy(e);
+      ctx_release(ctx, p, bytes);
+    }
+  } st{ctx};
+  CK_CUDA(ctx_alloc(ctx, &st.p, bytes));
+  st.bytes = bytes;
+  if (pl->codes == nullptr) {
+    pl->codes_bytes = std::max<size_t>(pl->codes_words(), 1) * 4;
+    CK_CUDA(ctx_alloc(ctx, reinterpret_cast<void **>(&pl->codes), pl->codes_bytes));
+  }
+  int rc = ensure_result_buf(ctx, max_results);
+  if (rc != CK_OK) return rc;
+  KingLaunch k = base_launch(pl);
+  k.kin_threshold = kin_threshold;
+  k.max_results = max_results;
+  k.results = ctx->result_buf;
+  k.counter = ctx->d_counter;
+  std::vector<uint64_t> band_prefix;
+  CK_CUDA(king_fp4_prepare(k, ctx, s, &band_prefix));
+  const uint32_t num_bands = uint32_t(band_prefix.size()) - 1;
+  const uint32_t chunk_bands = std::max<uint32_t>(1, ceil_div(num_bands, 24u));
+
+  // the copy stream starts after everything already queued on the compute stream (the buffers come from the ctx cache)
+  cudaEvent_t fork;
+  CK_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  st.events.push_back(fork);
+  CK_CUDA(cudaEventRecord(fork, s));
+  CK_CUDA(cudaStreamWaitEvent(cs, fork, 0));
+  struct Chunk { uint32_t band_lo, band_hi, s0, s1; cudaEvent_t ready; };
+  std::vector<Chunk> chunks;
+  for (uint32_t hi = num_bands; hi > 0;) {
+    const uint32_t lo = hi > chunk_bands ? hi - chunk_bands : 0;
+    Chunk c{lo, hi, lo * kFp4BandRows, std::min<uint32_t>(hi * kFp4BandRows, n), nullptr};
+    CK_CUDA(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+    st.events.push_back(c.ready);
+    const size_t off = size_t(c.s0) * words_per_sample;
+    CK_CUDA(cudaMemcpyAsync(static_cast<uint64_t *>(st.p) + off, bit_set + off, size_t(c.s1 - c.s0) * words_per_sample * 8,
+                            cudaMemcpyHostToDevice, cs));
+    CK_CUDA(cudaEventRecord(c.ready, cs));
+    chunks.push_back(c);
+    hi = lo;
+  }
+  ctx->timings.king_launches = 0;
+  CK_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), s));
+  CK_CUDA(cudaEventRecord(ctx->ev[0], s));
+  for (const Chunk &c : chunks) {
+    CK_CUDA(cudaStreamWaitEvent(s, c.ready, 0));
+    const uint32_t block0 = c.s0 / kTileSamples, num_blocks = ceil_div(c.s1, kTileSamples) - block0;
+    CK_CUDA(launch_import_ref_range(*pl, static_cast<const uint64_t *>(st.p), block0, num_blocks, s));
+    CK_CUDA(launch_finalize_codes_range(*pl, 3, block0, num_blocks, s));
+    k.tile_begin = band_prefix[c.band_lo];
+    k.tile_end = band_prefix[c.band_hi];
+    if (k.tile_end > k.tile_begin) CK_CUDA(launch_king_fp4(k, pl->map.num_blocks, ctx, s, &ctx->timings.king_launches));
+    ctx->timings.king_launches += 2;  // transpose + code kernels of the chunk
+  }
+  CK_CUDA(cudaEventRecord(ctx->ev[1], s));
+  pl->compute_stale = true;
+  pl->codes_stale = false;
+  pl->codes_kind = 3;
+  rc = finish_results(ctx, ctx->result_buf, max_results, results, 0, num_results, 1);
+  ctx->timings.h2d_ms = 0.f;     // overlapped: the whole upload + transpose + kernel span is reported as king_ms
+  ctx->timings.import_ms = 0.f;
+  return rc;
+}
+
 int ck_king_host_bitset(ck_ctx *ctx, uint32_t num_samples, uint32_t split_factor, uint32_t shard_index,
                         uint32_t num_sites, const uint64_t *bit_set, float kin_threshold, uint32_t max_results,
                         ck_result *results, uint32_t *num_results) {
@@ -773,8 +875,12 @@ int ck_king_host_bitset(ck_ctx *ctx, uint32_t num_samples, uint32_t split_factor
   ck_planes *pl = nullptr;
   rc = ck_planes_create(ctx, &sm, num_sites, &pl);
   if (rc != CK_OK) return rc;
-  rc = ck_planes_import_bitset(pl, bit_set, 0);
-  if (rc == CK_OK) rc = ck_king(pl, kin_threshold, max_results, results, 0, num_results, 1);
+  if (host_bitset_can_pipeline(pl)) {
+    rc = king_host_bitset_pipelined(pl, bit_set, kin_threshold, max_results, results, num_results);
+  } else {
+    rc = ck_planes_import_bitset(pl, bit_set, 0);
+    if (rc == CK_OK) rc = ck_king(pl, kin_threshold, max_results, results, 0, num_results, 1);
+  }
   ck_planes_destroy(pl);
   return rc;
 }

@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "../../include/cuking_b200.h"
 #include "layout.cuh"
@@ -53,6 +54,7 @@ struct ck_ctx {
   // alive-tile table of the tcgen05 kernel (grow-only device scratch)
   void *tile_table = nullptr;
   size_t tile_table_bytes = 0;
+  uint64_t tile_table_key[3] = {~0ull, 0, 0};  // (variant, rows/cols, global origins) of the table now on the device
   // grow-only scratch for the result sort (keys, indices, CUB temporaries, sorted records): no cudaMalloc/cudaFree
   // on the steady-state path
   void *sort_scratch = nullptr;
@@ -96,6 +98,10 @@ cudaError_t launch_pack(const ck_planes &pl, const int64_t *row, const int64_t *
                         size_t index_base, uint32_t *d_err, cudaStream_t s);
 cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s);
 cudaError_t launch_finalize_codes(const ck_planes &pl, int kind, cudaStream_t s);
+// the same for the 64-sample blocks [block0, block0 + num_blocks) only (pipelined host-buffer path)
+cudaError_t launch_finalize_codes_range(const ck_planes &pl, int kind, uint32_t block0, uint32_t num_blocks, cudaStream_t s);
+cudaError_t launch_import_ref_range(const ck_planes &pl, const uint64_t *d_bit_set, uint32_t block0, uint32_t num_blocks,
+                                    cudaStream_t s);
 cudaError_t launch_import_ref(const ck_planes &pl, const uint64_t *d_bit_set, cudaStream_t s);
 cudaError_t launch_export_ref(const ck_planes &pl, uint64_t *d_bit_set, cudaStream_t s);
 cudaError_t launch_synth_planes(const ck_planes &pl, uint64_t seed, uint32_t miss_thr, cudaStream_t s);
@@ -134,6 +140,11 @@ cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, ck_ctx 
 // ---- king_fp4_kernel.cu (variant 3: tcgen05 kind::mxf4 formulation, 128 x 80 tiles, band-ordered tile enumeration) ----
 uint64_t king_fp4_num_tiles(const KingLaunch &k);
 cudaError_t launch_king_fp4(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches);
+// Uploads the band table for this launch geometry unless it is already on the device (then: no copy, no stream
+// synchronisation - the pipelined host-buffer path launches many tile ranges back to back).  `band_prefix`, when not
+// NULL, receives the first linear tile index of every band (+ the total); a band is kFp4BandRows rows of the shard.
+cudaError_t king_fp4_prepare(const KingLaunch &k, ck_ctx *ctx, cudaStream_t s, std::vector<uint64_t> *band_prefix);
+constexpr uint32_t kFp4BandRows = 8 * 128;
 constexpr uint32_t kFp4MaxSites = 1u << 21;  // exactness of the tensor core's fp32 accumulation was measured up to this count
 
 }  // namespace ck

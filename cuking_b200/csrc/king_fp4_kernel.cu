@@ -496,25 +496,48 @@ uint64_t king_fp4_num_tiles(const KingLaunch &k) {
   return build_band_table(k).band_prefix.back();
 }
 
-cudaError_t launch_king_fp4(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches) {
-  if (k.tile_end <= k.tile_begin) return cudaSuccess;
+cudaError_t king_fp4_prepare(const KingLaunch &k, ck_ctx *ctx, cudaStream_t s, std::vector<uint64_t> *band_prefix) {
+  const uint64_t key[3] = {3, (uint64_t(k.num_rows) << 32) | k.num_cols, (uint64_t(k.row_global0) << 32) | k.col_global0};
+  const bool cached = ctx->tile_table != nullptr && ctx->tile_table_key[0] == key[0] && ctx->tile_table_key[1] == key[1] &&
+                      ctx->tile_table_key[2] == key[2];
+  if (cached && band_prefix == nullptr) return cudaSuccess;
   const BandTable bt = build_band_table(k);
+  if (band_prefix) band_prefix->assign(bt.band_prefix.begin(), bt.band_prefix.end());
+  if (cached) return cudaSuccess;
   const size_t prefix_bytes = (bt.band_prefix.size() * 8 + 255) & ~size_t(255), first_bytes = bt.band_first_col.size() * 4;
   if (ctx->tile_table_bytes < prefix_bytes + first_bytes) {  // grow-only scratch owned by the ctx
     if (ctx->tile_table) cudaFree(ctx->tile_table);
     ctx->tile_table = nullptr;
     ctx->tile_table_bytes = 0;
+    ctx->tile_table_key[0] = ~0ull;
     cudaError_t e = cudaMalloc(&ctx->tile_table, prefix_bytes + first_bytes);
     if (e != cudaSuccess) return e;
     ctx->tile_table_bytes = prefix_bytes + first_bytes;
   }
+  ctx->tile_table_key[0] = ~0ull;
   auto *d_prefix = static_cast<unsigned long long *>(ctx->tile_table);
-  auto *d_first = reinterpret_cast<uint32_t *>(static_cast<char *>(ctx->tile_table) + prefix_bytes);
+  auto *d_first = reinterpret_cast<uint32_t *>(static_cast<char *>(ctx->tile_table) + ctx->tile_table_bytes - first_bytes);
   cudaError_t e = cudaMemcpyAsync(d_prefix, bt.band_prefix.data(), bt.band_prefix.size() * 8, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_first, bt.band_first_col.data(), first_bytes, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the host vectors die with this frame
+  if (e == cudaSuccess) {
+    ctx->tile_table_key[0] = key[0];
+    ctx->tile_table_key[1] = key[1];
+    ctx->tile_table_key[2] = key[2];
+  }
+  return e;
+}
+
+cudaError_t launch_king_fp4(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches) {
   (void)total_blocks;  // every row / column a tile reads lies inside the shard's allocated blocks
-  const Fp4Tiles tiles{d_prefix, d_first, bt.num_bands, bt.num_row_tiles, bt.num_col_tiles};
+  if (k.tile_end <= k.tile_begin) return cudaSuccess;
+  cudaError_t e = king_fp4_prepare(k, ctx, s, nullptr);
+  if (e != cudaSuccess) return e;
+  const uint32_t num_row_tiles = ceil_div(k.num_rows, kFM), num_bands = ceil_div(num_row_tiles, kBand);
+  const size_t first_bytes = size_t(std::max<uint32_t>(num_bands, 1)) * 4;
+  auto *d_prefix = static_cast<unsigned long long *>(ctx->tile_table);
+  auto *d_first = reinterpret_cast<uint32_t *>(static_cast<char *>(ctx->tile_table) + ctx->tile_table_bytes - first_bytes);
+  const Fp4Tiles tiles{d_prefix, d_first, num_bands, num_row_tiles, ceil_div(k.num_cols, kFN)};
   const Fp4Config cfg = fp4_config();
   constexpr uint64_t kMaxGrid = 1ull << 30;
   for (uint64_t t = k.tile_begin; e == cudaSuccess && t < k.tile_end; t += kMaxGrid) {

@@ -434,6 +434,7 @@ cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, ck_ctx 
     if (e != cudaSuccess) return e;
     ctx->tile_table_bytes = prefix_bytes + first_bytes;
   }
+  ctx->tile_table_key[0] = ~0ull;  // the scratch no longer holds the mxf4 kernel's band table
   auto *d_prefix = static_cast<unsigned long long *>(ctx->tile_table);
   auto *d_first = reinterpret_cast<uint32_t *>(static_cast<char *>(ctx->tile_table) + prefix_bytes);
   cudaError_t e = cudaMemcpyAsync(d_prefix, tt.row_prefix.data(), tt.row_prefix.size() * 8, cudaMemcpyHostToDevice, s);

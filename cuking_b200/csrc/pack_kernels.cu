@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(256) finalize_codes_kernel(const uint32_t *__r
 // A CTA transposes a 64-sample x 32-word tile of one plane through shared memory so that both sides are coalesced.
 template <bool kImport>
 __global__ void __launch_bounds__(256) ref_transpose_kernel(uint32_t *raw, uint32_t *ref32, SlotMap map, uint32_t words,
-                                                            uint32_t ref_words_u64, uint32_t num_ref_slots) {
+                                                            uint32_t ref_words_u64, uint32_t num_ref_slots, uint32_t block0) {
   __shared__ uint32_t tile[kTileSamples][33];
-  const uint32_t block = blockIdx.y, plane = blockIdx.z;
+  const uint32_t block = block0 + blockIdx.y, plane = blockIdx.z;
   const uint32_t k0 = blockIdx.x * 32;
   const uint32_t ref_k = ref_words_u64;  // uint32 words per plane in the reference layout: 2 * (W/2)
   const uint32_t rows = sm_rows(map.sm);
@@ -286,27 +286,38 @@ cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s) {
 }
 
 cudaError_t launch_finalize_codes(const ck_planes &pl, int kind, cudaStream_t s) {
-  const size_t rows = size_t(pl.map.num_blocks) * pl.words;
+  return launch_finalize_codes_range(pl, kind, 0, pl.map.num_blocks, s);
+}
+cudaError_t launch_finalize_codes_range(const ck_planes &pl, int kind, uint32_t block0, uint32_t num_blocks, cudaStream_t s) {
+  if (num_blocks == 0) return cudaSuccess;
+  const size_t rows = size_t(num_blocks) * pl.words, row0 = size_t(block0) * pl.words;
+  const uint32_t *raw = pl.raw + row0 * kRawPlanes * kTileSamples;
+  uint4 *codes = reinterpret_cast<uint4 *>(pl.codes) + row0 * kTileSamples;
   if (kind == 3)
-    finalize_codes_kernel<true><<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(pl.raw, reinterpret_cast<uint4 *>(pl.codes), rows);
+    finalize_codes_kernel<true><<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(raw, codes, rows);
   else
-    finalize_codes_kernel<false><<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(pl.raw, reinterpret_cast<uint4 *>(pl.codes), rows);
+    finalize_codes_kernel<false><<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(raw, codes, rows);
   return cudaGetLastError();
 }
 
-cudaError_t launch_import_ref(const ck_planes &pl, const uint64_t *d_bit_set, cudaStream_t s) {
+cudaError_t launch_import_ref_range(const ck_planes &pl, const uint64_t *d_bit_set, uint32_t block0, uint32_t num_blocks,
+                                    cudaStream_t s) {
+  if (num_blocks == 0) return cudaSuccess;
   const uint32_t ref_k = ref_words_per_sample(pl.num_sites);  // u64 words per sample == u32 words per plane
-  dim3 grid(ceil_div(pl.words, 32u), pl.map.num_blocks, kRawPlanes);
+  dim3 grid(ceil_div(pl.words, 32u), num_blocks, kRawPlanes);
   ref_transpose_kernel<true><<<grid, 256, 0, s>>>(pl.raw, const_cast<uint32_t *>(reinterpret_cast<const uint32_t *>(d_bit_set)),
-                                                 pl.map, pl.words, ref_k, sm_samples(pl.map.sm));
+                                                 pl.map, pl.words, ref_k, sm_samples(pl.map.sm), block0);
   return cudaGetLastError();
+}
+cudaError_t launch_import_ref(const ck_planes &pl, const uint64_t *d_bit_set, cudaStream_t s) {
+  return launch_import_ref_range(pl, d_bit_set, 0, pl.map.num_blocks, s);
 }
 
 cudaError_t launch_export_ref(const ck_planes &pl, uint64_t *d_bit_set, cudaStream_t s) {
   const uint32_t ref_k = ref_words_per_sample(pl.num_sites);
   dim3 grid(ceil_div(pl.words, 32u), pl.map.num_blocks, kRawPlanes);
   ref_transpose_kernel<false><<<grid, 256, 0, s>>>(pl.raw, reinterpret_cast<uint32_t *>(d_bit_set), pl.map, pl.words,
-                                                  ref_k, sm_samples(pl.map.sm));
+                                                  ref_k, sm_samples(pl.map.sm), 0);
   return cudaGetLastError();
 }
 

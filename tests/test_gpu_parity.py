@@ -262,6 +262,23 @@ def test_host_bitset_seam_matches_oracle(ctx):
         assert_results_equal(got, want)
 
 
+def test_host_bitset_pipelined_upload_matches_oracle(ctx):
+    # >= 4096 samples on a diagonal shard: ck_king_host_bitset uploads the bit set last chunk first and launches each
+    # chunk's bands while the next chunk is still in flight; the result must not depend on that schedule
+    rng = np.random.default_rng(77)
+    n, s = 4400, 300
+    g = random_genotypes(rng, n, s)
+    osm = ko.submatrix(n, 1, 0)
+    bs = oracle_bitset(g, osm)
+    want, count, _ = ko.king(bs, s, osm, 0.1, 1 << 20)
+    assert count > 0
+    for _ in range(2):  # second call: cached buffers and tile table
+        got = ctx.king_host_bitset(n, 1, 0, s, bs, 0.1, 1 << 20)
+        assert_results_equal(got, want)
+    with pytest.raises(ck.CukingError):
+        ctx.king_host_bitset(n, 1, 0, s, bs, 0.1, count - 1)  # overflow is still the reference's error
+
+
 # ---- synthetic cohort ------------------------------------------------------------------------------------------
 
 
