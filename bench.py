@@ -12,10 +12,12 @@ configs[1]: 100,000 samples x 100,000 sites (synthetic cohort of SURVEY.md §8d,
 
 `value`   : planes already resident in HBM when the timed region starts (device-timed, max over ranks).
 `e2e`     : the same pass through the host-buffer C-ABI call ck_king_host_bitset: the reference-layout bit set starts
-            in pinned HOST memory, H2D + layout transpose + finalize + kernel + sort + D2H all inside the timed region.
-`roofline`: the pairwise kernel against the POPC.32 issue rate measured live on this GPU (the path is
-            bound by the quarter-rate POPC pipe, not by HBM or tensor throughput), algorithmic 0.1875 POPC.32 lane-ops
-            per pair·site (the reference formulation's 6 popcounts per site-bit).
+            in pinned HOST memory, H2D (overlapped with the kernel, last sample chunk first) + layout transpose + code
+            derivation + kernel + sort + D2H all inside the timed region.
+`roofline`: the pairwise kernel against the tensor throughput it is bound by: 10 fp4 ops (5 exact E2M1 MACs) per
+            pair·site against the dense kind::mxf4 rate measured on this pool's B200 (tools/umma_mxf4_probe.cu); the
+            SURVEY.md §8d view (0.1875 POPC.32 lane-ops per pair·site against the POPC issue rate measured live on
+            this GPU) is reported beside it as `popc_equivalent`, and is the roofline of --variant 0/1.
 `cpu_baseline` / --impl reference: the oracle's OpenMP restatement of the reference loop on this box's host cores, on
             a bounded sample of the same workload (the reference has no CPU implementation; kind = "port").
 """
@@ -364,6 +366,10 @@ def main():
             bf16 = json.load(f)
     except OSError:
         pass
+    # DRAM bytes of one king_fp4_kernel launch on the single-GPU cfg2 shape: dram__bytes_read.sum + dram__bytes_write.sum
+    # of the ncu --set full capture in profiles/r01_king_fp4_cfg2_ncu.txt (425.06 GB + 0.16 GB; 7 % of the DRAM peak - the
+    # codes are re-read from L2, hit rate 77 %; compulsory traffic is 5 GB).  Other shapes were not captured: null.
+    fp4_traffic = 425.21e9 if (args.workload == "cfg2" and n_gpus == 1) else None
     if variant == 3:
         # 5 exact E2M1 MACs = 10 ops per pair-site (xx, yy, yh, hy, hh) on the FP4 tensor path (kind::mxf4, unit block
         # scales, fp32 accumulation).  Peak = the dense FP4 rate measured on this pool's B200 by tools/umma_mxf4_probe.cu
@@ -372,7 +378,7 @@ def main():
         tops = my_units * 10.0 / (kernel_ms * 1e-3) / 1e12
         roofline = {
             "bound": "tensor", "kernel": "king_fp4_kernel", "achieved": tops, "peak": 8481.0, "unit": "TOP/s (fp4 e2m1, dense)",
-            "frac": tops / 8481.0, "traffic": None, "kernel_ms": kernel_ms, "units_per_launch": my_units,
+            "frac": tops / 8481.0, "traffic": fp4_traffic, "kernel_ms": kernel_ms, "units_per_launch": my_units,
             "algorithmic_per_unit": "10 fp4 ops (5 MACs: xx, yy, yh, hy, hh) per pair-site, fp32 accumulation (exact: counts < 2^21)",
             "peak_source": "measured: tools/umma_mxf4_probe.cu on this pool's B200 (profiles/r01_mxf4_probe.txt), "
                            "kind::mxf4 M=128 N=208, 15595 MAC/clk/SM = 8481 TOP/s at the burst clock (nominal dense fp4: 9000)",
