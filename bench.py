@@ -414,15 +414,10 @@ def main():
         host_bits = torch.from_numpy(bits_np).pin_memory()
         del bits_np
         h2d = host_bits.numel() * 8
-        if world == 1:
-            def e2e_step():
-                return ctx.king_host_bitset(n_samples, 1, 0, n_sites, host_bits, thr, max_results, out=results)
-        else:
-            # N > 1: every rank uploads the bit set and evaluates its tile slice (per-GPU host loading, no NCCL)
-            def e2e_step():
-                with ctx.planes(sm, n_sites) as pl:
-                    pl.import_bitset(host_bits)
-                    return pl.king(thr, max_results, sort=True, tiles=(t_begin, t_end), out=results)
+        # N > 1: every rank passes the same host bit set and its part index (per-GPU host loading, no NCCL); the library
+        # deals the bands of the pair matrix to the parts and overlaps each part's upload with its kernel
+        def e2e_step():
+            return ctx.king_host_bitset(n_samples, 1, 0, n_sites, host_bits, thr, max_results, out=results, part=(rank, world))
         e2e_step()  # warm-up (allocations)
         barrier()
         ev0.record(stream)
@@ -437,7 +432,8 @@ def main():
             e_ms = float(tmax.item())
         e2e = {"value": total_units / (e_ms / e2e_steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(len(r) * 24 + 8), "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps,
-               "api": "ck_king_host_bitset (pinned host bit set in the reference layout -> sorted KingResult[] on the host)"}
+               "api": ("ck_king_host_bitset" if world == 1 else f"ck_king_host_bitset_part (part r of {world} on GPU r)")
+                      + " (pinned host bit set in the reference layout -> sorted KingResult[] on the host)"}
         del host_bits
 
     cpu_baseline, ref_gpu, pack = None, None, None

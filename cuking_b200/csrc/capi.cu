@@ -783,8 +783,15 @@ static bool host_bitset_can_pipeline(const ck_planes *pl) {
   return !off && planes_variant(pl) == 3 && sm_diagonal(pl->map.sm) && sm_rows(pl->map.sm) >= 4 * kFp4BandRows;
 }
 
+// Owner of band b when the shard is split into num_parts parts: bands are dealt in snake order (0 .. P-1, P-1 .. 0, ...):
+// the tile count of a band falls linearly with its index, so every pair (g, 2P-1-g) of a group carries the same work.
+static uint32_t band_owner(uint32_t band, uint32_t num_parts) {
+  const uint32_t g = band % (2 * num_parts);
+  return g < num_parts ? g : 2 * num_parts - 1 - g;
+}
+
 static int king_host_bitset_pipelined(ck_planes *pl, const uint64_t *bit_set, float kin_threshold, uint32_t max_results,
-                                      ck_result *results, uint32_t *num_results) {
+                                      ck_result *results, uint32_t *num_results, uint32_t part_index, uint32_t num_parts) {
   if (!num_results) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
   if (max_results > 0 && !results) return fail(CK_ERR_INVALID_ARGUMENT, "results is NULL");
   *num_results = 0;
@@ -850,9 +857,15 @@ static int king_host_bitset_pipelined(ck_planes *pl, const uint64_t *bit_set, fl
     const uint32_t block0 = c.s0 / kTileSamples, num_blocks = ceil_div(c.s1, kTileSamples) - block0;
     CK_CUDA(launch_import_ref_range(*pl, static_cast<const uint64_t *>(st.p), block0, num_blocks, s));
     CK_CUDA(launch_finalize_codes_range(*pl, 3, block0, num_blocks, s));
-    k.tile_begin = band_prefix[c.band_lo];
-    k.tile_end = band_prefix[c.band_hi];
-    if (k.tile_end > k.tile_begin) CK_CUDA(launch_king_fp4(k, pl->map.num_blocks, ctx, s, &ctx->timings.king_launches));
+    for (uint32_t b = c.band_lo; b < c.band_hi;) {  // maximal runs of this part's bands (the whole chunk when num_parts == 1)
+      if (band_owner(b, num_parts) != part_index) { ++b; continue; }
+      uint32_t e = b + 1;
+      while (e < c.band_hi && band_owner(e, num_parts) == part_index) ++e;
+      k.tile_begin = band_prefix[b];
+      k.tile_end = band_prefix[e];
+      if (k.tile_end > k.tile_begin) CK_CUDA(launch_king_fp4(k, pl->map.num_blocks, ctx, s, &ctx->timings.king_launches));
+      b = e;
+    }
     ctx->timings.king_launches += 2;  // transpose + code kernels of the chunk
   }
   CK_CUDA(cudaEventRecord(ctx->ev[1], s));
@@ -868,7 +881,15 @@ static int king_host_bitset_pipelined(ck_planes *pl, const uint64_t *bit_set, fl
 int ck_king_host_bitset(ck_ctx *ctx, uint32_t num_samples, uint32_t split_factor, uint32_t shard_index,
                         uint32_t num_sites, const uint64_t *bit_set, float kin_threshold, uint32_t max_results,
                         ck_result *results, uint32_t *num_results) {
+  return ck_king_host_bitset_part(ctx, num_samples, split_factor, shard_index, num_sites, bit_set, kin_threshold,
+                                  max_results, results, num_results, 0, 1);
+}
+
+int ck_king_host_bitset_part(ck_ctx *ctx, uint32_t num_samples, uint32_t split_factor, uint32_t shard_index,
+                             uint32_t num_sites, const uint64_t *bit_set, float kin_threshold, uint32_t max_results,
+                             ck_result *results, uint32_t *num_results, uint32_t part_index, uint32_t num_parts) {
   if (!ctx || !bit_set || !num_results) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (num_parts == 0 || part_index >= num_parts) return fail(CK_ERR_INVALID_ARGUMENT, "part_index outside [0, num_parts)");
   ck_submatrix sm;
   int rc = ck_submatrix_init(num_samples, split_factor, shard_index, &sm);
   if (rc != CK_OK) return rc;
@@ -876,10 +897,14 @@ int ck_king_host_bitset(ck_ctx *ctx, uint32_t num_samples, uint32_t split_factor
   rc = ck_planes_create(ctx, &sm, num_sites, &pl);
   if (rc != CK_OK) return rc;
   if (host_bitset_can_pipeline(pl)) {
-    rc = king_host_bitset_pipelined(pl, bit_set, kin_threshold, max_results, results, num_results);
-  } else {
+    rc = king_host_bitset_pipelined(pl, bit_set, kin_threshold, max_results, results, num_results, part_index, num_parts);
+  } else {  // small or off-diagonal shards, other kernel variants: plain upload, contiguous slice of the tile grid
     rc = ck_planes_import_bitset(pl, bit_set, 0);
-    if (rc == CK_OK) rc = ck_king(pl, kin_threshold, max_results, results, 0, num_results, 1);
+    uint64_t tiles = 0;
+    if (rc == CK_OK) rc = ck_king_num_tiles(pl, &tiles);
+    if (rc == CK_OK)
+      rc = ck_king_tiles(pl, tiles * part_index / num_parts, tiles * (part_index + 1) / num_parts, kin_threshold, max_results,
+                         results, 0, num_results, 1);
   }
   ck_planes_destroy(pl);
   return rc;

@@ -95,15 +95,18 @@ class Context:
         return Planes(self, sm, num_sites)
 
     def king_host_bitset(self, n_samples: int, split_factor: int, shard_index: int, num_sites: int,
-                         bit_set, kin_threshold: float, max_results: int = 10 << 20, out: np.ndarray | None = None):
-        """The reference seam in one call with host buffers (ck_king_host_bitset): bit set in the reference layout
-        in, sorted KingResult records out.  `bit_set` may be a numpy array or a (pinned) CPU torch tensor."""
+                         bit_set, kin_threshold: float, max_results: int = 10 << 20, out: np.ndarray | None = None,
+                         part: tuple[int, int] = (0, 1)):
+        """The reference seam in one call with host buffers (ck_king_host_bitset[_part]): bit set in the reference
+        layout in, sorted KingResult records out.  `bit_set` may be a numpy array or a (pinned) CPU torch tensor;
+        `part = (index, count)` evaluates one of `count` disjoint parts of the shard (one per GPU of a box)."""
         addr, on_device = _ptr(bit_set)
         assert not on_device
         res = out if out is not None else np.empty(max_results, dtype=RESULT_DTYPE)
         n = C.c_uint32(0)
-        check(self._lib.ck_king_host_bitset(self._h, n_samples, split_factor, shard_index, num_sites, addr,
-                                            C.c_float(kin_threshold), max_results, res.ctypes.data, C.byref(n)))
+        check(self._lib.ck_king_host_bitset_part(self._h, n_samples, split_factor, shard_index, num_sites, addr,
+                                                 C.c_float(kin_threshold), max_results, res.ctypes.data, C.byref(n),
+                                                 part[0], part[1]))
         return res[: n.value]
 
     def synth_triples_device(self, seed: int, missing_rate: float, sample_begin: int, sample_end: int,

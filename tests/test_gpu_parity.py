@@ -277,6 +277,17 @@ def test_host_bitset_pipelined_upload_matches_oracle(ctx):
         assert_results_equal(got, want)
     with pytest.raises(ck.CukingError):
         ctx.king_host_bitset(n, 1, 0, s, bs, 0.1, count - 1)  # overflow is still the reference's error
+    # the multi-GPU form: disjoint parts whose union is the whole result (here all on one GPU)
+    for parts in (2, 3):
+        got = np.concatenate([ctx.king_host_bitset(n, 1, 0, s, bs, 0.1, 1 << 20, part=(p, parts)) for p in range(parts)])
+        assert len(got) == count
+        assert_results_equal(np.sort(got, order=["sample_i", "sample_j"]), want)
+    small = ko.submatrix(300, 2, 1)  # off-diagonal and small: the plain path, contiguous tile slices
+    g2 = random_genotypes(rng, 300, s)
+    bs2 = oracle_bitset(g2, small)
+    want2, _, _ = ko.king(bs2, s, small, 0.05, 1 << 16)
+    got2 = np.concatenate([ctx.king_host_bitset(300, 2, 1, s, bs2, 0.05, 1 << 16, part=(p, 2)) for p in range(2)])
+    assert_results_equal(np.sort(got2, order=["sample_i", "sample_j"]), want2)
 
 
 # ---- synthetic cohort ------------------------------------------------------------------------------------------
