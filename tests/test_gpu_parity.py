@@ -414,3 +414,97 @@ def test_baseline_shape_properties(ctx):
     got["sample_i"] -= ids[0]
     got["sample_j"] -= ids[0]
     assert_results_equal(got, want)
+
+
+# ---- the other BASELINE.json configs at their real shard shapes -------------------------------------------------------
+# One shard of each (what one GPU holds), synthetic cohort of SURVEY.md §8d generated on the device; the whole result
+# is checked through structure, the records of a sample of retained pairs and ONE whole rectangle of the pair matrix
+# against the oracle run on the same cohort regenerated on the host.
+
+
+def _check_shard_against_oracle(res, n_sites, thr, seed, miss, block_rows, block_cols, sampled=32):
+    assert np.all(res["sample_i"] < res["sample_j"]) and np.all(res["kin"] > np.float32(thr))
+    key = res["sample_i"].astype(np.int64) << 32 | res["sample_j"].astype(np.int64)
+    assert np.all(np.diff(key) > 0)  # sorted by (i, j), no duplicates
+
+    def genotypes(a, b):
+        return ck.synth_genotypes_host(seed, miss, a, b, 0, n_sites)
+
+    # (1) records of a sample of retained pairs, recomputed by the oracle
+    rng = np.random.default_rng(len(res))
+    for q in rng.choice(len(res), min(sampled, len(res)), replace=False):
+        r = res[q]
+        g = np.concatenate([genotypes(int(r["sample_i"]), int(r["sample_i"]) + 1), genotypes(int(r["sample_j"]), int(r["sample_j"]) + 1)])
+        bs, _ = ko.pack_dense(g)
+        c, kin = ko.pair_counts(bs, n_sites, 0, 1)
+        assert (int(r["ibs0"]), int(r["ibs2"])) == (c["opposing_hom"], c["concordant_hom"] + c["both_het"])
+        assert int(r["ibs1"]) == c["shared_sites"] - int(r["ibs0"]) - int(r["ibs2"])
+        assert bits_equal_f32([r["kin"]], [kin])
+    # (2) one whole rectangle rows x cols (disjoint ranges, rows before cols): exact retained set and records
+    (r0, r1), (c0, c1) = block_rows, block_cols
+    assert r1 <= c0
+    g = np.concatenate([genotypes(r0, r1), genotypes(c0, c1)])
+    nr = r1 - r0
+    osm = ko.Submatrix(0, nr, nr, nr + (c1 - c0))
+    want, _, ovf = ko.king(oracle_bitset(g, osm), n_sites, osm, thr, 1 << 22)
+    assert not ovf
+    sel = (res["sample_i"] >= r0) & (res["sample_i"] < r1) & (res["sample_j"] >= c0) & (res["sample_j"] < c1)
+    got = res[sel].copy()
+    got["sample_i"] -= r0
+    got["sample_j"] -= c0 - nr
+    assert_results_equal(got, want)
+    return len(want)
+
+
+def test_cfg3_shapes_300k_samples_split_factor_4(ctx):
+    # BASELINE.json configs[2]: 300,000 samples x 100,000 sites, split_factor 4 -> 75,000-sample blocks.
+    n, s, seed, miss = 300_000, 100_000, 42, 0.01
+    # diagonal shard 4 (block 1 x block 1), the config's threshold
+    sm = ck.submatrix(n, 4, 4)
+    assert (sm.i_begin, sm.i_end, sm.j_begin, sm.j_end) == (75_000, 150_000, 75_000, 150_000)
+    with ctx.planes(sm, s) as pl:
+        pl.synthesize(seed, miss)
+        res = pl.king(0.05, 10 << 20)
+    assert np.all(res["sample_i"] // 8 == res["sample_j"] // 8) and len(res) >= 12 * (75_000 // 8)
+    assert _check_shard_against_oracle(res, s, 0.05, seed, miss, (100_000, 100_124), (100_124, 100_256)) > 0  # splits a pedigree
+    # off-diagonal shard 1 (block 0 x block 1): no planted relatives there, so a threshold four standard deviations
+    # above the unrelated mean keeps ~1e5 chance pairs whose set and records must still be exact
+    sm = ck.submatrix(n, 4, 1)
+    assert (sm.i_begin, sm.i_end, sm.j_begin, sm.j_end) == (0, 75_000, 75_000, 150_000)
+    with ctx.planes(sm, s) as pl:
+        pl.synthesize(seed, miss)
+        res = pl.king(0.011, 10 << 20)
+    assert 1_000 < len(res) < (10 << 20)
+    assert res["sample_i"].max() < 75_000 <= res["sample_j"].min()
+    _check_shard_against_oracle(res, s, 0.011, seed, miss, (31_000, 31_256), (140_000, 140_256))
+
+
+def test_cfg4_shape_1m_samples_5pct_missing(ctx):
+    # BASELINE.json configs[3]: 1,000,000 samples x 100,000 sites, 5 % missing, threshold 0.0442; with 8 x 8 blocks of
+    # 125,000 samples a GPU holds one block pair at a time: the last diagonal shard (ragged against nothing, but at the
+    # far end of the index range) and one off-diagonal shard.
+    n, s, seed, miss, thr = 1_000_000, 100_000, 42, 0.05, 0.0442
+    last = ck.num_shards(8) - 1
+    sm = ck.submatrix(n, 8, last)
+    assert (sm.i_begin, sm.i_end, sm.j_begin, sm.j_end) == (875_000, 1_000_000, 875_000, 1_000_000)
+    with ctx.planes(sm, s) as pl:
+        pl.synthesize(seed, miss)
+        res = pl.king(thr, 10 << 20)
+    assert np.all(res["sample_i"] // 8 == res["sample_j"] // 8) and len(res) >= 12 * (125_000 // 8)
+    assert _check_shard_against_oracle(res, s, thr, seed, miss, (999_744, 999_868), (999_868, 1_000_000)) > 0  # splits a pedigree
+
+
+def test_cfg5_shape_dense_output_1m_sites(ctx):
+    # BASELINE.json configs[4] (50,000 samples x 1,000,000 sites, threshold -1: every pair is emitted), one diagonal
+    # shard of split_factor 16: 3,125 samples -> 4.9e6 records, each the sum of 10^6 sites.
+    n, s, seed, miss = 50_000, 1_000_000, 42, 0.01
+    sm = ck.submatrix(n, 16, ck.num_shards(16) - 1)
+    rows = sm.i_end - sm.i_begin
+    assert rows == 3_125
+    with ctx.planes(sm, s) as pl:
+        pl.synthesize(seed, miss)
+        assert pl.king_variant() == 3
+        res = pl.king(-1.0, rows * (rows - 1) // 2)
+    assert len(res) == rows * (rows - 1) // 2  # the synthetic cohort has hets everywhere: every kinship is finite
+    assert np.all(res["ibs0"].astype(np.int64) + res["ibs1"] + res["ibs2"] <= s)
+    _check_shard_against_oracle(res, s, -1.0, seed, miss, (sm.i_begin + 1_000, sm.i_begin + 1_032), (sm.i_begin + 2_000, sm.i_begin + 2_032), sampled=8)
