@@ -22,9 +22,8 @@ __global__ void fill_missing_kernel(uint4 *raw4, size_t n4) {
 }
 
 // ---- pack -----------------------------------------------------------------------------------------------------
-// One triple per thread per iteration, loads vectorised two triples at a time when the arrays allow it.  For
-// Hail-ordered input (site-major, sample-minor) the 32 lanes of a warp hit 32 consecutive words of one
-// (block, word, plane) row, i.e. each RED.AND warp instruction touches one or two 128-byte lines.
+// One triple per lane per load.  For Hail-ordered input (site-major, sample-minor) the 32 lanes of a warp hit 32
+// consecutive words of one (block, word, plane) row, i.e. each RED.AND warp instruction touches one 128-byte line.
 __device__ __forceinline__ void pack_one(uint32_t *raw, const SlotMap &map, uint32_t words, uint32_t num_sites,
                                          int64_t row64, int64_t col64, int32_t n_alt, size_t index, uint32_t *err) {
   const uint32_t col = uint32_t(int32_t(col64));                     // cuking.cu:676
@@ -49,26 +48,29 @@ __device__ __forceinline__ void pack_one(uint32_t *raw, const SlotMap &map, uint
 __global__ void __launch_bounds__(256) pack_kernel(uint32_t *raw, SlotMap map, uint32_t words, uint32_t num_sites,
                                                    const int64_t *__restrict__ row, const int64_t *__restrict__ col,
                                                    const int32_t *__restrict__ alt, size_t n, size_t index_base,
-                                                   uint32_t *err, int vec_ok) {
+                                                   uint32_t *err) {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (vec_ok) {
-    const size_t n2 = n / 2;
-    const longlong2 *row2 = reinterpret_cast<const longlong2 *>(row);
-    const longlong2 *col2 = reinterpret_cast<const longlong2 *>(col);
-    const int2 *alt2 = reinterpret_cast<const int2 *>(alt);
-    for (size_t i = tid; i < n2; i += stride) {
-      const longlong2 r = __ldcs(row2 + i);  // streaming: every triple is read exactly once
-      const longlong2 c = __ldcs(col2 + i);
-      const int2 a = __ldcs(alt2 + i);
-      pack_one(raw, map, words, num_sites, r.x, c.x, a.x, index_base + 2 * i, err);
-      pack_one(raw, map, words, num_sites, r.y, c.y, a.y, index_base + 2 * i + 1, err);
+  // One triple per lane per load group, kUnroll independent groups (20 B each) in flight per thread before the first
+  // atomic: the kernel is latency-bound (78 % long-scoreboard stalls with one group per iteration,
+  // profiles/r01_pack_kernel_ncu.txt).  Lane-contiguous triples keep both sides coalesced: a warp's loads are whole
+  // 256 / 256 / 128-byte runs, and for Hail-ordered input its RED.AND hits 32 consecutive words = one 128-byte line
+  // (two triples per lane - 16-byte loads - made every RED touch two lines at half sector efficiency).
+  constexpr int kUnroll = 8;
+  size_t i = tid;
+  for (; i + (kUnroll - 1) * stride < n; i += kUnroll * stride) {
+    int64_t r[kUnroll], c[kUnroll];
+    int32_t a[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      r[u] = __ldcs(row + i + u * stride);  // streaming: every triple is read exactly once
+      c[u] = __ldcs(col + i + u * stride);
+      a[u] = __ldcs(alt + i + u * stride);
     }
-    if ((n & 1) && tid == 0) pack_one(raw, map, words, num_sites, row[n - 1], col[n - 1], alt[n - 1], index_base + n - 1, err);
-  } else {
-    for (size_t i = tid; i < n; i += stride)
-      pack_one(raw, map, words, num_sites, row[i], col[i], alt[i], index_base + i, err);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) pack_one(raw, map, words, num_sites, r[u], c[u], a[u], index_base + i + u * stride, err);
   }
+  for (; i < n; i += stride) pack_one(raw, map, words, num_sites, __ldcs(row + i), __ldcs(col + i), __ldcs(alt + i), index_base + i, err);
 }
 
 // ---- finalize: raw (het, alt) -> compute (H, D, A) --------------------------------------------------------------
@@ -271,10 +273,8 @@ cudaError_t launch_fill_missing(uint32_t *raw, size_t num_words, cudaStream_t s)
 cudaError_t launch_pack(const ck_planes &pl, const int64_t *row, const int64_t *col, const int32_t *alt, size_t n,
                         size_t index_base, uint32_t *d_err, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
-  const int vec_ok = (reinterpret_cast<uintptr_t>(row) % 16 == 0) && (reinterpret_cast<uintptr_t>(col) % 16 == 0) &&
-                     (reinterpret_cast<uintptr_t>(alt) % 8 == 0);
-  pack_kernel<<<grid_for(vec_ok ? n / 2 + 1 : n, 256, 148 * 16), 256, 0, s>>>(pl.raw, pl.map, pl.words, pl.num_sites,
-                                                                            row, col, alt, n, index_base, d_err, vec_ok);
+  pack_kernel<<<grid_for(n / 8 + 1, 256, 148 * 8), 256, 0, s>>>(pl.raw, pl.map, pl.words, pl.num_sites, row, col, alt, n,
+                                                              index_base, d_err);
   return cudaGetLastError();
 }
 
