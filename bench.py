@@ -407,7 +407,7 @@ def main():
                         units_per_launch=my_units, hbm=hbm_view)
 
     # ---- e2e: host buffers through the reference-facing C-ABI call (rank-local slice is the whole shard at N=1) ----
-    e2e = None
+    e2e, exchange = None, None
     e2e_steps = args.steps if args.e2e_steps < 0 else args.e2e_steps
     if e2e_steps > 0:
         bits_np = planes.export_bitset()  # reference layout (cuking.cu:507-523), built once outside the timed region
@@ -434,6 +434,39 @@ def main():
                "d2h_bytes_per_step": int(len(r) * 24 + 8), "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps,
                "api": ("ck_king_host_bitset" if world == 1 else f"ck_king_host_bitset_part (part r of {world} on GPU r)")
                       + " (pinned host bit set in the reference layout -> sorted KingResult[] on the host)"}
+        # north_star: replicate the planes with an NCCL broadcast over NVLink "only if it beats per-GPU host loading".
+        # Measured here on the e2e call's own bytes: (a) every rank copies the whole pinned bit set to its GPU at the
+        # same time (what ck_king_host_bitset_part does, hidden behind its kernel), (b) rank 0 alone copies it,
+        # (c) rank 0 broadcasts the device copy to the other GPUs.  Device-timed, max over ranks.
+        if distributed:
+            hb = host_bits.view(torch.int64)
+            dbuf = torch.empty_like(hb, device=dev)
+
+            def timed(fn, reps=2):
+                fn()  # warm-up (NCCL channel setup, page-locking checks)
+                barrier()
+                ev0.record(stream)
+                for _ in range(reps):
+                    fn()
+                ev1.record(stream)
+                barrier()
+                t = torch.tensor([ev0.elapsed_time(ev1) / reps], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t.item())
+
+            all_ms = timed(lambda: dbuf.copy_(hb, non_blocking=True))
+            one_ms = timed(lambda: dbuf.copy_(hb, non_blocking=True) if rank == 0 else None)
+            bcast_ms = timed(lambda: dist.broadcast(dbuf, src=0))
+            gb = h2d / 1e9
+            exchange = {
+                "bytes": int(h2d), "per_gpu_host_load_ms": all_ms, "per_gpu_host_load_gbs_each": gb / (all_ms * 1e-3),
+                "single_gpu_host_load_ms": one_ms, "nccl_broadcast_ms": bcast_ms, "nccl_broadcast_gbs": gb / (bcast_ms * 1e-3),
+                "load_once_then_broadcast_ms": one_ms + bcast_ms,
+                "decision": "per-GPU host loading: the upload is overlapped with the pairwise kernel in ck_king_host_bitset_part "
+                            "(e2e within a few percent of the resident value), so neither option is on the critical path; "
+                            "load-once-then-broadcast would only pay off for an exposed upload",
+            }
+            del dbuf, hb
         del host_bits
 
     cpu_baseline, ref_gpu, pack = None, None, None
@@ -466,7 +499,7 @@ def main():
                 "input_synthesis_s": round(synth_s, 3),
             },
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "reference_gpu_kernel": ref_gpu, "pack": pack,
+            "reference_gpu_kernel": ref_gpu, "pack": pack, "plane_exchange": exchange,
         }
         print(json.dumps(line), flush=True)
     planes.close()
