@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     const uint4 *src = reinterpret_cast<const uint4 *>(p.codes) + (size_t(blk) * p.words + half) * kTileSamples + ln;
     const uint32_t b_off = (srow >> 3) * G::kSBO + (srow & 7) * 16 + half * kFLBO;
     const uint32_t num_subs = num_steps / kFSub;
+    const uint32_t smem_base = smem_u32(smem);
     constexpr uint32_t kSubsPerStage = BS / kFSub;
     uint4 z[kFBPrefetch][kFSub];
     auto load_sub = [&](uint32_t m, uint4 (&dst)[kFSub]) {
@@ -280,12 +281,12 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
         const unsigned long long p1 = FPROF_T();
         if (sub == 0 && fill > 0) mbar_wait_suspend(&empty_b[s], (fill - 1) & 1u);  // the MMAs that read this stage have completed
         const unsigned long long p2 = FPROF_T();
-        uint8_t *stage = smem + size_t(s) * G::kStageBytes + b_off + sub * kFSub * 2 * kFLBO;
+        const uint32_t stage = smem_base + s * G::kStageBytes + b_off + sub * kFSub * 2 * kFLBO;
 #pragma unroll
         for (uint32_t q = 0; q < kFSub; ++q) {
-          *reinterpret_cast<uint4 *>(stage + q * 2 * kFLBO) = make_uint4(x[q][0], x[q][1], x[q][2], x[q][3]);
-          *reinterpret_cast<uint4 *>(stage + G::kTile + q * 2 * kFLBO) = make_uint4(y[q][0], y[q][1], y[q][2], y[q][3]);
-          *reinterpret_cast<uint4 *>(stage + 2 * G::kTile + q * 2 * kFLBO) = make_uint4(h[q][0], h[q][1], h[q][2], h[q][3]);
+          sts128(stage + q * 2 * kFLBO, x[q][0], x[q][1], x[q][2], x[q][3]);
+          sts128(stage + G::kTile + q * 2 * kFLBO, y[q][0], y[q][1], y[q][2], y[q][3]);
+          sts128(stage + 2 * G::kTile + q * 2 * kFLBO, h[q][0], h[q][1], h[q][2], h[q][3]);
         }
         if (sub == kSubsPerStage - 1) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (tensor core)

@@ -36,6 +36,11 @@ __device__ __forceinline__ void tmem_store8(uint32_t taddr, const uint32_t (&v)[
                "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+// 16-byte shared-memory store by 32-bit shared address.  Through a generic pointer the compiler emitted ST.E.128 and
+// split some of the stores into 32- and 64-bit pieces (22 % extra wavefronts, profiles/r01_king_fp4_cfg2_ncu.txt).
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tcgen05_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ uint32_t elect_one() {
