@@ -47,7 +47,10 @@ WORKLOADS = {
     "mid": (20_000, 100_000, 0.01, 0.0884),     # quick smoke of the bench itself
     "prof": (8_192, 100_000, 0.01, 0.0884),     # short kernel for ncu captures (profiles/)
     "cfg5": (50_000, 1_000_000, 0.01, -1.0),    # BASELINE.json configs[4]: dense output, every finite-kin pair is emitted
+    "cfg4": (1_000_000, 100_000, 0.05, 0.0442), # BASELINE.json configs[3]: fixed cohort at every N (strong scaling): its
+                                                # ms_per_step is the metric's "wall-time for 1M x 100k"
 }
+FIXED_SIZE = {"cfg4"}
 
 
 def parse_args():
@@ -274,7 +277,8 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     n1, n_sites, missing, thr = WORKLOADS[args.workload]
-    n_samples = int(round(n1 * (n_gpus ** 0.5) / 64.0)) * 64 if n_gpus > 1 else n1  # weak scaling: pairs ~ N
+    fixed = args.workload in FIXED_SIZE
+    n_samples = int(round(n1 * (n_gpus ** 0.5) / 64.0)) * 64 if (n_gpus > 1 and not fixed) else n1  # weak scaling: pairs ~ N
     max_results = 10 << 20  # the reference's default --max_results (cuking.cu:40)
     if thr < 0:  # dense-output stress: room for every pair of this rank's slice
         max_results = int(n_samples * (n_samples - 1) // 2 // max(1, n_gpus) * 1.02) + 1024
@@ -487,13 +491,14 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if fixed else "weak", "vs_baseline": None,
             "dtype": {3: "fp4 (e2m1 indicators, exact fp32 accumulation)", 2: "int8 (indicators, s32 accumulation)"}.get(variant, "u32 (bit planes, LOP3+POPC)"),
             "data": "synthetic",
             "config": {
                 "workload": f"{args.workload}: {n_samples} samples x {n_sites} sites, missing {missing}, "
                             f"kin_threshold {thr}, max_results {max_results}"
-                            + (f" (weak scaling: {n1}*sqrt({n_gpus}) samples, tile grid split over {n_gpus} GPUs)" if n_gpus > 1 else ""),
+                            + ((f" (fixed cohort, tile grid split over {n_gpus} GPUs)" if fixed else
+                                f" (weak scaling: {n1}*sqrt({n_gpus}) samples, tile grid split over {n_gpus} GPUs)") if n_gpus > 1 else ""),
                 "tiles": tiles, "retained_pairs": retained, "kernel_variant": variant,
                 "l2": f"inputs larger than L2: {planes.device_bytes() * 3 // 5 >> 20} MiB of compute planes streamed per step",
                 "input_synthesis_s": round(synth_s, 3),
