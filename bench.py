@@ -64,6 +64,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the host-buffer leg (-1 = same as --steps, 0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--clock-sample-ms", type=float, default=200.0, help="NVML sampling period during the timed region (0 = off)")
+    ap.add_argument("--e2e-mode", choices=["allgather", "host"], default="allgather",
+                    help="N > 1 host-buffer leg: planes replicated by NCCL all-gather (default) or N full host uploads")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-ref-gpu", action="store_true")
     return ap.parse_args()
@@ -269,7 +271,9 @@ def main():
         import torch.distributed as dist
 
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL kernels of the plane replication run beside the pairwise kernel, which fills every SM: give them priority
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
         assert world == n_gpus, f"--gpus {n_gpus} but WORLD_SIZE={world}"
     elif n_gpus != 1:
         raise SystemExit("for --gpus N > 1 launch with torchrun (one rank per GPU)")
@@ -418,10 +422,21 @@ def main():
         host_bits = torch.from_numpy(bits_np).pin_memory()
         del bits_np
         h2d = host_bits.numel() * 8
-        # N > 1: every rank passes the same host bit set and its part index (per-GPU host loading, no NCCL); the library
-        # deals the bands of the pair matrix to the parts and overlaps each part's upload with its kernel
-        def e2e_step():
-            return ctx.king_host_bitset(n_samples, 1, 0, n_sites, host_bits, thr, max_results, out=results, part=(rank, world))
+        # N = 1: ck_king_host_bitset (upload overlapped with the kernel).  N > 1: the same schedule with the planes
+        # replicated over NVLink (every rank uploads 1/N of each chunk through its own PCIe link, NCCL all-gather,
+        # ck_king_stream_rows) - or, with --e2e-mode host, N independent full uploads through ck_king_host_bitset_part.
+        allgather = world > 1 and args.e2e_mode == "allgather"
+        if allgather:
+            from cuking_b200.distributed import king_host_bitset_allgather
+            side = torch.cuda.Stream(dev, priority=-1)
+
+            def e2e_step():
+                with ctx.planes(sm, n_sites) as pl:
+                    return king_host_bitset_allgather(pl, host_bits, ck.words_per_sample(n_sites), thr, max_results,
+                                                      out=results, side_stream=side)
+        else:
+            def e2e_step():
+                return ctx.king_host_bitset(n_samples, 1, 0, n_sites, host_bits, thr, max_results, out=results, part=(rank, world))
         e2e_step()  # warm-up (allocations)
         barrier()
         ev0.record(stream)
@@ -434,9 +449,12 @@ def main():
             tmax = torch.tensor([e_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             e_ms = float(tmax.item())
-        e2e = {"value": total_units / (e_ms / e2e_steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+        e2e = {"value": total_units / (e_ms / e2e_steps * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d // world) if allgather else int(h2d),  # per rank
                "d2h_bytes_per_step": int(len(r) * 24 + 8), "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps,
-               "api": ("ck_king_host_bitset" if world == 1 else f"ck_king_host_bitset_part (part r of {world} on GPU r)")
+               "api": ("ck_king_host_bitset" if world == 1 else
+                       f"ck_king_stream_* fed by 1/{world} uploads + NCCL all-gather (cuking_b200.distributed.king_host_bitset_allgather)"
+                       if allgather else f"ck_king_host_bitset_part (part r of {world} on GPU r)")
                       + " (pinned host bit set in the reference layout -> sorted KingResult[] on the host)"}
         # north_star: replicate the planes with an NCCL broadcast over NVLink "only if it beats per-GPU host loading".
         # Measured here on the e2e call's own bytes: (a) every rank copies the whole pinned bit set to its GPU at the
@@ -466,9 +484,9 @@ def main():
                 "bytes": int(h2d), "per_gpu_host_load_ms": all_ms, "per_gpu_host_load_gbs_each": gb / (all_ms * 1e-3),
                 "single_gpu_host_load_ms": one_ms, "nccl_broadcast_ms": bcast_ms, "nccl_broadcast_gbs": gb / (bcast_ms * 1e-3),
                 "load_once_then_broadcast_ms": one_ms + bcast_ms,
-                "decision": "per-GPU host loading: the upload is overlapped with the pairwise kernel in ck_king_host_bitset_part "
-                            "(e2e within a few percent of the resident value), so neither option is on the critical path; "
-                            "load-once-then-broadcast would only pay off for an exposed upload",
+                "decision": "at N = 2 concurrent per-GPU host loading matches a single load; at N = 8 it is host-limited (about 23 GB/s "
+                            "per GPU) and replication over NVLink wins, so the e2e leg uploads 1/N of every chunk per GPU and "
+                            "all-gathers it (king_host_bitset_allgather); both are overlapped with the pairwise kernel",
             }
             del dbuf, hb
         del host_bits

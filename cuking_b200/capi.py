@@ -65,7 +65,8 @@ EXPORTED_SYMBOLS = [
     "ck_ctx_set_king_variant", "ck_ctx_synchronize", "ck_ctx_get_timings", "ck_measure_int_peaks", "ck_ctx_destroy", "ck_planes_create",
     "ck_planes_reset", "ck_planes_destroy", "ck_planes_finalize", "ck_planes_num_sites", "ck_planes_device_bytes",
     "ck_pack_triples", "ck_host_alloc", "ck_host_free", "ck_planes_import_bitset", "ck_planes_export_bitset", "ck_planes_synthesize", "ck_king",
-    "ck_king_num_tiles", "ck_planes_king_variant", "ck_king_tiles", "ck_king_counts", "ck_king_host_bitset", "ck_king_host_bitset_part", "ck_synth_genotypes_host",
+    "ck_king_num_tiles", "ck_planes_king_variant", "ck_king_tiles", "ck_king_counts", "ck_king_host_bitset", "ck_king_host_bitset_part", "ck_king_stream_granularity", "ck_king_stream_begin",
+    "ck_king_stream_rows", "ck_king_stream_end", "ck_synth_genotypes_host",
     "ck_synth_triples_device",
 ]
 
@@ -107,6 +108,8 @@ def load() -> C.CDLL:
         "ck_king_counts": ([vp, vp, vp, C.c_size_t, vp, vp], i32),
         "ck_king_host_bitset": ([vp, u32, u32, u32, u32, vp, f32, u32, vp, C.POINTER(u32)], i32),
         "ck_king_host_bitset_part": ([vp, u32, u32, u32, u32, vp, f32, u32, vp, C.POINTER(u32), u32, u32], i32),
+        "ck_king_stream_granularity": ([], u32), "ck_king_stream_begin": ([vp, f32, u32, u32, u32], i32),
+        "ck_king_stream_rows": ([vp, vp, i32, u32, u32], i32), "ck_king_stream_end": ([vp, vp, C.POINTER(u32)], i32),
         "ck_synth_genotypes_host": ([C.POINTER(SynthParams), u32, u32, u32, u32, vp], i32),
         "ck_synth_triples_device": ([vp, C.POINTER(SynthParams), u32, u32, u32, u32, C.POINTER(vp), C.POINTER(vp),
                                      C.POINTER(vp), C.POINTER(C.c_size_t)], i32),

@@ -310,6 +310,11 @@ int ck_planes_reset(ck_planes *pl) {
 }
 
 int ck_planes_destroy(ck_planes *pl) {
+  if (pl && pl->stream_state) {
+    cudaStreamSynchronize(pl->ctx->stream);
+    delete pl->stream_state;
+    pl->stream_state = nullptr;
+  }
   if (!pl) return CK_OK;
   DeviceGuard guard(pl->ctx->device);
   cudaStreamSynchronize(pl->ctx->stream);
@@ -790,6 +795,91 @@ static uint32_t band_owner(uint32_t band, uint32_t num_parts) {
   return g < num_parts ? g : 2 * num_parts - 1 - g;
 }
 
+}  // extern "C"
+
+static int stream_begin_impl(ck_planes *pl, float kin_threshold, uint32_t max_results, uint32_t part_index, uint32_t num_parts) {
+  ck_ctx *ctx = pl->ctx;
+  if (num_parts == 0 || part_index >= num_parts) return fail(CK_ERR_INVALID_ARGUMENT, "part_index outside [0, num_parts)");
+  if (!sm_diagonal(pl->map.sm)) return fail(CK_ERR_INVALID_ARGUMENT, "streaming delivery needs a diagonal shard");
+  if (planes_variant(pl) != 3) return fail(CK_ERR_INVALID_ARGUMENT, "streaming delivery needs the mxf4 kernel (variant 3, at most 2^21 sites)");
+  if (pl->stream_state) return fail(CK_ERR_INVALID_ARGUMENT, "a stream session is already open on these planes");
+  if (pl->codes == nullptr) {
+    pl->codes_bytes = std::max<size_t>(pl->codes_words(), 1) * 4;
+    CK_CUDA(ctx_alloc(ctx, reinterpret_cast<void **>(&pl->codes), pl->codes_bytes));
+  }
+  int rc = ensure_result_buf(ctx, max_results);
+  if (rc != CK_OK) return rc;
+  KingStream *st = new (std::nothrow) KingStream();
+  if (!st) return fail(CK_ERR_OUT_OF_MEMORY, "host allocation failed");
+  st->k = base_launch(pl);
+  st->k.kin_threshold = kin_threshold;
+  st->k.max_results = max_results;
+  st->k.results = ctx->result_buf;
+  st->k.counter = ctx->d_counter;
+  st->part_index = part_index;
+  st->num_parts = num_parts;
+  st->max_results = max_results;
+  st->next_end = sm_rows(pl->map.sm);
+  cudaError_t e = king_fp4_prepare(st->k, ctx, ctx->stream, &st->band_prefix);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream);
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[0], ctx->stream);
+  if (e != cudaSuccess) {
+    delete st;
+    return fail_cuda(e, "ck_king_stream_begin", __FILE__, __LINE__);
+  }
+  ctx->timings.king_launches = 0;
+  pl->mark_stale();
+  pl->stream_state = st;
+  return CK_OK;
+}
+
+// Rows [s0, s1) of the shard, in device memory behind d_rows: transpose, derive the codes, launch this part's bands among
+// them.  Everything is queued on the ctx stream; nothing is synchronised.
+static int stream_rows_device(ck_planes *pl, const uint64_t *d_rows, uint32_t s0, uint32_t s1) {
+  KingStream *st = pl->stream_state;
+  ck_ctx *ctx = pl->ctx;
+  cudaStream_t s = ctx->stream;
+  const uint32_t n = sm_rows(pl->map.sm);
+  if (s1 != st->next_end || s0 >= s1 || s0 % kFp4BandRows != 0)
+    return fail(CK_ERR_INVALID_ARGUMENT, "stream rows must arrive in descending ranges that tile the shard at multiples of "
+                                         "ck_king_stream_granularity()");
+  const uint32_t block0 = s0 / kTileSamples, num_blocks = ceil_div(s1, kTileSamples) - block0;
+  CK_CUDA(launch_import_ref_range(*pl, d_rows, s0, block0, num_blocks, s));
+  CK_CUDA(launch_finalize_codes_range(*pl, 3, block0, num_blocks, s));
+  ctx->timings.king_launches += 2;
+  const uint32_t band_lo = s0 / kFp4BandRows, band_hi = ceil_div(std::min(s1, n), kFp4BandRows);
+  KingLaunch k = st->k;
+  for (uint32_t b = band_lo; b < band_hi;) {  // maximal runs of this part's bands (the whole range when num_parts == 1)
+    if (band_owner(b, st->num_parts) != st->part_index) { ++b; continue; }
+    uint32_t e = b + 1;
+    while (e < band_hi && band_owner(e, st->num_parts) == st->part_index) ++e;
+    k.tile_begin = st->band_prefix[b];
+    k.tile_end = st->band_prefix[e];
+    if (k.tile_end > k.tile_begin) CK_CUDA(launch_king_fp4(k, pl->map.num_blocks, ctx, s, &ctx->timings.king_launches));
+    b = e;
+  }
+  st->next_end = s0;
+  return CK_OK;
+}
+
+static int stream_end_impl(ck_planes *pl, ck_result *results, uint32_t *num_results) {
+  KingStream *st = pl->stream_state;
+  ck_ctx *ctx = pl->ctx;
+  const bool complete = st->next_end == 0;
+  const uint32_t max_results = st->max_results;
+  delete st;
+  pl->stream_state = nullptr;
+  CK_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (!complete) {
+    cudaStreamSynchronize(ctx->stream);
+    return fail(CK_ERR_INVALID_ARGUMENT, "ck_king_stream_end before every row of the shard was delivered");
+  }
+  pl->compute_stale = true;
+  pl->codes_stale = false;
+  pl->codes_kind = 3;
+  return finish_results(ctx, ctx->result_buf, max_results, results, 0, num_results, 1);
+}
+
 static int king_host_bitset_pipelined(ck_planes *pl, const uint64_t *bit_set, float kin_threshold, uint32_t max_results,
                                       ck_result *results, uint32_t *num_results, uint32_t part_index, uint32_t num_parts) {
   if (!num_results) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -813,20 +903,9 @@ static int king_host_bitset_pipelined(ck_planes *pl, const uint64_t *bit_set, fl
   } st{ctx};
   CK_CUDA(ctx_alloc(ctx, &st.p, bytes));
   st.bytes = bytes;
-  if (pl->codes == nullptr) {
-    pl->codes_bytes = std::max<size_t>(pl->codes_words(), 1) * 4;
-    CK_CUDA(ctx_alloc(ctx, reinterpret_cast<void **>(&pl->codes), pl->codes_bytes));
-  }
-  int rc = ensure_result_buf(ctx, max_results);
+  int rc = stream_begin_impl(pl, kin_threshold, max_results, part_index, num_parts);
   if (rc != CK_OK) return rc;
-  KingLaunch k = base_launch(pl);
-  k.kin_threshold = kin_threshold;
-  k.max_results = max_results;
-  k.results = ctx->result_buf;
-  k.counter = ctx->d_counter;
-  std::vector<uint64_t> band_prefix;
-  CK_CUDA(king_fp4_prepare(k, ctx, s, &band_prefix));
-  const uint32_t num_bands = uint32_t(band_prefix.size()) - 1;
+  const uint32_t num_bands = ceil_div(n, kFp4BandRows);
   const uint32_t chunk_bands = std::max<uint32_t>(1, ceil_div(num_bands, 24u));
 
   // the copy stream starts after everything already queued on the compute stream (the buffers come from the ctx cache)
@@ -835,11 +914,11 @@ static int king_host_bitset_pipelined(ck_planes *pl, const uint64_t *bit_set, fl
   st.events.push_back(fork);
   CK_CUDA(cudaEventRecord(fork, s));
   CK_CUDA(cudaStreamWaitEvent(cs, fork, 0));
-  struct Chunk { uint32_t band_lo, band_hi, s0, s1; cudaEvent_t ready; };
+  struct Chunk { uint32_t s0, s1; cudaEvent_t ready; };
   std::vector<Chunk> chunks;
   for (uint32_t hi = num_bands; hi > 0;) {
     const uint32_t lo = hi > chunk_bands ? hi - chunk_bands : 0;
-    Chunk c{lo, hi, lo * kFp4BandRows, std::min<uint32_t>(hi * kFp4BandRows, n), nullptr};
+    Chunk c{lo * kFp4BandRows, std::min<uint32_t>(hi * kFp4BandRows, n), nullptr};
     CK_CUDA(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
     st.events.push_back(c.ready);
     const size_t off = size_t(c.s0) * words_per_sample;
@@ -849,33 +928,57 @@ static int king_host_bitset_pipelined(ck_planes *pl, const uint64_t *bit_set, fl
     chunks.push_back(c);
     hi = lo;
   }
-  ctx->timings.king_launches = 0;
-  CK_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), s));
-  CK_CUDA(cudaEventRecord(ctx->ev[0], s));
   for (const Chunk &c : chunks) {
-    CK_CUDA(cudaStreamWaitEvent(s, c.ready, 0));
-    const uint32_t block0 = c.s0 / kTileSamples, num_blocks = ceil_div(c.s1, kTileSamples) - block0;
-    CK_CUDA(launch_import_ref_range(*pl, static_cast<const uint64_t *>(st.p), block0, num_blocks, s));
-    CK_CUDA(launch_finalize_codes_range(*pl, 3, block0, num_blocks, s));
-    for (uint32_t b = c.band_lo; b < c.band_hi;) {  // maximal runs of this part's bands (the whole chunk when num_parts == 1)
-      if (band_owner(b, num_parts) != part_index) { ++b; continue; }
-      uint32_t e = b + 1;
-      while (e < c.band_hi && band_owner(e, num_parts) == part_index) ++e;
-      k.tile_begin = band_prefix[b];
-      k.tile_end = band_prefix[e];
-      if (k.tile_end > k.tile_begin) CK_CUDA(launch_king_fp4(k, pl->map.num_blocks, ctx, s, &ctx->timings.king_launches));
-      b = e;
+    cudaError_t e = cudaStreamWaitEvent(s, c.ready, 0);
+    rc = e == cudaSuccess ? stream_rows_device(pl, static_cast<const uint64_t *>(st.p) + size_t(c.s0) * words_per_sample, c.s0, c.s1)
+                          : fail_cuda(e, "cudaStreamWaitEvent", __FILE__, __LINE__);
+    if (rc != CK_OK) {
+      cudaStreamSynchronize(cs);
+      cudaStreamSynchronize(s);
+      delete pl->stream_state;
+      pl->stream_state = nullptr;
+      return rc;
     }
-    ctx->timings.king_launches += 2;  // transpose + code kernels of the chunk
   }
-  CK_CUDA(cudaEventRecord(ctx->ev[1], s));
-  pl->compute_stale = true;
-  pl->codes_stale = false;
-  pl->codes_kind = 3;
-  rc = finish_results(ctx, ctx->result_buf, max_results, results, 0, num_results, 1);
+  rc = stream_end_impl(pl, results, num_results);
   ctx->timings.h2d_ms = 0.f;     // overlapped: the whole upload + transpose + kernel span is reported as king_ms
   ctx->timings.import_ms = 0.f;
   return rc;
+}
+
+extern "C" {
+
+uint32_t ck_king_stream_granularity(void) { return kFp4BandRows; }
+
+int ck_king_stream_begin(ck_planes *pl, float kin_threshold, uint32_t max_results, uint32_t part_index, uint32_t num_parts) {
+  if (!pl) return fail(CK_ERR_INVALID_ARGUMENT, "planes is NULL");
+  DeviceGuard guard(pl->ctx->device);
+  return stream_begin_impl(pl, kin_threshold, max_results, part_index, num_parts);
+}
+
+int ck_king_stream_rows(ck_planes *pl, const uint64_t *rows, int on_device, uint32_t sample_begin, uint32_t sample_end) {
+  if (!pl || !rows) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!pl->stream_state) return fail(CK_ERR_INVALID_ARGUMENT, "no stream session is open on these planes");
+  ck_ctx *ctx = pl->ctx;
+  DeviceGuard guard(ctx->device);
+  if (on_device) return stream_rows_device(pl, rows, sample_begin, sample_end);
+  if (sample_end <= sample_begin) return fail(CK_ERR_INVALID_ARGUMENT, "empty row range");
+  const size_t bytes = size_t(sample_end - sample_begin) * ref_words_per_sample(pl->num_sites) * 8;
+  DevBuf tmp;  // host rows: staged synchronously (callers that want overlap deliver device memory)
+  CK_CUDA(tmp.alloc(bytes));
+  CK_CUDA(cudaMemcpyAsync(tmp.p, rows, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = stream_rows_device(pl, tmp.as<uint64_t>(), sample_begin, sample_end);
+  CK_CUDA(cudaStreamSynchronize(ctx->stream));  // tmp dies with this frame
+  return rc;
+}
+
+int ck_king_stream_end(ck_planes *pl, ck_result *results, uint32_t *num_results) {
+  if (!pl || !num_results) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!pl->stream_state) return fail(CK_ERR_INVALID_ARGUMENT, "no stream session is open on these planes");
+  if (pl->stream_state->max_results > 0 && !results) return fail(CK_ERR_INVALID_ARGUMENT, "results is NULL");
+  *num_results = 0;
+  DeviceGuard guard(pl->ctx->device);
+  return stream_end_impl(pl, results, num_results);
 }
 
 int ck_king_host_bitset(ck_ctx *ctx, uint32_t num_samples, uint32_t split_factor, uint32_t shard_index,

@@ -72,6 +72,10 @@ void ctx_release(ck_ctx *ctx, void *ptr, size_t bytes);        // into the cache
 }  // namespace ck
 
 
+namespace ck {
+struct KingStream;  // below
+}
+
 struct ck_planes {
   ck_ctx *ctx = nullptr;
   size_t raw_bytes = 0, compute_bytes = 0, codes_bytes = 0;  // sizes of the three buffers as allocated
@@ -81,6 +85,7 @@ struct ck_planes {
   uint32_t *raw = nullptr;     // [num_blocks][words][2][64]
   uint32_t *compute = nullptr; // [num_blocks][words][3][64]   (LOP3+POPC kernels)
   uint32_t *codes = nullptr;   // [num_blocks][words][64][4]   (tcgen05 kernel; allocated on first use)
+  ck::KingStream *stream_state = nullptr;  // ck_king_stream_begin .. end
   bool compute_stale = true;   // raw changed since the last finalize into `compute`
   bool codes_stale = true;     // raw changed since the last finalize into `codes`
   int codes_kind = 0;          // which kernel variant `codes` was last derived for (2: int8 selectors, 3: E2M1 nibbles)
@@ -100,8 +105,9 @@ cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s);
 cudaError_t launch_finalize_codes(const ck_planes &pl, int kind, cudaStream_t s);
 // the same for the 64-sample blocks [block0, block0 + num_blocks) only (pipelined host-buffer path)
 cudaError_t launch_finalize_codes_range(const ck_planes &pl, int kind, uint32_t block0, uint32_t num_blocks, cudaStream_t s);
-cudaError_t launch_import_ref_range(const ck_planes &pl, const uint64_t *d_bit_set, uint32_t block0, uint32_t num_blocks,
-                                    cudaStream_t s);
+// d_rows points at the reference-layout row of slot ref_slot0 (a chunk of the bit set, or the whole of it with 0)
+cudaError_t launch_import_ref_range(const ck_planes &pl, const uint64_t *d_rows, uint32_t ref_slot0, uint32_t block0,
+                                    uint32_t num_blocks, cudaStream_t s);
 cudaError_t launch_import_ref(const ck_planes &pl, const uint64_t *d_bit_set, cudaStream_t s);
 cudaError_t launch_export_ref(const ck_planes &pl, uint64_t *d_bit_set, cudaStream_t s);
 cudaError_t launch_synth_planes(const ck_planes &pl, uint64_t seed, uint32_t miss_thr, cudaStream_t s);
@@ -129,6 +135,13 @@ struct KingLaunch {
   unsigned long long *counter;        // device, emitted pairs
   ck_counts *dump_counts;             // optional dense [num_rows][num_cols] dump (parity hook), else nullptr
   float *dump_kin;
+};
+struct KingStream {  // state of one ck_king_stream_begin .. end session (also used by the pipelined host-buffer path)
+  KingLaunch k{};
+  std::vector<uint64_t> band_prefix;  // first linear tile of every band + total
+  uint32_t part_index = 0, num_parts = 1;
+  uint32_t max_results = 0;
+  uint32_t next_end = 0;              // rows [next_end, n) have been delivered
 };
 uint64_t king_num_tiles(uint32_t num_row_blocks, uint32_t num_col_blocks, bool triangular);
 cudaError_t launch_king(const KingLaunch &k, int variant, cudaStream_t s, uint32_t *launches);

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) finalize_codes_kernel(const uint32_t *__r
 // A CTA transposes a 64-sample x 32-word tile of one plane through shared memory so that both sides are coalesced.
 template <bool kImport>
 __global__ void __launch_bounds__(256) ref_transpose_kernel(uint32_t *raw, uint32_t *ref32, SlotMap map, uint32_t words,
-                                                            uint32_t ref_words_u64, uint32_t num_ref_slots, uint32_t block0) {
+                                                            uint32_t ref_words_u64, uint32_t num_ref_slots, uint32_t block0,
+                                                            uint32_t ref_slot0 /* slot of the first row behind ref32 */) {
   __shared__ uint32_t tile[kTileSamples][33];
   const uint32_t block = block0 + blockIdx.y, plane = blockIdx.z;
   const uint32_t k0 = blockIdx.x * 32;
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) ref_transpose_kernel(uint32_t *raw, uint3
       const uint32_t o = ref_slot_of(block * kTileSamples + lane);
       uint32_t v = 0xffffffffu;  // padding lanes / padding words are missing
       if (o != 0xffffffffu && k0 + kk < ref_k)
-        v = ref32[(size_t(o) * 2 + plane) * ref_k + k0 + kk];
+        v = ref32[(size_t(o - ref_slot0) * 2 + plane) * ref_k + k0 + kk];
       tile[lane][kk] = v;
     }
     __syncthreads();
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(256) ref_transpose_kernel(uint32_t *raw, uint3
     for (uint32_t e = threadIdx.x; e < kTileSamples * 32; e += blockDim.x) {
       const uint32_t lane = e / 32, kk = e % 32;
       const uint32_t o = ref_slot_of(block * kTileSamples + lane);
-      if (o != 0xffffffffu && k0 + kk < ref_k) ref32[(size_t(o) * 2 + plane) * ref_k + k0 + kk] = tile[lane][kk];
+      if (o != 0xffffffffu && k0 + kk < ref_k) ref32[(size_t(o - ref_slot0) * 2 + plane) * ref_k + k0 + kk] = tile[lane][kk];
     }
   }
 }
@@ -300,24 +301,24 @@ cudaError_t launch_finalize_codes_range(const ck_planes &pl, int kind, uint32_t 
   return cudaGetLastError();
 }
 
-cudaError_t launch_import_ref_range(const ck_planes &pl, const uint64_t *d_bit_set, uint32_t block0, uint32_t num_blocks,
-                                    cudaStream_t s) {
+cudaError_t launch_import_ref_range(const ck_planes &pl, const uint64_t *d_rows, uint32_t ref_slot0, uint32_t block0,
+                                    uint32_t num_blocks, cudaStream_t s) {
   if (num_blocks == 0) return cudaSuccess;
   const uint32_t ref_k = ref_words_per_sample(pl.num_sites);  // u64 words per sample == u32 words per plane
   dim3 grid(ceil_div(pl.words, 32u), num_blocks, kRawPlanes);
-  ref_transpose_kernel<true><<<grid, 256, 0, s>>>(pl.raw, const_cast<uint32_t *>(reinterpret_cast<const uint32_t *>(d_bit_set)),
-                                                 pl.map, pl.words, ref_k, sm_samples(pl.map.sm), block0);
+  ref_transpose_kernel<true><<<grid, 256, 0, s>>>(pl.raw, const_cast<uint32_t *>(reinterpret_cast<const uint32_t *>(d_rows)),
+                                                 pl.map, pl.words, ref_k, sm_samples(pl.map.sm), block0, ref_slot0);
   return cudaGetLastError();
 }
 cudaError_t launch_import_ref(const ck_planes &pl, const uint64_t *d_bit_set, cudaStream_t s) {
-  return launch_import_ref_range(pl, d_bit_set, 0, pl.map.num_blocks, s);
+  return launch_import_ref_range(pl, d_bit_set, 0, 0, pl.map.num_blocks, s);
 }
 
 cudaError_t launch_export_ref(const ck_planes &pl, uint64_t *d_bit_set, cudaStream_t s) {
   const uint32_t ref_k = ref_words_per_sample(pl.num_sites);
   dim3 grid(ceil_div(pl.words, 32u), pl.map.num_blocks, kRawPlanes);
   ref_transpose_kernel<false><<<grid, 256, 0, s>>>(pl.raw, reinterpret_cast<uint32_t *>(d_bit_set), pl.map, pl.words,
-                                                  ref_k, sm_samples(pl.map.sm), 0);
+                                                  ref_k, sm_samples(pl.map.sm), 0, 0);
   return cudaGetLastError();
 }
 

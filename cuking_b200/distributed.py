@@ -1,9 +1,10 @@
 """Multi-GPU execution of one shard: one process per GPU (torch.distributed), every rank holds the shard's planes and
 evaluates a contiguous slice of its 64x64 tile grid; the sparse results are gathered on rank 0.
 
-There is NO data-path collective: pairs are independent (/root/reference/cuking.cu:197-201) and no count is ever
-combined across devices.  torch.distributed carries only the result gather (a few MB) and barriers.  The reference
-scales the same way but with one OS process per shard on separate VMs (README.md:94-102, cloud_batch_submit.py:45,73).
+Pairs are independent (/root/reference/cuking.cu:197-201) and no count is ever combined across devices, so the
+pairwise stage itself needs no collective; torch.distributed carries the result gather (a few MB), barriers and -
+in king_host_bitset_allgather - the replication of the input planes over NVLink.  The reference scales the same way
+but with one OS process per shard on separate VMs (README.md:94-102, cloud_batch_submit.py:45,73).
 """
 from __future__ import annotations
 
@@ -100,3 +101,64 @@ def king_distributed(evaluate_slice, total_tiles: int, max_results: int, group=N
     if len(merged) > max_results:
         raise CukingError(CK_ERR_RESULT_OVERFLOW, "Could not store all results: try increasing the --max_results parameter.")
     return merged
+
+
+def stream_chunks(num_samples: int, granularity: int, target_chunks: int = 24) -> list[tuple[int, int]]:
+    """Descending sample ranges [(begin, end), ...] that tile [0, num_samples) at multiples of `granularity` - the
+    delivery order of ck_king_stream_rows (the kernel starts on the bottom rows, which need no other sample)."""
+    bands = -(-num_samples // granularity)
+    per = max(1, -(-bands // target_chunks))
+    out, hi = [], bands
+    while hi > 0:
+        lo = max(0, hi - per)
+        out.append((lo * granularity, min(hi * granularity, num_samples)))
+        hi = lo
+    return out
+
+
+def king_host_bitset_allgather(planes, host_bits, words_per_sample: int, kin_threshold: float, max_results: int,
+                               out: np.ndarray | None = None, group=None, side_stream=None):
+    """The host-buffer seam on the G GPUs of one box with the planes replicated over NVLink instead of G times over
+    PCIe: every rank holds the bit set in pinned host memory (e.g. one shared mapping), uploads only ITS 1/G of every
+    chunk through its own PCIe link, and an NCCL all-gather hands every GPU the whole chunk; ck_king_stream_rows then
+    launches the rank's bands among those rows.  Chunks travel last rows first on a side stream, so upload and
+    all-gather of chunk c+1 overlap the pairwise kernel of chunk c.  Measured on 8 x B200 (bench.py plane_exchange):
+    eight concurrent full uploads are host-limited at 23 GB/s per GPU, while 1/8 per link + NVLink moves the 7 GB in a
+    few tens of ms - north_star's "NCCL broadcast only if it beats per-GPU host loading".
+    `planes`: this rank's Planes of the (diagonal) shard; `host_bits`: pinned CPU uint64/int64 tensor of the reference
+    layout, [num_samples * words_per_sample].  Returns this rank's sorted records (parts are disjoint)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    hb = host_bits.view(torch.int64)
+    n = hb.numel() // words_per_sample
+    dev = torch.device("cuda", torch.cuda.current_device())
+    main = torch.cuda.current_stream(dev)
+    side = side_stream if side_stream is not None else torch.cuda.Stream(dev)
+    gran = int(planes._lib.ck_king_stream_granularity())
+    chunks = stream_chunks(n, gran)
+    # chunk rows are padded to a multiple of `world` so that the all-gather pieces are equal
+    max_rows = max(e - b for b, e in chunks)
+    piece_rows = -(-max_rows // world)
+    stage = [torch.empty(piece_rows * world * words_per_sample, dtype=torch.int64, device=dev) for _ in range(len(chunks))]
+    side.wait_stream(main)
+    planes.stream_begin(kin_threshold, max_results, part=(rank, world))
+    for c, (b, e) in enumerate(chunks):
+        rows = e - b
+        pr = -(-rows // world)  # rows per rank in this chunk (the last rank's piece may be short or empty)
+        my_b, my_e = min(b + rank * pr, e), min(b + (rank + 1) * pr, e)
+        buf = stage[c][: pr * world * words_per_sample]
+        with torch.cuda.stream(side):
+            mine = buf[rank * pr * words_per_sample: (rank + 1) * pr * words_per_sample]
+            if my_e > my_b:
+                mine[: (my_e - my_b) * words_per_sample].copy_(hb[my_b * words_per_sample: my_e * words_per_sample], non_blocking=True)
+            if world > 1:
+                dist.all_gather_into_tensor(buf, mine, group=group)
+            ready = torch.cuda.Event()
+            ready.record(side)
+        main.wait_event(ready)
+        planes.stream_rows(buf.data_ptr(), b, e)
+    res = planes.stream_end(max_results, out=out)
+    del stage
+    return res

@@ -193,6 +193,23 @@ class Planes:
         check(self._lib.ck_king_num_tiles(self._h, C.byref(t)))
         return int(t.value)
 
+    # -- streaming delivery (ck_king_stream_*) -------------------------------------------------------------------
+    def stream_begin(self, kin_threshold: float, max_results: int = 10 << 20, part: tuple[int, int] = (0, 1)) -> None:
+        check(self._lib.ck_king_stream_begin(self._h, C.c_float(kin_threshold), max_results, part[0], part[1]))
+
+    def stream_rows(self, rows, sample_begin: int, sample_end: int) -> None:
+        """Reference-layout rows of the shard-local samples [sample_begin, sample_end) (numpy, torch CPU or CUDA tensor,
+        or a raw device address as int); ranges must arrive in descending order."""
+        addr, on_device = (rows, True) if isinstance(rows, int) else _ptr(rows)
+        check(self._lib.ck_king_stream_rows(self._h, addr, 1 if on_device else 0, sample_begin, sample_end))
+
+    def stream_end(self, max_results: int, out: np.ndarray | None = None):
+        res = out if out is not None else np.empty(max_results, dtype=RESULT_DTYPE)
+        n = C.c_uint32(0)
+        check(self._lib.ck_king_stream_end(self._h, res.ctypes.data, C.byref(n)))
+        self.last_count = int(n.value)
+        return res[: n.value]
+
     def king_variant(self) -> int:
         """The pairwise kernel variant ck_king* runs on these planes (3 = FP4 tensor path, 2 = int8 beyond 2^21 sites)."""
         v = C.c_int()

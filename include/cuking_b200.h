@@ -201,6 +201,22 @@ int ck_king_host_bitset_part(ck_ctx *ctx, uint32_t num_samples, uint32_t split_f
                              uint32_t num_sites, const uint64_t *bit_set, float kin_threshold, uint32_t max_results,
                              ck_result *results, uint32_t *num_results, uint32_t part_index, uint32_t num_parts);
 
+/* Streaming form of the seam, for callers that deliver the bit set in pieces (several readers + an NCCL all-gather over
+ * NVLink, a file reader, ...).  Diagonal shards and the mxf4 kernel (<= 2^21 sites) only.
+ *   ck_king_stream_begin(planes, thr, max_results, part_index, num_parts)
+ *   ck_king_stream_rows(planes, rows, on_device, sample_begin, sample_end)   repeatedly, for DESCENDING ranges of shard-
+ *       local sample indices that tile [0, rows of the shard): boundaries are multiples of ck_king_stream_granularity()
+ *       (the shard's end excepted); `rows` points at the reference-layout row (cuking.cu:507-513) of sample_begin.  The
+ *       call transposes the rows, derives the genotype codes and launches this part's bands among them - with device
+ *       memory everything is queued on the ctx stream and the call returns at once (keep `rows` alive until end);
+ *   ck_king_stream_end(planes, results, &num_results)   waits, applies the overflow rule, sorts, copies out.
+ * A band only pairs its rows with samples at or after them, which is why descending delivery lets the kernel start on
+ * the first piece.  ck_king_host_bitset[_part] is this API fed by chunked cudaMemcpyAsync from one host buffer. */
+uint32_t ck_king_stream_granularity(void);
+int ck_king_stream_begin(ck_planes *planes, float kin_threshold, uint32_t max_results, uint32_t part_index, uint32_t num_parts);
+int ck_king_stream_rows(ck_planes *planes, const uint64_t *rows, int on_device, uint32_t sample_begin, uint32_t sample_end);
+int ck_king_stream_end(ck_planes *planes, ck_result *results, uint32_t *num_results);
+
 /* ---- synthetic inputs (bench / tests) --------------------------------------------------------------------- */
 
 /* Dense genotypes of the synthetic cohort on the HOST: out[(s - sample_begin) * num_sites_out + (r - site_begin)]

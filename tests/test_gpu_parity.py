@@ -290,6 +290,46 @@ def test_host_bitset_pipelined_upload_matches_oracle(ctx):
     assert_results_equal(np.sort(got2, order=["sample_i", "sample_j"]), want2)
 
 
+def test_streaming_delivery_matches_oracle(ctx):
+    # ck_king_stream_*: the bit set arrives in descending row ranges (host memory, device memory, several parts)
+    import torch
+    from cuking_b200.distributed import stream_chunks
+
+    rng = np.random.default_rng(5)
+    n, s = 2500, 400
+    g = random_genotypes(rng, n, s)
+    osm = ko.submatrix(n, 1, 0)
+    bs = oracle_bitset(g, osm)
+    want, count, _ = ko.king(bs, s, osm, 0.1, 1 << 20)
+    w = ck.words_per_sample(s)
+    gran = 1024
+    chunks = stream_chunks(n, gran, target_chunks=3)
+    assert chunks[0][1] == n and chunks[-1][0] == 0 and all(b % gran == 0 for b, _ in chunks)
+    dev_bits = torch.from_numpy(bs.view(np.int64)).cuda()
+    for source in ("host", "device"):
+        for parts in (1, 2):
+            got = []
+            for p in range(parts):
+                with ctx.planes(ck.submatrix(n), s) as pl:
+                    pl.stream_begin(0.1, 1 << 20, part=(p, parts))
+                    for b, e in chunks:
+                        rows = bs[b * w: e * w] if source == "host" else dev_bits[b * w: e * w]
+                        pl.stream_rows(rows, b, e)
+                    got.append(pl.stream_end(1 << 20))
+            got = np.concatenate(got)
+            assert_results_equal(np.sort(got, order=["sample_i", "sample_j"]), want)
+    with ctx.planes(ck.submatrix(n), s) as pl:  # protocol errors are reported, not executed
+        pl.stream_begin(0.1, 1 << 20)
+        with pytest.raises(ck.CukingError):
+            pl.stream_rows(bs[: gran * w], 0, gran)          # not the last rows first
+        pl.stream_rows(bs[chunks[0][0] * w: n * w], chunks[0][0], n)
+        with pytest.raises(ck.CukingError):
+            pl.stream_end(1 << 20)                            # rows [0, chunks[0][0]) never arrived
+    with ctx.planes(ck.submatrix(n, 2, 1), s) as pl:
+        with pytest.raises(ck.CukingError):
+            pl.stream_begin(0.1, 1 << 20)                     # off-diagonal shard
+
+
 # ---- synthetic cohort ------------------------------------------------------------------------------------------
 
 
