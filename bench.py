@@ -445,10 +445,16 @@ def main():
         ev1.record(stream)
         barrier()
         e_ms = ev0.elapsed_time(ev1)
+        e2e_retained = len(r)
         if distributed:
             tmax = torch.tensor([e_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             e_ms = float(tmax.item())
+            tot = torch.tensor([float(e2e_retained)], device=dev, dtype=torch.float64)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            e2e_retained = int(tot.item())
+        if e2e_retained != retained:  # the host-buffer leg must keep exactly the pairs the resident leg kept
+            raise SystemExit(f"e2e leg retained {e2e_retained} pairs, resident leg {retained}")
         e2e = {"value": total_units / (e_ms / e2e_steps * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d // world) if allgather else int(h2d),  # per rank
                "d2h_bytes_per_step": int(len(r) * 24 + 8), "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps,
