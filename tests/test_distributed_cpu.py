@@ -90,3 +90,16 @@ def test_two_rank_overflow_is_global(tmp_path):
 
     mp.spawn(_worker, args=(2, _free_port(), 200, 300, 1, 0, -1.0, 50, str(tmp_path)), nprocs=2, join=True)
     assert "max_results" in (tmp_path / "error.txt").read_text()
+
+
+def test_stream_chunks_tile_the_shard_in_descending_order():
+    # delivery order of ck_king_stream_rows: last rows first, boundaries at the stream granularity, nothing missing
+    from cuking_b200.distributed import stream_chunks
+
+    for n, gran, target in [(1, 1024, 24), (1024, 1024, 24), (1025, 1024, 24), (100_000, 1024, 24), (282_816, 1024, 24),
+                            (5_000, 1024, 3), (2_500, 1024, 1)]:
+        chunks = stream_chunks(n, gran, target)
+        assert chunks[0][1] == n and chunks[-1][0] == 0
+        assert all(b % gran == 0 and b < e for b, e in chunks)
+        assert all(chunks[q][0] == chunks[q + 1][1] for q in range(len(chunks) - 1))  # contiguous, descending
+        assert len(chunks) <= max(target, 1) + 1
