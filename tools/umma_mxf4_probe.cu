@@ -72,7 +72,7 @@ constexpr uint32_t kACol = 416;   // columns [416, 480): A operand (up to 64 col
 //         2 = A in TMEM, one element per byte (low nibble); 3 = A in TMEM, one element per byte (high nibble)
 template <int N>
 __global__ void __launch_bounds__(128) probe_kernel(const uint8_t *A, const uint8_t *B, float *D, int kbytes, int reps, int a_mode,
-                                                    unsigned long long *cycles) {
+                                                    unsigned long long *cycles, int k_per_mma = 64) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_smem;
@@ -124,13 +124,17 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t *A, const uint
 
   unsigned long long t0 = clock64();
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_mxf4(M, N);
+    // k_per_mma = 96: the descriptor's K-size bit (dense K96, documented for kind::mxf4 in CUTLASS' mma_sm100_desc.hpp;
+    // possibly sm_103a only) - 48 bytes = three core matrices per row and instruction
+    const uint32_t idesc = make_idesc_mxf4(M, N) | (k_per_mma == 96 ? (1u << 31) : 0u);
+    const uint32_t cm = k_per_mma / 32;  // 16-byte core matrices per row per MMA
+    if (k_per_mma == 96) a_cols_per_mma = 12;
     for (int rep = 0; rep < reps; ++rep)
-      for (uint32_t ks = 0; ks < uint32_t(kbytes) / 32; ++ks) {
-        const uint64_t db = make_smem_desc(smem_u32(sB) + ks * 2 * LBO, LBO, SBO);
+      for (uint32_t ks = 0; ks < uint32_t(kbytes) / (cm * 16); ++ks) {
+        const uint64_t db = make_smem_desc(smem_u32(sB) + ks * cm * LBO, LBO, SBO);
         const uint32_t acc = (rep > 0 || ks > 0) ? 1u : 0u;
         if (a_mode == 0)
-          umma_mxf4_ss(tmem_base, make_smem_desc(smem_u32(sA) + ks * 2 * LBO, LBO, SBO), db, idesc, tmem_base + kSfCol, tmem_base + kSfCol + 16, acc);
+          umma_mxf4_ss(tmem_base, make_smem_desc(smem_u32(sA) + ks * cm * LBO, LBO, SBO), db, idesc, tmem_base + kSfCol, tmem_base + kSfCol + 16, acc);
         else
           umma_mxf4_ts(tmem_base, tmem_base + kACol + ks * a_cols_per_mma, db, idesc, tmem_base + kSfCol, tmem_base + kSfCol + 16, acc);
       }
@@ -160,7 +164,7 @@ static int e2m1_value(uint32_t nib) {  // only the codes the probe uses
 
 // fill: 0 = random {-1,0,+1}; 1 = all +1 (largest possible count); 2 = random {0,+1} (monotone partial sums)
 template <int N>
-static int run(int kbytes, int reps, int a_mode, int fill, const char *label) {
+static int run(int kbytes, int reps, int a_mode, int fill, const char *label, int k_per_mma = 64) {
   constexpr int M = 128;
   std::vector<uint8_t> hA(size_t(M) * kbytes), hB(size_t(N) * kbytes);
   uint32_t s = 4242u + N + fill;
@@ -179,7 +183,7 @@ static int run(int kbytes, int reps, int a_mode, int fill, const char *label) {
   CK(cudaMemcpy(dB, hB.data(), hB.size(), cudaMemcpyHostToDevice));
   const size_t smem = size_t(M + N) * kbytes;
   CK(cudaFuncSetAttribute(probe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  probe_kernel<N><<<1, 128, smem>>>(dA, dB, dD, kbytes, reps, a_mode, dC);
+  probe_kernel<N><<<1, 128, smem>>>(dA, dB, dD, kbytes, reps, a_mode, dC, k_per_mma);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> hD(M * N);
@@ -198,7 +202,7 @@ static int run(int kbytes, int reps, int a_mode, int fill, const char *label) {
         printf("  %s mismatch (m=%d,n=%d): got %.1f want %lld\n", label, m, n, hD[m * N + n], ref);
     }
   printf("{\"probe\": \"umma_mxf4\", \"test\": \"%s\", \"a_mode\": %d, \"fill\": %d, \"N\": %d, \"K\": %d, \"reps\": %d, \"total_sites\": %lld, \"max_abs_count\": %lld, \"mismatches\": %d, \"clk_per_mma\": %.1f}\n",
-         label, a_mode, fill, N, 2 * kbytes, reps, (long long)2 * kbytes * reps, max_abs, bad, double(cyc) / (double(reps) * kbytes / 32));
+         label, a_mode, fill, N, 2 * kbytes, reps, (long long)2 * kbytes * reps, max_abs, bad, double(cyc) / (double(reps) * kbytes / (k_per_mma / 2)));
   cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dC);
   return bad;
 }
@@ -279,6 +283,13 @@ static void run_rate(int n0, int n1, int issuers, int a_in_tmem) {
 }
 
 int main(int argc, char **argv) {
+  if (argc > 1 && !strcmp(argv[1], "k96")) {  // separate invocation: an unsupported descriptor bit may fault the context
+    int bad = run<160>(96, 1, 0, 0, "k96_ss", 96);
+    bad += run<160>(96, 1, 1, 0, "k96_ts", 96);
+    bad += run<160>(96, 2000, 1, 2, "k96_ts_long", 96);
+    printf("{\"probe\": \"umma_mxf4\", \"k96\": %s}\n", bad ? "\"not usable on this GPU (results differ)\"" : "\"exact\"");
+    return 0;
+  }
   int bad_ss = 0;
   // 1. plumbing, SS mode (the layout CUTLASS uses): small K, random signs
   bad_ss += run<80>(128, 1, 0, 0, "ss_small");
