@@ -158,11 +158,12 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t *A, const uint
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
 }
 
-static int e2m1_value(uint32_t nib) {  // only the codes the probe uses
-  return nib == 0x2 ? 1 : nib == 0xA ? -1 : 0;
+static int e2m1_value4(uint32_t nib) {  // 4 x the E2M1 value, only for the codes the probe uses
+  return nib == 0x2 ? 4 : nib == 0xA ? -4 : nib == 0x1 ? 2 : 0;
 }
 
-// fill: 0 = random {-1,0,+1}; 1 = all +1 (largest possible count); 2 = random {0,+1} (monotone partial sums)
+// fill: 0 = random {-1,0,+1}; 1 = all +1 (largest possible count); 2 = random {0,+1} (monotone partial sums);
+//       3 = random {0, 0.5, +1, -1}: the operand values of the KING kernel (h = 0.5), products are multiples of 1/4
 template <int N>
 static int run(int kbytes, int reps, int a_mode, int fill, const char *label, int k_per_mma = 64) {
   constexpr int M = 128;
@@ -173,6 +174,7 @@ static int run(int kbytes, int reps, int a_mode, int fill, const char *label, in
     const uint32_t r = (s >> 24) % 3;
     if (fill == 1) return 0x2;
     if (fill == 2) return r ? 0x2 : 0x0;
+    if (fill == 3) { const uint32_t q = (s >> 20) % 4; return q == 0 ? 0x0 : q == 1 ? 0x1 : q == 2 ? 0x2 : 0xA; }
     return r == 0 ? 0x0 : r == 1 ? 0x2 : 0xA;
   };
   for (auto &x : hA) { uint8_t lo = nib(), hi = nib(); x = uint8_t(lo | (hi << 4)); }
@@ -193,13 +195,14 @@ static int run(int kbytes, int reps, int a_mode, int fill, const char *label, in
   long long max_abs = 0;
   for (int m = 0; m < M; ++m)
     for (int n = 0; n < N; ++n) {
-      long long ref = 0;
+      long long ref16 = 0;  // in units of 1/16
       for (int k = 0; k < 2 * kbytes; ++k)
-        ref += e2m1_value((hA[size_t(m) * kbytes + (k >> 1)] >> (4 * (k & 1))) & 0xf) * e2m1_value((hB[size_t(n) * kbytes + (k >> 1)] >> (4 * (k & 1))) & 0xf);
-      ref *= reps;
+        ref16 += e2m1_value4((hA[size_t(m) * kbytes + (k >> 1)] >> (4 * (k & 1))) & 0xf) * e2m1_value4((hB[size_t(n) * kbytes + (k >> 1)] >> (4 * (k & 1))) & 0xf);
+      ref16 *= reps;
+      const long long ref = ref16 / 16;
       if (llabs(ref) > max_abs) max_abs = llabs(ref);
-      if (double(ref) != double(hD[m * N + n]) && bad++ < 4)
-        printf("  %s mismatch (m=%d,n=%d): got %.1f want %lld\n", label, m, n, hD[m * N + n], ref);
+      if (double(ref16) != 16.0 * double(hD[m * N + n]) && bad++ < 4)
+        printf("  %s mismatch (m=%d,n=%d): got %.2f want %.4f\n", label, m, n, hD[m * N + n], double(ref16) / 16.0);
     }
   printf("{\"probe\": \"umma_mxf4\", \"test\": \"%s\", \"a_mode\": %d, \"fill\": %d, \"N\": %d, \"K\": %d, \"reps\": %d, \"total_sites\": %lld, \"max_abs_count\": %lld, \"mismatches\": %d, \"clk_per_mma\": %.1f}\n",
          label, a_mode, fill, N, 2 * kbytes, reps, (long long)2 * kbytes * reps, max_abs, bad, double(cyc) / (double(reps) * kbytes / (k_per_mma / 2)));
@@ -307,6 +310,7 @@ int main(int argc, char **argv) {
     bad_exact += run<160>(64, reps, amode, 1, "exact_all_ones");
     bad_exact += run<160>(64, reps, amode, 2, "exact_random_01");
     bad_exact += run<160>(64, reps, amode, 0, "exact_random_pm1");
+    bad_exact += run<160>(64, reps, amode, 3, "exact_random_king_values");
   }
   // 4. sustained rate, KING issue pattern
   run_rate(80, 160, 3, 1);
