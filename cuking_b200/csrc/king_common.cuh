@@ -55,6 +55,25 @@ __device__ __forceinline__ void mbar_wait_suspend(uint64_t *bar, uint32_t parity
         : "memory");
   }
 }
+// The same operations by 32-bit shared address.  Hot loops compute the address of barrier i as base + 8 i once;
+// going through a generic pointer makes the compiler rebuild the shared window (S2UR SR_CgaCtaId + LEA) at every use.
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_suspend_addr(uint32_t bar, uint32_t parity, uint32_t hint_ns = 20000u) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+  }
+}
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); completion is signalled on the mbarrier.
 __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -43,8 +43,12 @@ namespace ck {
 
 namespace {
 
-constexpr uint32_t kFM = 128, kFN = 80;     // tile rows (A operand, TMEM lanes) x tile columns (B operand)
-constexpr uint32_t kFSlots = 4;             // A ring in TMEM: one 64-site step per slot; AS slots form one A stage (barrier pair)
+#ifndef CK_FP4_TILE_N  // tile shape experiments: -DCK_FP4_TILE_N=64 -DCK_FP4_SLOTS=6 (profiles/r01_fp4_tuning.md)
+#define CK_FP4_TILE_N 80
+#define CK_FP4_SLOTS 4
+#endif
+constexpr uint32_t kFM = 128, kFN = CK_FP4_TILE_N;  // tile rows (A operand, TMEM lanes) x tile columns (B operand)
+constexpr uint32_t kFSlots = CK_FP4_SLOTS;  // A ring in TMEM: one 64-site step per slot; AS slots form one A stage (barrier pair)
 constexpr uint32_t kFGroups = 2;            // groups of four A warps; group g fills the A stages with stage % 2 == g
 constexpr uint32_t kFSub = 4;               // B expanders work in sub-stages of 4 steps (register prefetch unit)
 constexpr uint32_t kFLBO = 128;             // bytes between K-adjacent 8x16-byte core matrices
@@ -59,12 +63,12 @@ constexpr uint32_t kFColSF = kFColA + 24 * kFSlots;  // 16 columns of scale fact
 constexpr uint32_t kFTmemCols = 512;
 constexpr uint32_t kBand = 8;               // row tiles per band of the tile enumeration
 static_assert(kFBWarps * 32 == 2 * kFN, "two threads per column sample must fill whole warps");
-static_assert(kFColSF + 16 == kFTmemCols, "TMEM budget");
+static_assert(kFColSF + 16 <= kFTmemCols, "TMEM budget");
 static_assert(kChunkWords % (2 * kFGroups * kFAPrefetchSteps) == 0 && kChunkWords % (2 * kFSub * kFBPrefetch) == 0, "loop unrolling");
 
 template <uint32_t AS, uint32_t BS, uint32_t NS>
 struct Fp4Geo {
-  static_assert(BS % kFSub == 0 && BS % kFSlots == 0 && (AS == 1 || AS == 2), "stage geometry");
+  static_assert(BS % kFSub == 0 && BS % AS == 0 && kFSlots % AS == 0 && (AS == 1 || AS == 2), "stage geometry");
   static constexpr uint32_t kAStages = kFSlots / AS;        // A stages in the TMEM ring
   static constexpr uint32_t kSBO = BS * 2 * kFLBO;          // a stage holds 32 K-bytes (64 sites) per step
   static constexpr uint32_t kTile = (kFN / 8) * kSBO;       // one B operand plane of one stage
@@ -304,6 +308,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     // ===== MMA issuers: warps 13 (x.x), 14 (y.[y;h]), 15 (h.[y;h]).  The whole warp runs the loop (warp-uniform control
     // flow keeps the descriptor arithmetic in the uniform datapath); one elected lane issues the MMA and the commits.
     const uint32_t which = warp - kFExpWarps;
+    if (which < kFIssuers) {
     const uint32_t idesc = which == 0 ? make_idesc_mxf4(kFM, kFN) : make_idesc_mxf4(kFM, 2 * kFN);
     const uint32_t d_addr = tmem_base + (which == 0 ? kFColXX : which == 1 ? kFColY : kFColH);
     const uint32_t a_addr = tmem_base + kFColA + which * 8;
@@ -337,6 +342,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
       if (which == 1) FPROF_ADD(11, q1 - q0 - waited);
     }
     if (elected) umma_commit_arrive(&acc_bar);  // this issuer's accumulator is final
+    }
   }
 
   // ===== epilogue: all 16 warps; thread = row (TMEM lane quadrant warp % 4), 20 columns per warp group (16 + 4) =====
@@ -391,7 +397,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
       emit_pair(p, cand, gi, gj, kin, opp, conc, both_het, shared);
     };
     constexpr uint32_t kColsPerGroup = kFN / 4;  // 20
-    static_assert(kColsPerGroup == 20, "epilogue column split");
+    static_assert(kColsPerGroup == 20 || kColsPerGroup == 16, "epilogue column split");
     const uint32_t c0 = group * kColsPerGroup;
     {
       uint32_t xx[16], yy[16], yh[16], hy[16], hh[16];
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
 #pragma unroll
       for (uint32_t q = 0; q < 16; ++q) finish(c0 + q, xx[q], yy[q], yh[q], hy[q], hh[q]);
     }
-    {
+    if constexpr (kColsPerGroup > 16) {
       uint32_t xx[4], yy[4], yh[4], hy[4], hh[4];
       tmem_load4(lane_base + kFColXX + c0 + 16, xx);
       tmem_load4(lane_base + kFColY + c0 + 16, yy);
