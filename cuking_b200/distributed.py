@@ -116,6 +116,14 @@ def stream_chunks(num_samples: int, granularity: int, target_chunks: int = 24) -
     return out
 
 
+def chunk_piece(begin: int, end: int, rank: int, world: int) -> tuple[int, int, int]:
+    """Rows of chunk [begin, end) that `rank` uploads before the all-gather: (rows per piece, my_begin, my_end).  Pieces
+    are equal-sized (the all-gather needs that), in rank order, so the gathered buffer holds the chunk's rows in order;
+    the last pieces may be short or empty."""
+    per = -(-(end - begin) // world)
+    return per, min(begin + rank * per, end), min(begin + (rank + 1) * per, end)
+
+
 def king_host_bitset_allgather(planes, host_bits, words_per_sample: int, kin_threshold: float, max_results: int,
                                out: np.ndarray | None = None, group=None, side_stream=None):
     """The host-buffer seam on the G GPUs of one box with the planes replicated over NVLink instead of G times over
@@ -145,9 +153,7 @@ def king_host_bitset_allgather(planes, host_bits, words_per_sample: int, kin_thr
     side.wait_stream(main)
     planes.stream_begin(kin_threshold, max_results, part=(rank, world))
     for c, (b, e) in enumerate(chunks):
-        rows = e - b
-        pr = -(-rows // world)  # rows per rank in this chunk (the last rank's piece may be short or empty)
-        my_b, my_e = min(b + rank * pr, e), min(b + (rank + 1) * pr, e)
+        pr, my_b, my_e = chunk_piece(b, e, rank, world)
         buf = stage[c][: pr * world * words_per_sample]
         with torch.cuda.stream(side):
             mine = buf[rank * pr * words_per_sample: (rank + 1) * pr * words_per_sample]

@@ -196,7 +196,8 @@ int ck_king_host_bitset(ck_ctx *ctx, uint32_t num_samples, uint32_t split_factor
 /* The same seam for several GPUs of one box: every GPU calls it on its own ctx with the same host bit set and its own
  * part_index in [0, num_parts); the library picks the partition of the shard's pair matrix (bands of rows dealt in
  * snake order so that the parts carry equal work and every part can overlap its upload with its kernel) and returns
- * that part's retained pairs, sorted.  The parts are disjoint and their union is ck_king_host_bitset's result. */
+ * that part's retained pairs, sorted.  The parts are disjoint and their union is ck_king_host_bitset's result;
+ * max_results bounds each part (the caller applies the reference's overflow rule to the total if it wants it global). */
 int ck_king_host_bitset_part(ck_ctx *ctx, uint32_t num_samples, uint32_t split_factor, uint32_t shard_index,
                              uint32_t num_sites, const uint64_t *bit_set, float kin_threshold, uint32_t max_results,
                              ck_result *results, uint32_t *num_results, uint32_t part_index, uint32_t num_parts);

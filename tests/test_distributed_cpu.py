@@ -103,3 +103,19 @@ def test_stream_chunks_tile_the_shard_in_descending_order():
         assert all(b % gran == 0 and b < e for b, e in chunks)
         assert all(chunks[q][0] == chunks[q + 1][1] for q in range(len(chunks) - 1))  # contiguous, descending
         assert len(chunks) <= max(target, 1) + 1
+
+
+def test_allgather_pieces_cover_every_chunk_in_rank_order():
+    from cuking_b200.distributed import chunk_piece, stream_chunks
+
+    for n, world in [(100_000, 2), (282_816, 8), (5_000, 3), (1_030, 4)]:
+        for b, e in stream_chunks(n, 1024):
+            pieces = [chunk_piece(b, e, r, world) for r in range(world)]
+            per = pieces[0][0]
+            assert all(p[0] == per for p in pieces) and per * world >= e - b
+            covered = b
+            for r, (_, pb, pe) in enumerate(pieces):
+                assert pb == min(b + r * per, e) and pb <= pe <= e  # piece r sits at offset r * per of the gathered buffer
+                assert pb == covered or pb == e
+                covered = max(covered, pe)
+            assert covered == e
