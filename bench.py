@@ -356,7 +356,7 @@ def main():
     # algorithmic HBM bytes per launch: each tile streams its row samples and its column samples once
     # (tcgen05 variant: 128 x 80 tiles of 4-bit genotype codes; LOP3+POPC variants: 64 x 64 tiles of 3 bit planes)
     words = -(-(-(-n_sites // 32)) // 16) * 16
-    variant = args.variant if args.variant >= 0 else (3 if n_sites <= (1 << 21) else 2)  # the library's own choice
+    variant = args.variant if args.variant >= 0 else (3 if n_sites <= (1 << 23) else 2)  # the library's own choice
     umma = variant in (2, 3)
     tile_bytes = (128 + 80) * words * 16 if umma else 2 * 64 * words * 12
     popc_view = {
@@ -387,7 +387,7 @@ def main():
         roofline = {
             "bound": "tensor", "kernel": "king_fp4_kernel", "achieved": tops, "peak": 8481.0, "unit": "TOP/s (fp4 e2m1, dense)",
             "frac": tops / 8481.0, "traffic": fp4_traffic, "kernel_ms": kernel_ms, "units_per_launch": my_units,
-            "algorithmic_per_unit": "10 fp4 ops (5 MACs: xx, yy, yh, hy, hh) per pair-site, fp32 accumulation (exact: counts < 2^21)",
+            "algorithmic_per_unit": "10 fp4 ops (5 MACs: xx, yy, yh, hy, hh) per pair-site, fp32 accumulation (exact: counts <= 2^23)",
             "peak_source": "measured: tools/umma_mxf4_probe.cu on this pool's B200 (profiles/r01_mxf4_probe.txt), "
                            "kind::mxf4 M=128 N=208, 15595 MAC/clk/SM = 8481 TOP/s at the burst clock (nominal dense fp4: 9000)",
             "vs_4x_measured_bf16_burst": (tops / (4 * bf16["bf16_tflops"])) if bf16 else None,

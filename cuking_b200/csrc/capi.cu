@@ -801,7 +801,7 @@ static int stream_begin_impl(ck_planes *pl, float kin_threshold, uint32_t max_re
   ck_ctx *ctx = pl->ctx;
   if (num_parts == 0 || part_index >= num_parts) return fail(CK_ERR_INVALID_ARGUMENT, "part_index outside [0, num_parts)");
   if (!sm_diagonal(pl->map.sm)) return fail(CK_ERR_INVALID_ARGUMENT, "streaming delivery needs a diagonal shard");
-  if (planes_variant(pl) != 3) return fail(CK_ERR_INVALID_ARGUMENT, "streaming delivery needs the mxf4 kernel (variant 3, at most 2^21 sites)");
+  if (planes_variant(pl) != 3) return fail(CK_ERR_INVALID_ARGUMENT, "streaming delivery needs the mxf4 kernel (variant 3, at most 2^23 sites)");
   if (pl->stream_state) return fail(CK_ERR_INVALID_ARGUMENT, "a stream session is already open on these planes");
   if (pl->codes == nullptr) {
     pl->codes_bytes = std::max<size_t>(pl->codes_words(), 1) * 4;

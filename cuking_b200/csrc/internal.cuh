@@ -158,6 +158,6 @@ cudaError_t launch_king_fp4(const KingLaunch &k, uint32_t total_blocks, ck_ctx *
 // NULL, receives the first linear tile index of every band (+ the total); a band is kFp4BandRows rows of the shard.
 cudaError_t king_fp4_prepare(const KingLaunch &k, ck_ctx *ctx, cudaStream_t s, std::vector<uint64_t> *band_prefix);
 constexpr uint32_t kFp4BandRows = 8 * 128;
-constexpr uint32_t kFp4MaxSites = 1u << 21;  // exactness of the tensor core's fp32 accumulation was measured up to this count
+constexpr uint32_t kFp4MaxSites = 1u << 23;  // exactness of the tensor core's fp32 accumulation was measured up to this count
 
 }  // namespace ck

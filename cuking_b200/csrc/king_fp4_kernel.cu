@@ -8,9 +8,9 @@
 //     D_h = h_i.[y_j ; h_j] = ((i het, j hom) / 2 | both_het / 4)
 // kind::mxf4 multiplies 64 sites per instruction — twice kind::i8 — and the operands are 4 bits wide, so operand
 // expansion, TMEM stores and shared-memory traffic per site all halve as well.  Exactness: every operand is 0, 0.5 or
-// +-1 in E2M1, every product a multiple of 1/4, every partial sum a multiple of 1/4 below 2^22: exactly representable
+// +-1 in E2M1, every product a multiple of 1/4, every partial sum a multiple of 1/4 below 2^24 / 4: exactly representable
 // in the fp32 accumulator.  tools/umma_mxf4_probe.cu measured the tensor core's accumulation to be exact for counts up
-// to 2^21 on this pool's B200s (profiles/r01_mxf4_probe.txt); capi.cu routes cohorts with more than 2^21 sites to the
+// to 2^23 on this pool's B200s (profiles/r01_mxf4_probe.txt); capi.cu routes cohorts with more than 2^23 sites to the
 // int8 kernel (exact to 2^31) instead.
 //
 // Operands are expanded on the fly from 4-bit genotype codes (layout.cuh) chosen so that the expansion is ONE logic
@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     const uint32_t gi = i0 + r;
     const uint32_t lane_base = tmem_base + ((quad * 32u) << 16);
     // Cheap conservative screen before the exact kinship, in fp32 on the raw accumulators (no conversions).  With
-    // every count below 2^21 all the quantities below are exact in fp32:
+    // every count at most 2^23 the accumulators are exact and the two expressions below are exact or off by one ulp
+    // (relative 2^-23, far inside the margin whenever they matter: |num| >= 2^23 implies den >= 2^23 / |thr - 0.5|):
     //     num = 2 both_het - 4 opp - het_i - het_j = 2 (D_xx - D_yy - D_hy - D_yh)          (cuking.cu:289-292)
     //     den = 4 min(het_i, het_j)                = 8 (2 D_hh + min(D_hy, D_yh))           (cuking.cu:293)
     // and kin = fl(0.5 + fl(num / den)) differs from the real value by < 2^-22 relative, so a pair with

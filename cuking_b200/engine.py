@@ -211,7 +211,7 @@ class Planes:
         return res[: n.value]
 
     def king_variant(self) -> int:
-        """The pairwise kernel variant ck_king* runs on these planes (3 = FP4 tensor path, 2 = int8 beyond 2^21 sites)."""
+        """The pairwise kernel variant ck_king* runs on these planes (3 = FP4 tensor path, 2 = int8 beyond 2^23 sites)."""
         v = C.c_int()
         check(self._lib.ck_planes_king_variant(self._h, C.byref(v)))
         return int(v.value)

@@ -108,8 +108,8 @@ int ck_ctx_create(int device, ck_ctx **out);
 int ck_ctx_set_stream(ck_ctx *ctx, void *cuda_stream);
 /* Pairwise kernel variant: 0 = LOP3 + 5 POPC per pair and 32 sites, 1 = carry-save (2.5 POPC + 5 more LOP3),
  * 2 = tcgen05 int8 tensor-core formulation (five exact s32 GEMMs of indicator vectors), 3 = the same five GEMMs on
- * the FP4 tensor path (kind::mxf4 E2M1 operands, unit block scales, fp32 accumulation - exact for counts < 2^21; planes
- * with more than 2^21 sites are routed to variant 2), -1 = library default (= 3; also settable with the
+ * the FP4 tensor path (kind::mxf4 E2M1 operands, unit block scales, fp32 accumulation - exact for counts <= 2^23; planes
+ * with more than 2^23 sites are routed to variant 2), -1 = library default (= 3; also settable with the
  * CUKING_KING_VARIANT environment variable).  Results are bit-identical across variants. */
 int ck_ctx_set_king_variant(ck_ctx *ctx, int variant);
 int ck_ctx_synchronize(ck_ctx *ctx);
@@ -171,7 +171,7 @@ int ck_king(ck_planes *planes, float kin_threshold, uint32_t max_results, ck_res
             uint32_t *num_results, int sort);
 
 /* The pairwise kernel variant that ck_king* will run on these planes (the ctx's variant, except that variant 3 falls
- * back to 2 beyond 2^21 sites). */
+ * back to 2 beyond 2^23 sites). */
 int ck_planes_king_variant(const ck_planes *pl, int *variant);
 /* Same, restricted to the linear range [tile_begin, tile_end) of the sub-matrix's tile grid (row-major over the tiles
  * that can contain an i < j pair; the tile shape belongs to the active kernel variant, so tile counts are only
@@ -203,7 +203,7 @@ int ck_king_host_bitset_part(ck_ctx *ctx, uint32_t num_samples, uint32_t split_f
                              ck_result *results, uint32_t *num_results, uint32_t part_index, uint32_t num_parts);
 
 /* Streaming form of the seam, for callers that deliver the bit set in pieces (several readers + an NCCL all-gather over
- * NVLink, a file reader, ...).  Diagonal shards and the mxf4 kernel (<= 2^21 sites) only.
+ * NVLink, a file reader, ...).  Diagonal shards and the mxf4 kernel (<= 2^23 sites) only.
  *   ck_king_stream_begin(planes, thr, max_results, part_index, num_parts)
  *   ck_king_stream_rows(planes, rows, on_device, sample_begin, sample_end)   repeatedly, for DESCENDING ranges of shard-
  *       local sample indices that tile [0, rows of the shard): boundaries are multiples of ck_king_stream_granularity()

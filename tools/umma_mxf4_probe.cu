@@ -3,7 +3,7 @@
 // Questions answered on the GPU (nothing here is taken from documentation we cannot read offline):
 //   1. descriptor / scale-factor plumbing: SS mode (both operands in shared memory) against a CPU dot product;
 //   2. the TMEM layout of a 4-bit A operand (TS mode), tried under several hypotheses;
-//   3. exactness of the fp32 accumulation for counts up to 2^21 (operands in {-1, 0, +1}, scales 2^0): every partial
+//   3. exactness of the fp32 accumulation for counts up to 2^23 (operands in {-1, 0, 0.5, +1}, scales 2^0): every partial
 //      sum is an integer below 2^24, so an IEEE fp32 accumulator is exact — is the tensor core's?
 //   4. the sustained rate with the KING issue pattern: three issuers, N = 80 / 160 / 160, A from TMEM.
 // All scale factors are the constant 1.0 (0x7F), so the scale-factor TMEM layout does not matter: the whole region is
@@ -306,7 +306,7 @@ int main(int argc, char **argv) {
   // 3. exactness of long accumulations (total sites = K * reps)
   const int amode = (bad_ss == 0) ? (ts_mode ? ts_mode : 0) : 0;
   int bad_exact = 0;
-  for (int reps : {64, 1024, 8192, 16384}) {          // 2^13 ... 2^21 sites
+  for (int reps : {64, 1024, 8192, 16384, 65536}) {   // 2^13 ... 2^23 sites
     bad_exact += run<160>(64, reps, amode, 1, "exact_all_ones");
     bad_exact += run<160>(64, reps, amode, 2, "exact_random_01");
     bad_exact += run<160>(64, reps, amode, 0, "exact_random_pm1");
