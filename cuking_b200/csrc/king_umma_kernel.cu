@@ -34,6 +34,7 @@
 
 #include "internal.cuh"
 #include "king_common.cuh"
+#include "umma_common.cuh"
 
 namespace ck {
 
@@ -207,10 +208,14 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
           expand_codes(z[u][q].y, x[q][2], x[q][3], y[q][2], y[q][3], h[q][2], h[q][3]);
           expand_codes(z[u][q].z, x[q][4], x[q][5], y[q][4], y[q][5], h[q][4], h[q][5]);
           expand_codes(z[u][q].w, x[q][6], x[q][7], y[q][6], y[q][7], h[q][6], h[q][7]);
+          // keep the expansion ahead of the barrier wait below (the compiler otherwise sinks it onto the refill's critical path)
+          asm volatile("" ::"r"(x[q][0]), "r"(x[q][1]), "r"(x[q][2]), "r"(x[q][3]), "r"(x[q][4]), "r"(x[q][5]), "r"(x[q][6]), "r"(x[q][7]));
+          asm volatile("" ::"r"(y[q][0]), "r"(y[q][1]), "r"(y[q][2]), "r"(y[q][3]), "r"(y[q][4]), "r"(y[q][5]), "r"(y[q][6]), "r"(y[q][7]));
+          asm volatile("" ::"r"(h[q][0]), "r"(h[q][1]), "r"(h[q][2]), "r"(h[q][3]), "r"(h[q][4]), "r"(h[q][5]), "r"(h[q][6]), "r"(h[q][7]));
         }
         load_fill(n + kAPrefetch, z[u]);  // refill the registers just consumed
         const unsigned long long p1 = PROF_T();
-        if (n > 0) mbar_wait(&empty_a[group], (n - 1) & 1u);  // the MMAs that read the previous fill have completed
+        if (n > 0) mbar_wait_suspend(&empty_a[group], (n - 1) & 1u);  // the MMAs that read the previous fill have completed
         __syncwarp();  // tcgen05.st is warp-collective; the polling loop may leave the lanes diverged
         const unsigned long long p2 = PROF_T();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
         if (lane == 0) {
           // The issuers wait on full_a only.  Group 0's fill n starts B stage n, so it is group 0 that makes sure the
           // B operands are in shared memory before it announces the A stage (acquire on full_b, release on full_a).
-          if (group == 0) mbar_wait(&full_b[n % kBStages], (n / kBStages) & 1u);
+          if (group == 0) mbar_wait_suspend(&full_b[n % kBStages], (n / kBStages) & 1u);
           mbar_arrive(&full_a[group]);
         }
         const unsigned long long p3 = PROF_T();
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
     const uint2 *src = reinterpret_cast<const uint2 *>(p.codes) + (size_t(blk) * p.words * kTileSamples + ln) * 2 + half;
     const uint32_t b_off = (srow >> 3) * kSBO + (srow & 7) * 16 + half * kLBO;
     const uint32_t num_bstages = num_steps / kBStageSteps;
+    const uint32_t smem_base = smem_u32(smem);
     uint2 z[kBPrefetch][kBStageSteps];
     auto load_stage = [&](uint32_t m, uint2 (&dst)[kBStageSteps]) {
 #pragma unroll
@@ -268,14 +274,14 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
         }
         load_stage(m + kBPrefetch, z[u]);
         const unsigned long long p1 = PROF_T();
-        if (fill > 0) mbar_wait(&empty_b[s], (fill - 1) & 1u);  // the MMAs that read this stage have completed
+        if (fill > 0) mbar_wait_suspend(&empty_b[s], (fill - 1) & 1u);  // the MMAs that read this stage have completed
         const unsigned long long p2 = PROF_T();
-        uint8_t *stage = smem + size_t(s) * kBStageBytes + b_off;
+        const uint32_t stage = smem_base + s * kBStageBytes + b_off;
 #pragma unroll
         for (uint32_t q = 0; q < kBStageSteps; ++q) {
-          *reinterpret_cast<uint4 *>(stage + q * 2 * kLBO) = make_uint4(x[q][0], x[q][1], x[q][2], x[q][3]);
-          *reinterpret_cast<uint4 *>(stage + kBTile + q * 2 * kLBO) = make_uint4(y[q][0], y[q][1], y[q][2], y[q][3]);
-          *reinterpret_cast<uint4 *>(stage + 2 * kBTile + q * 2 * kLBO) = make_uint4(h[q][0], h[q][1], h[q][2], h[q][3]);
+          sts128(stage + q * 2 * kLBO, x[q][0], x[q][1], x[q][2], x[q][3]);
+          sts128(stage + kBTile + q * 2 * kLBO, y[q][0], y[q][1], y[q][2], y[q][3]);
+          sts128(stage + 2 * kBTile + q * 2 * kLBO, h[q][0], h[q][1], h[q][2], h[q][3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (tensor core)
         __syncwarp();
@@ -302,7 +308,7 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
     for (uint32_t ma = 0; ma < num_astages; ++ma) {
       const uint32_t g = ma & 1u, mb = ma >> 1, sb = mb % kBStages;  // A stage g, B stage mb (4 steps = 2 A stages)
       const unsigned long long q0 = PROF_T();
-      mbar_wait(&full_a[g], (ma >> 1) & 1u);  // covers the B stage too (see the A expanders)
+      mbar_wait_suspend(&full_a[g], (ma >> 1) & 1u);  // covers the B stage too (see the A expanders)
       const unsigned long long q1 = PROF_T();
       PROF_ADD(8 + which, q1 - q0);
       PROF_ADD(11, which == 0 ? 1 : 0);
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
   // ================= epilogue: all 16 warps; thread = row (TMEM lane quadrant warp % 4), column chunks by warp / 4 ====
   {
     __syncwarp();
-    mbar_wait(&acc_bar, 0);
+    mbar_wait_suspend(&acc_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t quad = warp & 3, group = warp >> 2;
     const uint32_t r = quad * 32 + lane;
