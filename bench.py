@@ -524,7 +524,8 @@ def main():
                             + ((f" (fixed cohort, tile grid split over {n_gpus} GPUs)" if fixed else
                                 f" (weak scaling: {n1}*sqrt({n_gpus}) samples, tile grid split over {n_gpus} GPUs)") if n_gpus > 1 else ""),
                 "tiles": tiles, "retained_pairs": retained, "kernel_variant": variant,
-                "l2": f"inputs larger than L2: {planes.device_bytes() * 3 // 5 >> 20} MiB of compute planes streamed per step",
+                "l2": (f"inputs larger than L2: {(-(-n_samples // 64) * 64 * words * 16) >> 20} MiB of genotype codes streamed per step" if umma else
+                       f"inputs larger than L2: {(-(-n_samples // 64) * 64 * words * 12) >> 20} MiB of compute planes streamed per step"),
                 "input_synthesis_s": round(synth_s, 3),
             },
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
