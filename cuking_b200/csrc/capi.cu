@@ -657,10 +657,15 @@ static int finish_results(ck_ctx *ctx, ck_result *d_emit, uint32_t max_results, 
   const uint32_t n = uint32_t(count);
   if (n == 0) return CK_OK;
 
-  cudaEvent_t t0, t1, t2;
-  CK_CUDA(cudaEventCreate(&t0));
-  CK_CUDA(cudaEventCreate(&t1));
-  CK_CUDA(cudaEventCreate(&t2));
+  struct Events {  // destroyed on every exit path
+    cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+    ~Events() {
+      for (cudaEvent_t x : e)
+        if (x) cudaEventDestroy(x);
+    }
+  } ev;
+  for (cudaEvent_t &x : ev.e) CK_CUDA(cudaEventCreate(&x));
+  cudaEvent_t t0 = ev.e[0], t1 = ev.e[1], t2 = ev.e[2];
   cudaEventRecord(t0, s);
   const ck_result *d_final = d_emit;
   if (sort) {
@@ -676,9 +681,6 @@ static int finish_results(ck_ctx *ctx, ck_result *d_emit, uint32_t max_results, 
   ctx->timings.sort_ms = elapsed(t0, t1);
   ctx->timings.d2h_ms = elapsed(t1, t2);
   if (dbg) fprintf(stderr, "[ck] sort+d2h: host %.2f ms (device sort %.2f, d2h %.2f)\n", ms_since(tp1), ctx->timings.sort_ms, ctx->timings.d2h_ms);
-  cudaEventDestroy(t0);
-  cudaEventDestroy(t1);
-  cudaEventDestroy(t2);
   CK_CUDA(e);
   return CK_OK;
 }
