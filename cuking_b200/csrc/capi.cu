@@ -787,7 +787,7 @@ int ck_king_counts(ck_planes *pl, const uint32_t *sample_i, const uint32_t *samp
 // pair with is already on the device.  The bottom chunks hold few tiles, so only the first small upload is exposed.
 static bool host_bitset_can_pipeline(const ck_planes *pl) {
   static const bool off = getenv("CUKING_NO_PIPELINE") != nullptr;
-  return !off && planes_variant(pl) == 3 && sm_diagonal(pl->map.sm) && sm_rows(pl->map.sm) >= 4 * kFp4BandRows;
+  return !off && planes_variant(pl) >= 2 && sm_diagonal(pl->map.sm) && sm_rows(pl->map.sm) >= 4 * kFp4BandRows;
 }
 
 // Owner of band b when the shard is split into num_parts parts: bands are dealt in snake order (0 .. P-1, P-1 .. 0, ...):
@@ -803,7 +803,8 @@ static int stream_begin_impl(ck_planes *pl, float kin_threshold, uint32_t max_re
   ck_ctx *ctx = pl->ctx;
   if (num_parts == 0 || part_index >= num_parts) return fail(CK_ERR_INVALID_ARGUMENT, "part_index outside [0, num_parts)");
   if (!sm_diagonal(pl->map.sm)) return fail(CK_ERR_INVALID_ARGUMENT, "streaming delivery needs a diagonal shard");
-  if (planes_variant(pl) != 3) return fail(CK_ERR_INVALID_ARGUMENT, "streaming delivery needs the mxf4 kernel (variant 3, at most 2^23 sites)");
+  const int variant = planes_variant(pl);
+  if (variant < 2) return fail(CK_ERR_INVALID_ARGUMENT, "streaming delivery needs a tensor-core kernel variant (2 or 3): their band-ordered tiles");
   if (pl->stream_state) return fail(CK_ERR_INVALID_ARGUMENT, "a stream session is already open on these planes");
   if (pl->codes == nullptr) {
     pl->codes_bytes = std::max<size_t>(pl->codes_words(), 1) * 4;
@@ -818,11 +819,12 @@ static int stream_begin_impl(ck_planes *pl, float kin_threshold, uint32_t max_re
   st->k.max_results = max_results;
   st->k.results = ctx->result_buf;
   st->k.counter = ctx->d_counter;
+  st->variant = variant;
   st->part_index = part_index;
   st->num_parts = num_parts;
   st->max_results = max_results;
   st->next_end = sm_rows(pl->map.sm);
-  cudaError_t e = king_fp4_prepare(st->k, ctx, ctx->stream, &st->band_prefix);
+  cudaError_t e = band_prepare(st->k, kBandTileCols, ctx, ctx->stream, &st->band_prefix, nullptr);
   if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream);
   if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[0], ctx->stream);
   if (e != cudaSuccess) {
@@ -847,7 +849,7 @@ static int stream_rows_device(ck_planes *pl, const uint64_t *d_rows, uint32_t s0
                                          "ck_king_stream_granularity()");
   const uint32_t block0 = s0 / kTileSamples, num_blocks = ceil_div(s1, kTileSamples) - block0;
   CK_CUDA(launch_import_ref_range(*pl, d_rows, s0, block0, num_blocks, s));
-  CK_CUDA(launch_finalize_codes_range(*pl, 3, block0, num_blocks, s));
+  CK_CUDA(launch_finalize_codes_range(*pl, st->variant, block0, num_blocks, s));
   ctx->timings.king_launches += 2;
   const uint32_t band_lo = s0 / kFp4BandRows, band_hi = ceil_div(std::min(s1, n), kFp4BandRows);
   KingLaunch k = st->k;
@@ -857,7 +859,9 @@ static int stream_rows_device(ck_planes *pl, const uint64_t *d_rows, uint32_t s0
     while (e < band_hi && band_owner(e, st->num_parts) == st->part_index) ++e;
     k.tile_begin = st->band_prefix[b];
     k.tile_end = st->band_prefix[e];
-    if (k.tile_end > k.tile_begin) CK_CUDA(launch_king_fp4(k, pl->map.num_blocks, ctx, s, &ctx->timings.king_launches));
+    if (k.tile_end > k.tile_begin)
+      CK_CUDA(st->variant == 3 ? launch_king_fp4(k, pl->map.num_blocks, ctx, s, &ctx->timings.king_launches)
+                               : launch_king_umma(k, pl->map.num_blocks, ctx, s, &ctx->timings.king_launches));
     b = e;
   }
   st->next_end = s0;
@@ -869,6 +873,7 @@ static int stream_end_impl(ck_planes *pl, ck_result *results, uint32_t *num_resu
   ck_ctx *ctx = pl->ctx;
   const bool complete = st->next_end == 0;
   const uint32_t max_results = st->max_results;
+  const int variant = st->variant;
   delete st;
   pl->stream_state = nullptr;
   CK_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -878,7 +883,7 @@ static int stream_end_impl(ck_planes *pl, ck_result *results, uint32_t *num_resu
   }
   pl->compute_stale = true;
   pl->codes_stale = false;
-  pl->codes_kind = 3;
+  pl->codes_kind = variant;
   return finish_results(ctx, ctx->result_buf, max_results, results, 0, num_results, 1);
 }
 

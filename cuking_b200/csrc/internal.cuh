@@ -139,12 +139,29 @@ struct KingLaunch {
 struct KingStream {  // state of one ck_king_stream_begin .. end session (also used by the pipelined host-buffer path)
   KingLaunch k{};
   std::vector<uint64_t> band_prefix;  // first linear tile of every band + total
+  int variant = 3;                    // 3 = mxf4 kernel, 2 = int8 kernel (same 128 x 80 band-ordered tiles)
   uint32_t part_index = 0, num_parts = 1;
   uint32_t max_results = 0;
   uint32_t next_end = 0;              // rows [next_end, n) have been delivered
 };
 uint64_t king_num_tiles(uint32_t num_row_blocks, uint32_t num_col_blocks, bool triangular);
 cudaError_t launch_king(const KingLaunch &k, int variant, cudaStream_t s, uint32_t *launches);
+
+// ---- band_tiles.cu: tile enumeration shared by the two tensor-core kernels ----
+constexpr uint32_t kBandTileRows = 128;  // tile rows (TMEM lanes)
+constexpr uint32_t kBandRowTiles = 8;    // row tiles per band
+constexpr uint32_t kBandTileCols = 80;   // tile columns of both tensor-core kernels (what the streaming seam assumes)
+struct BandTiles {                       // device view of the band table (ctx scratch)
+  const unsigned long long *band_prefix;  // [num_bands + 1] tiles before band b
+  const uint32_t *band_first_col;         // [num_bands] first column tile enumerated in band b
+  uint32_t num_bands, num_row_tiles, num_col_tiles;
+};
+uint64_t band_num_tiles(const KingLaunch &k, uint32_t tile_cols);
+// Uploads the band table for this launch geometry unless it is already on the device (then: no copy, no stream
+// synchronisation - the streaming seam launches many tile ranges back to back).  `band_prefix`, when not NULL, receives
+// the first linear tile index of every band (+ the total); `tiles`, when not NULL, the device view.
+cudaError_t band_prepare(const KingLaunch &k, uint32_t tile_cols, ck_ctx *ctx, cudaStream_t s, std::vector<uint64_t> *band_prefix,
+                         BandTiles *tiles);
 
 // ---- king_umma_kernel.cu (variant 2: tcgen05 int8 tensor-core formulation, 128 x 96 tiles) ----
 uint64_t king_umma_num_tiles(const KingLaunch &k);
@@ -153,11 +170,9 @@ cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, ck_ctx 
 // ---- king_fp4_kernel.cu (variant 3: tcgen05 kind::mxf4 formulation, 128 x 80 tiles, band-ordered tile enumeration) ----
 uint64_t king_fp4_num_tiles(const KingLaunch &k);
 cudaError_t launch_king_fp4(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches);
-// Uploads the band table for this launch geometry unless it is already on the device (then: no copy, no stream
-// synchronisation - the pipelined host-buffer path launches many tile ranges back to back).  `band_prefix`, when not
-// NULL, receives the first linear tile index of every band (+ the total); a band is kFp4BandRows rows of the shard.
+// band table of this launch geometry for the mxf4 kernel's tile shape (band_prepare)
 cudaError_t king_fp4_prepare(const KingLaunch &k, ck_ctx *ctx, cudaStream_t s, std::vector<uint64_t> *band_prefix);
-constexpr uint32_t kFp4BandRows = 8 * 128;
+constexpr uint32_t kFp4BandRows = kBandRowTiles * kBandTileRows;
 constexpr uint32_t kFp4MaxSites = 1u << 23;  // exactness of the tensor core's fp32 accumulation was measured up to this count
 
 }  // namespace ck

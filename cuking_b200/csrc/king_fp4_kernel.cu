@@ -26,7 +26,7 @@
 //                 kinship in the reference's fp32 order and append through the warp-aggregated atomic.
 // TMEM: 400 accumulator columns + 4 x 24 A columns + 16 scale-factor columns (all 0x7F = 2^0; every byte is the same,
 // so the scale-factor layout is immaterial) = 512.
-// Tiles are enumerated in bands of kBand row tiles, column-major inside a band, so that the ~148 tiles in flight share
+// Tiles are enumerated in bands of 8 row tiles (band_tiles.cu), column-major inside a band, so that the ~148 tiles in flight share
 // 8 row blocks and ~19 column blocks and the genotype codes are served from L2.
 #include <cuda_runtime.h>
 
@@ -61,9 +61,9 @@ constexpr uint32_t kFColXX = 0, kFColY = kFN, kFColH = 3 * kFN;  // accumulators
 constexpr uint32_t kFColA = 5 * kFN;        // A ring: slot s at kFColA + 24 s: x, y, h (8 columns = 64 E2M1 each)
 constexpr uint32_t kFColSF = kFColA + 24 * kFSlots;  // 16 columns of scale factors
 constexpr uint32_t kFTmemCols = 512;
-constexpr uint32_t kBand = 8;               // row tiles per band of the tile enumeration
 static_assert(kFBWarps * 32 == 2 * kFN, "two threads per column sample must fill whole warps");
 static_assert(kFColSF + 16 <= kFTmemCols, "TMEM budget");
+static_assert(kFM == kBandTileRows && (kFN == kBandTileCols || CK_FP4_TILE_N != 80), "band enumeration tile shape");
 static_assert(kChunkWords % (2 * kFGroups * kFAPrefetchSteps) == 0 && kChunkWords % (2 * kFSub * kFBPrefetch) == 0, "loop unrolling");
 
 template <uint32_t AS, uint32_t BS, uint32_t NS>
@@ -103,12 +103,6 @@ __device__ unsigned long long g_fp4_prof[16];
 #define FPROF_ADD(slot, dt) do { (void)(dt); } while (0)
 #endif
 
-struct Fp4Tiles {  // band enumeration, built on the host per launch
-  const unsigned long long *band_prefix;  // [num_bands + 1] tiles before band b
-  const uint32_t *band_first_col;         // [num_bands] first column tile enumerated in band b
-  uint32_t num_bands, num_row_tiles, num_col_tiles;
-};
-
 // Pins eight values in registers at this point of the instruction stream: without it the compiler sinks the operand
 // expansion below the barrier wait that follows, i.e. onto the critical path of the A-slot refill.
 __device__ __forceinline__ void pin8(const uint32_t (&v)[8]) {
@@ -121,7 +115,7 @@ __device__ __forceinline__ void expand_fp4(uint32_t z, uint32_t &x, uint32_t &y,
 }
 
 template <uint32_t AS, uint32_t BS, uint32_t NS>
-__global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch p, const Fp4Tiles tiles) {
+__global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch p, const BandTiles tiles) {
   using G = Fp4Geo<AS, BS, NS>;
   constexpr uint32_t kAStages = G::kAStages;
   extern __shared__ uint8_t smem_raw[];
@@ -130,16 +124,9 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // ---- which tile: band b (kBand row tiles), column-major inside the band ----
-  const unsigned long long t = p.tile_begin + blockIdx.x;
-  uint32_t lo = 0, hi = tiles.num_bands;  // largest b with band_prefix[b] <= t
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (tiles.band_prefix[mid] <= t) lo = mid; else hi = mid;
-  }
-  const uint32_t band_rows = min(kBand, tiles.num_row_tiles - lo * kBand);
-  const uint32_t q_in_band = uint32_t(t - tiles.band_prefix[lo]);
-  const uint32_t ti = lo * kBand + q_in_band % band_rows, tj = tiles.band_first_col[lo] + q_in_band / band_rows;
+  // ---- which tile: band order (band_tiles.cu) ----
+  uint32_t ti, tj;
+  band_decode(tiles, p.tile_begin + blockIdx.x, ti, tj);
   const uint32_t row0 = ti * kFM, col0 = tj * kFN;  // offsets inside the sub-matrix
   const uint32_t rows_here = min(kFM, p.num_rows - row0), cols_here = min(kFN, p.num_cols - col0);
   const uint32_t i0 = p.row_global0 + row0, j0 = p.col_global0 + col0;
@@ -430,39 +417,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
   if (warp == kFExpWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kFTmemCols));
 }
 
-// ---- host side: band table -----------------------------------------------------------------------------------------
-
-struct BandTable {
-  std::vector<unsigned long long> band_prefix;
-  std::vector<uint32_t> band_first_col;
-  uint32_t num_bands = 0, num_row_tiles = 0, num_col_tiles = 0;
-};
-
-// first column tile holding an i < j pair for row tile ti (num_col_tiles if there is none)
-uint32_t first_alive_col(const KingLaunch &k, uint32_t ti, uint32_t num_col_tiles) {
-  const uint64_t i_min = uint64_t(k.row_global0) + uint64_t(ti) * kFM;
-  if (uint64_t(k.col_global0) + k.num_cols - 1 <= i_min) return num_col_tiles;
-  if (i_min < k.col_global0) return 0;
-  const uint64_t need = i_min - k.col_global0 + 1;  // need a local column index >= need in the tile
-  const uint32_t first = uint32_t(need / kFN);      // the tile that holds local column `need`
-  return first < num_col_tiles ? first : num_col_tiles - 1;
-}
-
-BandTable build_band_table(const KingLaunch &k) {
-  BandTable bt;
-  bt.num_row_tiles = ceil_div(k.num_rows, kFM);
-  bt.num_col_tiles = ceil_div(k.num_cols, kFN);
-  bt.num_bands = ceil_div(bt.num_row_tiles, kBand);
-  bt.band_prefix.assign(bt.num_bands + 1, 0);
-  bt.band_first_col.assign(std::max<uint32_t>(bt.num_bands, 1), 0);
-  for (uint32_t b = 0; b < bt.num_bands; ++b) {
-    const uint32_t rows = std::min(kBand, bt.num_row_tiles - b * kBand);
-    const uint32_t first = first_alive_col(k, b * kBand, bt.num_col_tiles);  // non-decreasing in the row tile
-    bt.band_first_col[b] = first;
-    bt.band_prefix[b + 1] = bt.band_prefix[b] + uint64_t(rows) * (bt.num_col_tiles - first);
-  }
-  return bt;
-}
+// ---- host side ------------------------------------------------------------------------------------------------------
 
 struct Fp4Config { uint32_t as, bs, ns; };
 Fp4Config fp4_config() {  // stage geometry; CUKING_FP4_STAGE = "<steps per A stage>x<steps per B stage>x<B stages>" is a tuning knob
@@ -478,7 +433,7 @@ Fp4Config fp4_config() {  // stage geometry; CUKING_FP4_STAGE = "<steps per A st
 }
 
 template <uint32_t AS, uint32_t BS, uint32_t NS>
-cudaError_t launch_cfg(const KingLaunch &part, const Fp4Tiles &tiles, cudaStream_t s) {
+cudaError_t launch_cfg(const KingLaunch &part, const BandTiles &tiles, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(king_fp4_kernel<AS, BS, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Fp4Geo<AS, BS, NS>::kSmem));
@@ -499,53 +454,18 @@ extern "C" void ck_debug_fp4_prof(unsigned long long *out) {
 }
 #endif
 
-uint64_t king_fp4_num_tiles(const KingLaunch &k) {
-  if (k.num_rows == 0 || k.num_cols == 0) return 0;
-  return build_band_table(k).band_prefix.back();
-}
+uint64_t king_fp4_num_tiles(const KingLaunch &k) { return band_num_tiles(k, kFN); }
 
 cudaError_t king_fp4_prepare(const KingLaunch &k, ck_ctx *ctx, cudaStream_t s, std::vector<uint64_t> *band_prefix) {
-  const uint64_t key[3] = {3, (uint64_t(k.num_rows) << 32) | k.num_cols, (uint64_t(k.row_global0) << 32) | k.col_global0};
-  const bool cached = ctx->tile_table != nullptr && ctx->tile_table_key[0] == key[0] && ctx->tile_table_key[1] == key[1] &&
-                      ctx->tile_table_key[2] == key[2];
-  if (cached && band_prefix == nullptr) return cudaSuccess;
-  const BandTable bt = build_band_table(k);
-  if (band_prefix) band_prefix->assign(bt.band_prefix.begin(), bt.band_prefix.end());
-  if (cached) return cudaSuccess;
-  const size_t prefix_bytes = (bt.band_prefix.size() * 8 + 255) & ~size_t(255), first_bytes = bt.band_first_col.size() * 4;
-  if (ctx->tile_table_bytes < prefix_bytes + first_bytes) {  // grow-only scratch owned by the ctx
-    if (ctx->tile_table) cudaFree(ctx->tile_table);
-    ctx->tile_table = nullptr;
-    ctx->tile_table_bytes = 0;
-    ctx->tile_table_key[0] = ~0ull;
-    cudaError_t e = cudaMalloc(&ctx->tile_table, prefix_bytes + first_bytes);
-    if (e != cudaSuccess) return e;
-    ctx->tile_table_bytes = prefix_bytes + first_bytes;
-  }
-  ctx->tile_table_key[0] = ~0ull;
-  auto *d_prefix = static_cast<unsigned long long *>(ctx->tile_table);
-  auto *d_first = reinterpret_cast<uint32_t *>(static_cast<char *>(ctx->tile_table) + ctx->tile_table_bytes - first_bytes);
-  cudaError_t e = cudaMemcpyAsync(d_prefix, bt.band_prefix.data(), bt.band_prefix.size() * 8, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_first, bt.band_first_col.data(), first_bytes, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the host vectors die with this frame
-  if (e == cudaSuccess) {
-    ctx->tile_table_key[0] = key[0];
-    ctx->tile_table_key[1] = key[1];
-    ctx->tile_table_key[2] = key[2];
-  }
-  return e;
+  return band_prepare(k, kFN, ctx, s, band_prefix, nullptr);
 }
 
 cudaError_t launch_king_fp4(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches) {
   (void)total_blocks;  // every row / column a tile reads lies inside the shard's allocated blocks
   if (k.tile_end <= k.tile_begin) return cudaSuccess;
-  cudaError_t e = king_fp4_prepare(k, ctx, s, nullptr);
+  BandTiles tiles{};
+  cudaError_t e = band_prepare(k, kFN, ctx, s, nullptr, &tiles);
   if (e != cudaSuccess) return e;
-  const uint32_t num_row_tiles = ceil_div(k.num_rows, kFM), num_bands = ceil_div(num_row_tiles, kBand);
-  const size_t first_bytes = size_t(std::max<uint32_t>(num_bands, 1)) * 4;
-  auto *d_prefix = static_cast<unsigned long long *>(ctx->tile_table);
-  auto *d_first = reinterpret_cast<uint32_t *>(static_cast<char *>(ctx->tile_table) + ctx->tile_table_bytes - first_bytes);
-  const Fp4Tiles tiles{d_prefix, d_first, num_bands, num_row_tiles, ceil_div(k.num_cols, kFN)};
   const Fp4Config cfg = fp4_config();
   constexpr uint64_t kMaxGrid = 1ull << 30;
   for (uint64_t t = k.tile_begin; e == cudaSuccess && t < k.tile_end; t += kMaxGrid) {

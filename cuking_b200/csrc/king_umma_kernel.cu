@@ -58,6 +58,7 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColXX = 0, kColY = kUN, kColH = 3 * kUN;  // accumulators: xx | (yy|yh) | (hy|hh)
 constexpr uint32_t kColA = 5 * kUN;                // A ring: slot s at kColA + 24 s: x, y, h (8 columns each)
 static_assert(kBWarps * 32 == 2 * kUN, "two threads per column sample must fill whole warps");
+static_assert(kUM == kBandTileRows && kUN == kBandTileCols, "band enumeration tile shape");
 static_assert(kColA + 24 * kASlots <= kTmemCols, "TMEM budget");
 static_assert(kASlots == 2 * kAStageSteps && kBStageSteps == 2 * kAStageSteps, "stage geometry");
 static_assert(kChunkWords % (2 * kAStageSteps * kAPrefetch) == 0 && kChunkWords % (kBStageSteps * kBPrefetch) == 0, "loop unrolling");
@@ -106,13 +107,6 @@ __device__ unsigned long long g_umma_prof[16];
 #define PROF_ADD(slot, dt) do { (void)(dt); } while (0)
 #endif
 
-struct UmmaTiles {  // alive-tile enumeration (tiles with at least one i < j pair), built on the host per launch
-  const unsigned long long *row_prefix;  // [num_row_tiles + 1] alive tiles before row tile t
-  const uint32_t *first_col;             // [num_row_tiles] first alive column tile of row tile t
-  uint32_t num_row_tiles, num_col_tiles;
-  uint32_t total_blocks;                 // 64-sample plane blocks allocated (reads beyond are treated as missing)
-};
-
 // One code word = 8 genotypes (nibbles: 1 het, 2 hom-alt, 4 hom-ref, 0 missing) -> 8 bytes of each operand row.
 // PRMT picks, per output byte, the table byte indexed by the nibble: tables hold the operand value of each code.
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -135,7 +129,7 @@ __device__ __forceinline__ void expand_codes(uint32_t z, uint32_t &x_lo, uint32_
   h_hi = prmt(0x0000ff00u, 0x00000000u, zh);
 }
 
-__global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunch p, const UmmaTiles tiles) {
+__global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunch p, const BandTiles tiles) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_a[2], empty_a[2], full_b[kBStages], empty_b[kBStages], acc_bar;
   __shared__ uint32_t tmem_base_smem;
@@ -143,17 +137,13 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // ---- which tile ----
-  const unsigned long long t = p.tile_begin + blockIdx.x;
-  uint32_t lo = 0, hi = tiles.num_row_tiles;  // largest ti with row_prefix[ti] <= t
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (tiles.row_prefix[mid] <= t) lo = mid; else hi = mid;
-  }
-  const uint32_t ti = lo, tj = tiles.first_col[ti] + uint32_t(t - tiles.row_prefix[ti]);
+  // ---- which tile: band order (band_tiles.cu) ----
+  uint32_t ti, tj;
+  band_decode(tiles, p.tile_begin + blockIdx.x, ti, tj);
   const uint32_t row0 = ti * kUM, col0 = tj * kUN;           // offsets inside the sub-matrix
   const uint32_t rows_here = min(kUM, p.num_rows - row0), cols_here = min(kUN, p.num_cols - col0);
   const uint32_t i0 = p.row_global0 + row0, j0 = p.col_global0 + col0;
+  if (j0 + cols_here - 1 <= i0) return;  // no i < j pair in this tile (below the diagonal): whole CTA leaves
 
   if (warp == kExpanderWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(kTmemCols));
@@ -183,7 +173,7 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
     const uint32_t group = warp >> 2, srow = (warp & 3) * 32 + lane;
     const uint32_t slot = p.row_block0 * kTileSamples + row0 + srow;
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
-    const bool in_range = blk < tiles.total_blocks && srow < rows_here;
+    const bool in_range = srow < rows_here;
     const uint4 *src = reinterpret_cast<const uint4 *>(p.codes) + size_t(blk) * p.words * kTileSamples + ln;
     const uint32_t ta = tmem_base + ((uint32_t(warp & 3) * 32u) << 16) + kColA + group * (kAStageSteps * 24);
     const uint32_t num_fills = num_steps / kASlots;  // fills of this group's stage
@@ -247,7 +237,7 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
     const uint32_t half = idx / kUN, srow = idx % kUN;  // half: K bytes 16*half .. 16*half+15 of every step
     const uint32_t slot = p.col_block0 * kTileSamples + col0 + srow;
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
-    const bool in_range = blk < tiles.total_blocks && srow < cols_here;
+    const bool in_range = srow < cols_here;
     const uint2 *src = reinterpret_cast<const uint2 *>(p.codes) + (size_t(blk) * p.words * kTileSamples + ln) * 2 + half;
     const uint32_t b_off = (srow >> 3) * kSBO + (srow & 7) * 16 + half * kLBO;
     const uint32_t num_bstages = num_steps / kBStageSteps;
@@ -374,39 +364,6 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
   if (warp == kExpanderWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
 }
 
-// ---- host side: alive-tile table ---------------------------------------------------------------------------------
-
-struct TileTable {
-  std::vector<unsigned long long> row_prefix;
-  std::vector<uint32_t> first_col;
-  uint32_t num_row_tiles = 0, num_col_tiles = 0;
-};
-
-TileTable build_tile_table(const KingLaunch &k) {
-  TileTable tt;
-  tt.num_row_tiles = ceil_div(k.num_rows, kUM);
-  tt.num_col_tiles = ceil_div(k.num_cols, kUN);
-  tt.row_prefix.assign(tt.num_row_tiles + 1, 0);
-  tt.first_col.assign(std::max<uint32_t>(tt.num_row_tiles, 1), 0);
-  for (uint32_t ti = 0; ti < tt.num_row_tiles; ++ti) {
-    const uint64_t i_min = uint64_t(k.row_global0) + uint64_t(ti) * kUM;
-    // first column tile whose largest j exceeds i_min:  col_global0 + min(96 tj + 95, num_cols - 1) > i_min
-    uint32_t first = tt.num_col_tiles;
-    if (uint64_t(k.col_global0) + k.num_cols - 1 > i_min) {
-      if (i_min < k.col_global0) {
-        first = 0;
-      } else {
-        const uint64_t need = i_min - k.col_global0 + 1;  // need local j_max >= need
-        first = uint32_t(need <= kUN - 1 ? 0 : (need - (kUN - 1) + kUN - 1) / kUN);
-        if (first >= tt.num_col_tiles) first = tt.num_col_tiles - 1;  // the last (ragged) tile holds num_cols - 1
-      }
-    }
-    tt.first_col[ti] = first;
-    tt.row_prefix[ti + 1] = tt.row_prefix[ti] + (tt.num_col_tiles - first);
-  }
-  return tt;
-}
-
 }  // namespace
 
 #ifdef CK_UMMA_PROFILE
@@ -417,12 +374,10 @@ extern "C" void ck_debug_umma_prof(unsigned long long *out) {
 }
 #endif
 
-uint64_t king_umma_num_tiles(const KingLaunch &k) {
-  if (k.num_rows == 0 || k.num_cols == 0) return 0;
-  return build_tile_table(k).row_prefix.back();
-}
+uint64_t king_umma_num_tiles(const KingLaunch &k) { return band_num_tiles(k, kUN); }
 
 cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches) {
+  (void)total_blocks;  // every row / column a tile reads lies inside the shard's allocated blocks
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(king_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUmmaSmem));
@@ -430,23 +385,9 @@ cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, ck_ctx 
     configured = true;
   }
   if (k.tile_end <= k.tile_begin) return cudaSuccess;
-  const TileTable tt = build_tile_table(k);
-  const size_t prefix_bytes = (tt.row_prefix.size() * 8 + 255) & ~size_t(255), first_bytes = tt.first_col.size() * 4;
-  if (ctx->tile_table_bytes < prefix_bytes + first_bytes) {  // grow-only scratch owned by the ctx
-    if (ctx->tile_table) cudaFree(ctx->tile_table);
-    ctx->tile_table = nullptr;
-    ctx->tile_table_bytes = 0;
-    cudaError_t e = cudaMalloc(&ctx->tile_table, prefix_bytes + first_bytes);
-    if (e != cudaSuccess) return e;
-    ctx->tile_table_bytes = prefix_bytes + first_bytes;
-  }
-  ctx->tile_table_key[0] = ~0ull;  // the scratch no longer holds the mxf4 kernel's band table
-  auto *d_prefix = static_cast<unsigned long long *>(ctx->tile_table);
-  auto *d_first = reinterpret_cast<uint32_t *>(static_cast<char *>(ctx->tile_table) + prefix_bytes);
-  cudaError_t e = cudaMemcpyAsync(d_prefix, tt.row_prefix.data(), tt.row_prefix.size() * 8, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_first, tt.first_col.data(), first_bytes, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the host vectors die with this frame
-  UmmaTiles tiles{d_prefix, d_first, tt.num_row_tiles, tt.num_col_tiles, total_blocks};
+  BandTiles tiles{};
+  cudaError_t e = band_prepare(k, kUN, ctx, s, nullptr, &tiles);
+  if (e != cudaSuccess) return e;
   constexpr uint64_t kMaxGrid = 1ull << 30;
   for (uint64_t t = k.tile_begin; e == cudaSuccess && t < k.tile_end; t += kMaxGrid) {
     KingLaunch part = k;

@@ -52,4 +52,17 @@ __device__ __forceinline__ uint32_t elect_one() {
   return elected;
 }
 
+// Linear tile index -> (row tile, column tile) of the band enumeration (band_tiles.cu).
+__device__ __forceinline__ void band_decode(const BandTiles &tiles, unsigned long long t, uint32_t &ti, uint32_t &tj) {
+  uint32_t lo = 0, hi = tiles.num_bands;  // largest b with band_prefix[b] <= t
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (tiles.band_prefix[mid] <= t) lo = mid; else hi = mid;
+  }
+  const uint32_t band_rows = min(kBandRowTiles, tiles.num_row_tiles - lo * kBandRowTiles);
+  const uint32_t q = uint32_t(t - tiles.band_prefix[lo]);
+  ti = lo * kBandRowTiles + q % band_rows;
+  tj = tiles.band_first_col[lo] + q / band_rows;
+}
+
 }  // namespace ck

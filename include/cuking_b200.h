@@ -203,7 +203,7 @@ int ck_king_host_bitset_part(ck_ctx *ctx, uint32_t num_samples, uint32_t split_f
                              ck_result *results, uint32_t *num_results, uint32_t part_index, uint32_t num_parts);
 
 /* Streaming form of the seam, for callers that deliver the bit set in pieces (several readers + an NCCL all-gather over
- * NVLink, a file reader, ...).  Diagonal shards and the mxf4 kernel (<= 2^23 sites) only.
+ * NVLink, a file reader, ...).  Diagonal shards and the tensor-core kernel variants (2, 3) only.
  *   ck_king_stream_begin(planes, thr, max_results, part_index, num_parts)
  *   ck_king_stream_rows(planes, rows, on_device, sample_begin, sample_end)   repeatedly, for DESCENDING ranges of shard-
  *       local sample indices that tile [0, rows of the shard): boundaries are multiples of ck_king_stream_granularity()

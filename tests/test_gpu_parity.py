@@ -319,6 +319,17 @@ def test_streaming_delivery_matches_oracle(ctx):
                     got.append(pl.stream_end(1 << 20))
             got = np.concatenate(got)
             assert_results_equal(np.sort(got, order=["sample_i", "sample_j"]), want)
+    ctx.set_king_variant(2)  # the int8 tensor kernel shares the band-ordered tiles, hence the seam
+    with ctx.planes(ck.submatrix(n), s) as pl:
+        pl.stream_begin(0.1, 1 << 20)
+        for b, e in chunks:
+            pl.stream_rows(dev_bits[b * w: e * w], b, e)
+        assert_results_equal(pl.stream_end(1 << 20), want)
+    ctx.set_king_variant(0)
+    with ctx.planes(ck.submatrix(n), s) as pl:
+        with pytest.raises(ck.CukingError):
+            pl.stream_begin(0.1, 1 << 20)                     # LOP3+POPC kernels: other tile order
+    ctx.set_king_variant(-1)
     with ctx.planes(ck.submatrix(n), s) as pl:  # protocol errors are reported, not executed
         pl.stream_begin(0.1, 1 << 20)
         with pytest.raises(ck.CukingError):
