@@ -342,6 +342,35 @@ def test_streaming_delivery_matches_oracle(ctx):
             pl.stream_begin(0.1, 1 << 20)                     # off-diagonal shard
 
 
+def test_allgather_fed_seam_single_rank(ctx):
+    # cuking_b200.distributed.king_host_bitset_allgather with a one-rank NCCL group: pinned host bit set -> per-chunk
+    # upload on a side stream -> ck_king_stream_rows; the N > 1 form differs only by the all-gather between the two
+    import torch
+    import torch.distributed as dist
+    from cuking_b200.distributed import king_host_bitset_allgather
+
+    rng = np.random.default_rng(11)
+    n, s = 3100, 350
+    g = random_genotypes(rng, n, s)
+    osm = ko.submatrix(n, 1, 0)
+    bs = oracle_bitset(g, osm)
+    want, count, _ = ko.king(bs, s, osm, 0.1, 1 << 20)
+    host = torch.from_numpy(bs.view(np.int64)).pin_memory()
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+    try:
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            with ck.Context(0, stream=stream.cuda_stream) as c2, c2.planes(ck.submatrix(n), s) as pl:
+                got = king_host_bitset_allgather(pl, host, ck.words_per_sample(s), 0.1, 1 << 20)
+                assert_results_equal(got, want)
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
 # ---- synthetic cohort ------------------------------------------------------------------------------------------
 
 
