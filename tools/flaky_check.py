@@ -1,9 +1,11 @@
+"""Repeats small pack + pairwise runs 150 times per shape and compares every one with the oracle: a race in the kernels' barrier
+protocol would show up as an occasional mismatch.  usage: tools/flaky_check.py [kernel variant]"""
 import sys; sys.path.insert(0, "/root/repo")
 import numpy as np, ctypes as C
 import cuking_b200 as ck
 from oracle import king_oracle as ko
 from tests.helpers import random_genotypes, triples_of, oracle_bitset, ko_sm
-ctx = ck.Context(0, king_variant=2)
+ctx = ck.Context(0, king_variant=int(sys.argv[1]) if len(sys.argv) > 1 else 3)  # 3 = mxf4 kernel (default), 2 = int8
 bad_king = bad_counts = 0
 for n, s in [(3, 31), (17, 33), (129, 511), (300, 1000)]:
     rng = np.random.default_rng(n * 31 + s * 7)
