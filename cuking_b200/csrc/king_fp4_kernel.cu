@@ -16,8 +16,9 @@
 // Operands are expanded on the fly from 4-bit genotype codes (layout.cuh) chosen so that the expansion is ONE logic
 // instruction per operand per 8 genotypes: code = 1 het, 2 hom-alt, 0xA hom-ref, 0 missing, i.e. E2M1(0.5), E2M1(+1),
 // E2M1(-1), 0, and   x = z & 0xAAAAAAAA   y = z & 0x22222222   h = z & 0x11111111.
-//   * warps 0-7   A operands: one thread per row sample; the two groups of four warps take alternate 64-site steps and
-//                 write straight into a 4-slot TMEM ring with tcgen05.st (thread = TMEM lane = row);
+//   * warps 0-7   A operands: one thread per row sample; the two groups of four warps take alternate A stages (two 64-site
+//                 steps each) and write straight into a 4-slot TMEM ring with tcgen05.st (thread = TMEM lane = row);
+//                 a slot is announced as soon as it is stored, a stage is released by one commit per issuer;
 //   * warps 8-12  B operands: two threads per column sample (32 sites each per step) write K-major no-swizzle canonical
 //                 shared-memory tiles, several steps per stage so the proxy fence and barrier round trip are amortised;
 //   * one lane of each of warps 13-15 issues one of the three MMAs per step (A from TMEM, B from shared memory) and
