@@ -272,8 +272,11 @@ def main():
 
         torch.cuda.set_device(local_rank)
         # NCCL kernels of the plane replication run beside the pairwise kernel, which fills every SM: give them priority
-        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
+        except (AttributeError, TypeError):  # older torch: default-priority NCCL streams still work, only slower to get SMs
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         assert world == n_gpus, f"--gpus {n_gpus} but WORLD_SIZE={world}"
     elif n_gpus != 1:
         raise SystemExit("for --gpus N > 1 launch with torchrun (one rank per GPU)")
