@@ -50,7 +50,7 @@ WORKLOADS = {
     "cfg4": (1_000_000, 100_000, 0.05, 0.0442), # BASELINE.json configs[3]: fixed cohort at every N (strong scaling): its
                                                 # ms_per_step is the metric's "wall-time for 1M x 100k"
 }
-FIXED_SIZE = {"cfg4"}
+FIXED_SIZE = {"cfg4", "cfg5"}  # BASELINE.json quotes these on a fixed cohort spread over the 8 GPUs
 
 
 def parse_args():
