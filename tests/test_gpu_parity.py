@@ -358,8 +358,11 @@ def test_allgather_fed_seam_single_rank(ctx):
     host = torch.from_numpy(bs.view(np.int64)).pin_memory()
     created = not dist.is_initialized()
     if created:
-        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
-                                device_id=torch.device("cuda", 0))
+        try:
+            dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
+                                    device_id=torch.device("cuda", 0))
+        except Exception as exc:  # no loopback / port in use: the seam itself is covered by the streaming test above
+            pytest.skip(f"cannot create a one-rank NCCL group here: {exc!r}")
     try:
         stream = torch.cuda.Stream()
         with torch.cuda.stream(stream):
