@@ -39,6 +39,16 @@ class Counts(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("het_i", "het_j", "both_het", "opposing_hom", "concordant_hom", "shared_sites")]
 
 
+class WorkItem(C.Structure):
+    """ck_work_item: one (shard, part) assigned to a GPU by ck_plan_work."""
+
+    _fields_ = [("shard_index", C.c_uint32), ("part_index", C.c_uint32), ("num_parts", C.c_uint32), ("gpu", C.c_uint32),
+                ("pairs", C.c_uint64)]
+
+    def __repr__(self):
+        return f"WorkItem(shard={self.shard_index}, part={self.part_index}/{self.num_parts}, gpu={self.gpu}, pairs={self.pairs})"
+
+
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("missing_rate", C.c_double)]
 
@@ -67,8 +77,11 @@ EXPORTED_SYMBOLS = [
     "ck_pack_triples", "ck_host_alloc", "ck_host_free", "ck_planes_import_bitset", "ck_planes_export_bitset", "ck_planes_synthesize", "ck_king",
     "ck_king_num_tiles", "ck_planes_king_variant", "ck_king_tiles", "ck_king_counts", "ck_king_host_bitset", "ck_king_host_bitset_part", "ck_king_stream_granularity", "ck_king_stream_begin",
     "ck_king_stream_rows", "ck_king_stream_end", "ck_synth_genotypes_host",
-    "ck_synth_triples_device",
+    "ck_synth_triples_device", "ck_ctx_fp4_selftest", "ck_planes_and_reduce", "ck_king_view", "ck_king_view_sink", "ck_plan_work",
 ]
+
+# typedef int (*ck_result_sink)(void *user, const ck_result *records, size_t count)
+RESULT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
 
 _lib = None
 
@@ -110,6 +123,11 @@ def load() -> C.CDLL:
         "ck_king_host_bitset_part": ([vp, u32, u32, u32, u32, vp, f32, u32, vp, C.POINTER(u32), u32, u32], i32),
         "ck_king_stream_granularity": ([], u32), "ck_king_stream_begin": ([vp, f32, u32, u32, u32], i32),
         "ck_king_stream_rows": ([vp, vp, i32, u32, u32], i32), "ck_king_stream_end": ([vp, vp, C.POINTER(u32)], i32),
+        "ck_plan_work": ([u32, u32, u32, u32, u32, C.POINTER(WorkItem), u32, C.POINTER(u32)], i32),
+        "ck_ctx_fp4_selftest": ([vp, C.POINTER(i32)], i32),
+        "ck_planes_and_reduce": ([C.POINTER(vp), u32], i32),
+        "ck_king_view": ([vp, SMp, u32, u32, f32, u32, vp, i32, C.POINTER(u32), i32], i32),
+        "ck_king_view_sink": ([vp, SMp, u32, u32, f32, u32, C.c_size_t, RESULT_SINK, vp, C.POINTER(u64)], i32),
         "ck_synth_genotypes_host": ([C.POINTER(SynthParams), u32, u32, u32, u32, vp], i32),
         "ck_synth_triples_device": ([vp, C.POINTER(SynthParams), u32, u32, u32, u32, C.POINTER(vp), C.POINTER(vp),
                                      C.POINTER(vp), C.POINTER(C.c_size_t)], i32),

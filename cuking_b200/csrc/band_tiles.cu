@@ -86,7 +86,7 @@ cudaError_t band_prepare(const KingLaunch &k, uint32_t tile_cols, ck_ctx *ctx, c
     if (ctx->tile_table) cudaFree(ctx->tile_table);
     ctx->tile_table = nullptr;
     ctx->tile_table_bytes = 0;
-    cudaError_t e = cudaMalloc(&ctx->tile_table, prefix_bytes + first_bytes);
+    cudaError_t e = dev_alloc(ctx, &ctx->tile_table, prefix_bytes + first_bytes);
     if (e != cudaSuccess) return e;
     ctx->tile_table_bytes = prefix_bytes + first_bytes;
   }

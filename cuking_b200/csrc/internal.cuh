@@ -2,8 +2,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/cuking_b200.h"
@@ -26,19 +28,37 @@ struct EventPair {
   cudaEvent_t a = nullptr, b = nullptr;
 };
 
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute belongs to the (kernel, device) pair, and one
+// process may drive several GPUs from several threads (bin/cuking --num_gpus / --all_shards): `done` holds one bit per
+// device.  Two threads racing on the same device both set the attribute, which is harmless.
+template <typename F>
+cudaError_t optin_dynamic_smem(F func, size_t bytes, std::atomic<uint64_t> &done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t bit = 1ull << (unsigned(dev) & 63u);
+  if (dev < 64 && (done.load(std::memory_order_acquire) & bit)) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  if (e == cudaSuccess && dev < 64) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+
 }  // namespace ck
 
 struct ck_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;       // own_stream or a caller-supplied one
-  cudaStream_t copy_stream = nullptr;  // host staging copies overlap the pack kernel
+  cudaStream_t copy_stream = nullptr;  // host -> device staging copies overlap the kernels
+  cudaStream_t d2h_stream = nullptr;   // device -> host result copies overlap the kernels (PCIe is full duplex)
   cudaEvent_t ev[2] = {nullptr, nullptr};
   ck_timings timings{};
   int num_sms = 0;
   // scratch owned by the ctx
-  unsigned long long *d_counter = nullptr;  // [0] emitted-pair counter
-  uint32_t *d_pack_err = nullptr;           // [0] invalid-genotype index+1 (min), [1] out-of-range index+1 (min)
+  static constexpr uint32_t kHoleSlots = 1024;  // dense output: one below-threshold counter per output region
+  unsigned long long *d_counter = nullptr;      // [0] emitted-pair counter, [1] spare, [2 ..] hole counters
+  unsigned long long *h_holes = nullptr;        // pinned host mirror of the hole counters
+  unsigned long long *d_pack_err = nullptr;     // [0] invalid-genotype index+1 (min), [1] out-of-range index+1 (min)
   void *pinned[2] = {nullptr, nullptr};   // host staging for ck_pack_triples(on_device = 0)
   void *staging[2] = {nullptr, nullptr};  // device side of the same double buffer
   size_t pinned_bytes = 0;
@@ -51,14 +71,25 @@ struct ck_ctx {
   ck_result *result_buf = nullptr;
   size_t result_cap = 0;
   int king_variant = -1;  // -1 = library default
+  // kind::mxf4 accumulation self-test (fp4_selftest.cu): 0 = not run yet, 1 = exact, -1 = inexact -> int8 kernel
+  int fp4_state = 0;
   // alive-tile table of the tcgen05 kernel (grow-only device scratch)
   void *tile_table = nullptr;
   size_t tile_table_bytes = 0;
   uint64_t tile_table_key[3] = {~0ull, 0, 0};  // (variant, rows/cols, global origins) of the table now on the device
+  // dense output: first output slot of every band (device copy + the host vector the async upload reads)
+  unsigned long long *dense_table = nullptr;
+  size_t dense_table_entries = 0;
+  std::vector<unsigned long long> dense_host;
   // grow-only scratch for the result sort (keys, indices, CUB temporaries, sorted records): no cudaMalloc/cudaFree
   // on the steady-state path
   void *sort_scratch = nullptr;
   size_t sort_scratch_bytes = 0;
+  // page-locked double buffer for chunked result delivery (ck_king_view_sink)
+  void *out_pinned[2] = {nullptr, nullptr};
+  size_t out_pinned_records = 0;
+  std::vector<cudaEvent_t> event_pool;  // timing-disabled events reused by the pipelined paths
+  size_t events_used = 0;
   // small cache of released device buffers (planes, staging) so that a create / destroy cycle per call - the
   // host-buffer entry point ck_king_host_bitset - does not pay cudaMalloc / cudaFree of gigabytes every time
   static constexpr int kCacheSlots = 8;
@@ -67,8 +98,46 @@ struct ck_ctx {
 };
 
 namespace ck {
-cudaError_t ctx_alloc(ck_ctx *ctx, void **ptr, size_t bytes);  // exact-size reuse from the cache, else cudaMalloc
+cudaError_t ctx_alloc(ck_ctx *ctx, void **ptr, size_t bytes);  // exact-size reuse from the cache, else dev_alloc
 void ctx_release(ck_ctx *ctx, void *ptr, size_t bytes);        // into the cache (evicting the smallest entry) or cudaFree
+// cudaMalloc for everything the ctx owns: on cudaErrorMemoryAllocation the buffer cache is dropped and the allocation
+// retried once, so idle cached gigabytes never turn into CK_ERR_OUT_OF_MEMORY
+cudaError_t dev_alloc(ck_ctx *ctx, void **ptr, size_t bytes);
+// a timing-disabled event from the ctx pool (valid until events_reset)
+cudaError_t pool_event(ck_ctx *ctx, cudaEvent_t *out);
+inline void events_reset(ck_ctx *ctx) { ctx->events_used = 0; }
+
+struct DeviceGuard {  // every entry point runs on the ctx's device and restores the caller's
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    (void)cudaGetLastError();  // a stale non-sticky error of an earlier (successful) call must not be blamed on ours
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+struct DevBuf {  // RAII device allocation for per-call temporaries
+  ck_ctx *ctx;
+  void *p = nullptr;
+  explicit DevBuf(ck_ctx *c) : ctx(c) {}
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return dev_alloc(ctx, &p, bytes ? bytes : 1); }
+  template <typename T>
+  T *as() const { return static_cast<T *>(p); }
+};
+
+inline float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
 }  // namespace ck
 
 
@@ -100,7 +169,7 @@ namespace ck {
 // ---- pack_kernels.cu ----
 cudaError_t launch_fill_missing(uint32_t *raw, size_t num_words, cudaStream_t s);
 cudaError_t launch_pack(const ck_planes &pl, const int64_t *row, const int64_t *col, const int32_t *alt, size_t n,
-                        size_t index_base, uint32_t *d_err, cudaStream_t s);
+                        size_t index_base, unsigned long long *d_err, cudaStream_t s);
 cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s);
 cudaError_t launch_finalize_codes(const ck_planes &pl, int kind, cudaStream_t s);
 // the same for the 64-sample blocks [block0, block0 + num_blocks) only (pipelined host-buffer path)
@@ -123,9 +192,11 @@ struct KingLaunch {
   const uint32_t *compute;  // compute planes (LOP3+POPC kernels)
   const uint32_t *codes;    // nibble-coded genotypes (tcgen05 kernel)
   uint32_t words;           // padded words per plane
-  uint32_t row_block0, num_row_blocks;
+  uint32_t row_slot0, col_slot0;      // plane slot of the first row / column sample (tensor-core kernels: any slot, so
+                                      // that a shard can be a VIEW into the planes of a larger sample set)
+  uint32_t row_block0, num_row_blocks;  // the same in 64-sample blocks (LOP3+POPC kernels: whole blocks only)
   uint32_t col_block0, num_col_blocks;
-  uint32_t row_global0, col_global0;  // global sample index of slot row_block0*64 / col_block0*64
+  uint32_t row_global0, col_global0;  // global sample index of the first row / column
   uint32_t num_rows, num_cols;
   uint32_t triangular;                // rows and columns are the same sample range
   uint64_t tile_begin, tile_end;
@@ -135,6 +206,24 @@ struct KingLaunch {
   unsigned long long *counter;        // device, emitted pairs
   ck_counts *dump_counts;             // optional dense [num_rows][num_cols] dump (parity hook), else nullptr
   float *dump_kin;
+  // Dense output (tensor-core kernels): when not NULL, the record of pair (i, j) goes to the slot it has in the sorted
+  // output - dense_band_base[band of i] + its closed-form offset inside the band - so neither the append counter nor a
+  // sort is needed; a pair at or below the threshold leaves a hole (sample_i = 0xffffffff) and bumps *holes.
+  const unsigned long long *dense_band_base;
+  unsigned long long *holes;
+};
+// Where the records of one evaluation go (king_api.cu).  Sparse: appended through the atomic counter, sorted afterwards.
+// Dense: every pair has its slot in the sorted output; `regions` lists the output ranges in launch order with the event
+// that marks them complete, so that their device -> host copies overlap the kernels still running.
+struct OutRegion {
+  unsigned long long offset, count;  // records
+  cudaEvent_t ready;
+  uint32_t holes_slot;               // index into ck_ctx::d_counter + 2
+};
+struct ResultPlan {
+  bool dense = false;
+  unsigned long long part_pairs = 0;  // i < j pairs of this part (= the dense buffer's size)
+  std::vector<OutRegion> regions;
 };
 struct KingStream {  // state of one ck_king_stream_begin .. end session (also used by the pipelined host-buffer path)
   KingLaunch k{};
@@ -143,7 +232,16 @@ struct KingStream {  // state of one ck_king_stream_begin .. end session (also u
   uint32_t part_index = 0, num_parts = 1;
   uint32_t max_results = 0;
   uint32_t next_end = 0;              // rows [next_end, n) have been delivered
+  ResultPlan plan;
+  std::vector<std::pair<void *, size_t>> staged;  // device copies of host-delivered rows (ctx cache buffers)
 };
+void stream_discard(ck_planes *pl);  // king_api.cu: abandons an open stream session
+// capi.cu
+int planes_variant(const ck_planes *pl);   // the variant that runs on these planes (runs the mxf4 self-test on first use)
+int ensure_compute(ck_planes *pl);   // derives what that variant reads from the raw planes
+// fp4_selftest.cu: adversarial accumulation patterns through tcgen05.mma kind::mxf4 on this GPU; *exact = 1 when every
+// checked accumulator equals the integer arithmetic
+int fp4_selftest(ck_ctx *ctx, int *exact, std::string *detail);
 uint64_t king_num_tiles(uint32_t num_row_blocks, uint32_t num_col_blocks, bool triangular);
 cudaError_t launch_king(const KingLaunch &k, int variant, cudaStream_t s, uint32_t *launches);
 

@@ -94,13 +94,51 @@ __device__ __forceinline__ float kinship(uint32_t het_i, uint32_t het_j, uint32_
   return __fadd_rn(0.5f, __fdiv_rn(num, den));
 }
 
-// Threshold + warp-aggregated append of one pair per lane (cuking.cu:297-312).  Must be called by all 32 lanes of a
-// warp.  One atomicAdd per warp and call instead of one per retained pair; the 64-bit counter cannot wrap, and the
-// host turns counter > max_results into the reference's overflow error (:747-751).
-__device__ __forceinline__ void emit_pair(const KingLaunch &p, bool valid, uint32_t gi, uint32_t gj, float kin,
+// Rows per band of the tensor-core kernels' tile enumeration (band_tiles.cu: kBandRowTiles x kBandTileRows).
+constexpr uint32_t kDenseBandRows = 1024;
+static_assert(kDenseBandRows == kBandRowTiles * kBandTileRows, "band height");
+
+// Offset of pair (li, lj) - row / column index inside the sub-matrix - among the pairs of its band, in the sorted
+// (row-major) order: a triangular row li holds the columns (li, num_cols), a rectangular one all of them.
+__host__ __device__ inline unsigned long long dense_offset_in_band(uint32_t li, uint32_t lj, uint32_t num_cols, bool triangular) {
+  const unsigned long long b0 = (li / kDenseBandRows) * kDenseBandRows, r = li - b0;
+  if (!triangular) return r * num_cols + lj;
+  return r * (num_cols - 1ull) - (b0 * r + r * (r - 1ull) / 2ull) + (lj - li - 1ull);
+}
+// pairs of the band that starts at row b0
+__host__ __device__ inline unsigned long long dense_band_pairs(uint32_t b0, uint32_t num_rows, uint32_t num_cols, bool triangular) {
+  const unsigned long long rows = (num_rows - b0 < kDenseBandRows) ? num_rows - b0 : kDenseBandRows;
+  if (!triangular) return rows * num_cols;
+  return rows * (num_cols - 1ull) - (b0 * rows + rows * (rows - 1ull) / 2ull);
+}
+
+// Threshold + result store of one pair per lane (cuking.cu:297-312).  Must be called by all 32 lanes of a warp.
+//   pair : this lane holds an i < j pair of the sub-matrix;  maybe : it may pass the threshold (a cheap screen said so)
+// Sparse mode: one atomicAdd per warp and call instead of one per retained pair (warp-aggregated append); the 64-bit
+// counter cannot wrap, and the host turns counter > max_results into the reference's overflow error (:747-751).
+// Dense mode (p.dense_band_base): the record goes straight to its slot in the sorted output.
+__device__ __forceinline__ void emit_pair(const KingLaunch &p, bool pair, bool maybe, uint32_t gi, uint32_t gj, float kin,
                                           uint32_t opp, uint32_t conc, uint32_t both_het, uint32_t shared) {
   const uint32_t lane = threadIdx.x & 31;
-  const bool emit = valid && (kin > p.kin_threshold);  // strict; NaN / -inf never pass (cuking.cu:297)
+  const bool emit = pair && maybe && (kin > p.kin_threshold);  // strict; NaN / -inf never pass (cuking.cu:297)
+  if (p.dense_band_base != nullptr) {
+    const uint32_t holes = __ballot_sync(0xffffffffu, pair && !emit);
+    if (holes != 0 && int(lane) == __ffs(holes) - 1) atomicAdd(p.holes, (unsigned long long)__popc(holes));
+    if (pair) {
+      const uint32_t li = gi - p.row_global0, lj = gj - p.col_global0;
+      const unsigned long long slot = p.dense_band_base[li / kDenseBandRows] + dense_offset_in_band(li, lj, p.num_cols, p.triangular != 0);
+      uint2 *dst = reinterpret_cast<uint2 *>(p.results + slot);  // our own 256-byte aligned buffer: 24-byte records are 8-aligned
+      if (emit) {
+        const uint32_t ibs2 = conc + both_het;
+        dst[0] = make_uint2(gi, gj);
+        dst[1] = make_uint2(__float_as_uint(kin), opp);
+        dst[2] = make_uint2(shared - opp - ibs2, ibs2);
+      } else {
+        dst[0] = make_uint2(0xffffffffu, 0xffffffffu);
+      }
+    }
+    return;
+  }
   const uint32_t ballot = __ballot_sync(0xffffffffu, emit);
   if (ballot == 0) return;
   const int leader = __ffs(ballot) - 1;

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     const uint32_t group = warp >> 2, srow = (warp & 3) * 32 + lane;
     // rows beyond the tile's edge re-read its first row (always allocated): their pairs are masked in the epilogue, and
     // the loads stay unconditional
-    const uint32_t slot = p.row_block0 * kTileSamples + row0 + (srow < rows_here ? srow : 0u);
+    const uint32_t slot = p.row_slot0 + row0 + (srow < rows_here ? srow : 0u);
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
     const uint4 *src = reinterpret_cast<const uint4 *>(p.codes) + size_t(blk) * p.words * kTileSamples + ln;
     const uint32_t lane_base = tmem_base + ((uint32_t(warp & 3) * 32u) << 16);
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     // ===== B expanders: two threads per column sample (32 sites of every step each), BS steps per stage =====
     const uint32_t idx = tid - kFAWarps * 32;
     const uint32_t half = idx / kFN, srow = idx % kFN;  // half: K bytes 16*half .. 16*half+15 of every step
-    const uint32_t slot = p.col_block0 * kTileSamples + col0 + (srow < cols_here ? srow : 0u);  // see the A expanders
+    const uint32_t slot = p.col_slot0 + col0 + (srow < cols_here ? srow : 0u);  // see the A expanders
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
     const uint4 *src = reinterpret_cast<const uint4 *>(p.codes) + (size_t(blk) * p.words + half) * kTileSamples + ln;
     const uint32_t b_off = (srow >> 3) * G::kSBO + (srow & 7) * 16 + half * kFLBO;
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     // num <= (thr - 0.5 - margin) den cannot pass the strict threshold test and skips the conversions and the IEEE
     // division.  den == 0 implies num <= 0 (both_het <= min_hets), i.e. -inf / NaN, which the reference never emits.
     const float screen4 = 4.f * (p.kin_threshold - 0.5f - (1e-3f + 1e-5f * fabsf(p.kin_threshold)));
-    const bool dump = p.dump_counts != nullptr;
+    const bool dump = p.dump_counts != nullptr, dense = p.dense_band_base != nullptr;
     auto finish = [&](uint32_t c, uint32_t xx, uint32_t yy, uint32_t yh, uint32_t hy, uint32_t hh) {
       const uint32_t gj = j0 + c;
       const float fxx = __uint_as_float(xx), fyy = __uint_as_float(yy), fyh = __uint_as_float(yh), fhy = __uint_as_float(hy),
@@ -361,8 +361,9 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
       const float half_num = (fxx - fyy) - (fhy + fyh);
       const float eighth_den = fmaf(2.f, fhh, fminf(fhy, fyh));
       const bool in_tile = r < rows_here && c < cols_here;
-      const bool cand = in_tile && gi < gj && half_num > screen4 * eighth_den;
-      if (__ballot_sync(0xffffffffu, cand || dump) == 0) return;
+      const bool pair = in_tile && gi < gj;
+      const bool cand = pair && half_num > screen4 * eighth_den;
+      if (__ballot_sync(0xffffffffu, cand || dump || (dense && pair)) == 0) return;  // dense output: every pair owns a slot
       // the accumulators hold exact multiples of 1/4 (see the header): scale back to integer counts
       const int32_t n_xx = __float2int_rn(fxx);                    // conc - opp (signed)
       const uint32_t n_yy = uint32_t(__float2int_rn(fyy));         // conc + opp
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
         p.dump_counts[idx] = out;
         p.dump_kin[idx] = kin;
       }
-      emit_pair(p, cand, gi, gj, kin, opp, conc, both_het, shared);
+      emit_pair(p, pair, cand, gi, gj, kin, opp, conc, both_het, shared);
     };
     constexpr uint32_t kColsPerGroup = kFN / 4;  // 20
     static_assert(kColsPerGroup == 20 || kColsPerGroup == 16, "epilogue column split");
@@ -435,12 +436,8 @@ Fp4Config fp4_config() {  // stage geometry; CUKING_FP4_STAGE = "<steps per A st
 
 template <uint32_t AS, uint32_t BS, uint32_t NS>
 cudaError_t launch_cfg(const KingLaunch &part, const BandTiles &tiles, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(king_fp4_kernel<AS, BS, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Fp4Geo<AS, BS, NS>::kSmem));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};  // one bit per device
+  if (cudaError_t e = optin_dynamic_smem(king_fp4_kernel<AS, BS, NS>, Fp4Geo<AS, BS, NS>::kSmem, configured); e != cudaSuccess) return e;
   king_fp4_kernel<AS, BS, NS><<<unsigned(part.tile_end - part.tile_begin), kFThreads, Fp4Geo<AS, BS, NS>::kSmem, s>>>(part, tiles);
   return cudaGetLastError();
 }

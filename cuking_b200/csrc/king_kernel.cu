@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) king_tile_kernel(const KingLaunch
         p.dump_counts[idx] = out;
         p.dump_kin[idx] = kin;
       }
-      emit_pair(p, valid, gi, gj, kin, opp, conc, both_het, shared);
+      emit_pair(p, valid, true, gi, gj, kin, opp, conc, both_het, shared);
     }
   }
 }
@@ -243,15 +243,9 @@ uint64_t king_num_tiles(uint32_t num_row_blocks, uint32_t num_col_blocks, bool t
 }
 
 cudaError_t launch_king(const KingLaunch &k, int variant, cudaStream_t s, uint32_t *launches) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(king_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         int(kSmemBytes));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(king_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured[2] = {{0}, {0}};  // one bit per device
+  if (cudaError_t e = optin_dynamic_smem(king_tile_kernel<false>, kSmemBytes, configured[0]); e != cudaSuccess) return e;
+  if (cudaError_t e = optin_dynamic_smem(king_tile_kernel<true>, kSmemBytes, configured[1]); e != cudaSuccess) return e;
   // CUDA grids are limited to 2^31-1 blocks in x; slice very large tile ranges into several launches.
   constexpr uint64_t kMaxGrid = 1ull << 30;
   for (uint64_t t = k.tile_begin; t < k.tile_end; t += kMaxGrid) {

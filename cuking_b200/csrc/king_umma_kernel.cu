@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
     // ===== A expanders: one thread per row; group g (4 warps) owns A stage g = TMEM slots 2g, 2g+1 and fills it with
     // the steps {4n + 2g, 4n + 2g + 1}, n = 0, 1, ...  =====
     const uint32_t group = warp >> 2, srow = (warp & 3) * 32 + lane;
-    const uint32_t slot = p.row_block0 * kTileSamples + row0 + srow;
+    const uint32_t slot = p.row_slot0 + row0 + srow;
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
     const bool in_range = srow < rows_here;
     const uint4 *src = reinterpret_cast<const uint4 *>(p.codes) + size_t(blk) * p.words * kTileSamples + ln;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
     // ================= B expanders: two threads per column sample, kBStageSteps steps per stage =================
     const uint32_t idx = tid - kAWarps * 32;
     const uint32_t half = idx / kUN, srow = idx % kUN;  // half: K bytes 16*half .. 16*half+15 of every step
-    const uint32_t slot = p.col_block0 * kTileSamples + col0 + srow;
+    const uint32_t slot = p.col_slot0 + col0 + srow;
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
     const bool in_range = srow < cols_here;
     const uint2 *src = reinterpret_cast<const uint2 *>(p.codes) + (size_t(blk) * p.words * kTileSamples + ln) * 2 + half;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
           p.dump_counts[idx] = out;
           p.dump_kin[idx] = kin;
         }
-        emit_pair(p, in_tile && gi < gj, gi, gj, kin, opp, conc, both_het, shared);
+        emit_pair(p, in_tile && gi < gj, true, gi, gj, kin, opp, conc, both_het, shared);
       }
     }
   }
@@ -378,12 +378,8 @@ uint64_t king_umma_num_tiles(const KingLaunch &k) { return band_num_tiles(k, kUN
 
 cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches) {
   (void)total_blocks;  // every row / column a tile reads lies inside the shard's allocated blocks
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(king_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUmmaSmem));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};  // one bit per device
+  if (cudaError_t e = optin_dynamic_smem(king_umma_kernel, kUmmaSmem, configured); e != cudaSuccess) return e;
   if (k.tile_end <= k.tile_begin) return cudaSuccess;
   BandTiles tiles{};
   cudaError_t e = band_prepare(k, kUN, ctx, s, nullptr, &tiles);

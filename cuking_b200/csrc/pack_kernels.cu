@@ -25,11 +25,11 @@ __global__ void fill_missing_kernel(uint4 *raw4, size_t n4) {
 // One triple per lane per load.  For Hail-ordered input (site-major, sample-minor) the 32 lanes of a warp hit 32
 // consecutive words of one (block, word, plane) row, i.e. each RED.AND warp instruction touches one 128-byte line.
 __device__ __forceinline__ void pack_one(uint32_t *raw, const SlotMap &map, uint32_t words, uint32_t num_sites,
-                                         int64_t row64, int64_t col64, int32_t n_alt, size_t index, uint32_t *err) {
+                                         int64_t row64, int64_t col64, int32_t n_alt, size_t index, unsigned long long *err) {
   const uint32_t col = uint32_t(int32_t(col64));                     // cuking.cu:676
   if (!sm_contains(map.sm, col)) return;                             // cuking.cu:677-679
   const uint32_t site = uint32_t(int32_t(row64));                    // cuking.cu:680
-  const uint32_t tag = index + 1 > 0xfffffffeull ? 0xffffffffu : uint32_t(index + 1);
+  const unsigned long long tag = (unsigned long long)index + 1ull;  // 64-bit: the 'no error' sentinel ~0 is never a real tag
   if (uint32_t(n_alt) > 2u) {                                        // cuking.cu:698-701
     atomicMin(&err[0], tag);
     return;
@@ -48,7 +48,7 @@ __device__ __forceinline__ void pack_one(uint32_t *raw, const SlotMap &map, uint
 __global__ void __launch_bounds__(256) pack_kernel(uint32_t *raw, SlotMap map, uint32_t words, uint32_t num_sites,
                                                    const int64_t *__restrict__ row, const int64_t *__restrict__ col,
                                                    const int32_t *__restrict__ alt, size_t n, size_t index_base,
-                                                   uint32_t *err) {
+                                                   unsigned long long *err) {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   // One triple per lane per load group, kUnroll independent groups (20 B each) in flight per thread before the first
@@ -272,7 +272,7 @@ cudaError_t launch_fill_missing(uint32_t *raw, size_t num_words, cudaStream_t s)
 }
 
 cudaError_t launch_pack(const ck_planes &pl, const int64_t *row, const int64_t *col, const int32_t *alt, size_t n,
-                        size_t index_base, uint32_t *d_err, cudaStream_t s) {
+                        size_t index_base, unsigned long long *d_err, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   pack_kernel<<<grid_for(n / 8 + 1, 256, 148 * 8), 256, 0, s>>>(pl.raw, pl.map, pl.words, pl.num_sites, row, col, alt, n,
                                                               index_base, d_err);

@@ -1,5 +1,6 @@
-"""Multi-GPU execution of one shard: one process per GPU (torch.distributed), every rank holds the shard's planes and
-evaluates a contiguous slice of its 64x64 tile grid; the sparse results are gathered on rank 0.
+"""Multi-GPU execution: one process per GPU (torch.distributed).  Every rank holds the planes and evaluates its PART of a
+shard - the bands of 1024 rows are dealt to the parts in snake order (ck_king_view) - or its share of the shards of a
+--split_factor run (ck_plan_work); the sparse results are gathered on rank 0.
 
 Pairs are independent (/root/reference/cuking.cu:197-201) and no count is ever combined across devices, so the
 pairwise stage itself needs no collective; torch.distributed carries the result gather (a few MB), barriers and -
@@ -8,46 +9,49 @@ but with one OS process per shard on separate VMs (README.md:94-102, cloud_batch
 """
 from __future__ import annotations
 
-import math
-
 import numpy as np
 
 from .capi import RESULT_DTYPE, CukingError, CK_ERR_RESULT_OVERFLOW
 
-TILE = 64  # samples per tile edge (cuking_b200/csrc/layout.cuh: kTileSamples)
+BAND_ROWS = 1024  # rows per band of the tensor-core kernels' tile enumeration (csrc/band_tiles.cu) = the partition unit
 
 
-def tile_slice(num_tiles: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous, balanced slice [begin, end) of the linear tile index space for `rank` of `world`."""
-    return num_tiles * rank // world, num_tiles * (rank + 1) // world
+def band_owner(band: int, num_parts: int) -> int:
+    """Part that evaluates band `band` of a shard split into `num_parts` parts: snake order 0..P-1, P-1..0, ... (the
+    work of a band falls linearly with its index, so every pair (g, 2P-1-g) carries the same work).  Mirror of
+    band_owner() in csrc/king_api.cu."""
+    g = band % (2 * num_parts)
+    return g if g < num_parts else 2 * num_parts - 1 - g
 
 
-def num_tiles(num_rows: int, num_cols: int, triangular: bool) -> int:
-    rb, cb = -(-num_rows // TILE), -(-num_cols // TILE)
-    return rb * (rb + 1) // 2 if triangular else rb * cb
+def part_of_pair(i_local: int, num_parts: int) -> int:
+    """Part that evaluates the pairs of row `i_local` (row index inside the shard)."""
+    return band_owner(i_local // BAND_ROWS, num_parts)
 
 
-def tile_coords(t: int, num_row_blocks: int, num_col_blocks: int, triangular: bool) -> tuple[int, int]:
-    """Linear tile index -> (row block, column block); mirror of tile_coords() in csrc/king_kernel.cu.  Triangular
-    grids (rows == columns) enumerate bj >= bi row-major."""
-    if not triangular:
-        return t // num_col_blocks, t % num_col_blocks
-    n = num_row_blocks
-    b = int((2 * n + 1 - math.isqrt((2 * n + 1) ** 2 - 8 * t)) // 2)
-    off = lambda x: x * n - x * (x - 1) // 2
-    while b > 0 and off(b) > t:
-        b -= 1
-    while b + 1 < n and off(b + 1) <= t:
-        b += 1
-    return b, b + (t - off(b))
+_MIX = (np.uint64(0x9E3779B97F4A7C15), np.uint64(0xC2B2AE3D27D4EB4F), np.uint64(0x165667B19E3779F9))
 
 
-def tile_of_pair(i_local: int, j_local: int, num_row_blocks: int, num_col_blocks: int, triangular: bool) -> int:
-    """Linear tile index that evaluates the pair at (row offset, column offset) of the sub-matrix."""
-    bi, bj = i_local // TILE, j_local // TILE
-    if not triangular:
-        return bi * num_col_blocks + bj
-    return bi * num_row_blocks - bi * (bi - 1) // 2 + (bj - bi)
+def record_checksum(records: np.ndarray, chunk: int = 1 << 22) -> tuple[int, int, int]:
+    """Order-independent checksum of KingResult records over all six fields: (count, sum, xor) of a 64-bit mix of each
+    24-byte record.  Sums over disjoint sets of records add (mod 2^64) and xors xor, so the checksum of a result
+    scattered over ranks is all_reduce(sum) / all_reduce(xor) of the per-rank values."""
+    total, acc_sum, acc_xor = len(records), np.uint64(0), np.uint64(0)
+    with np.errstate(over="ignore"):
+        for lo in range(0, total, chunk):
+            w = np.ascontiguousarray(records[lo: lo + chunk]).view(np.uint64).reshape(-1, 3)
+            h = (w[:, 0] * _MIX[0]) ^ ((w[:, 1] + _MIX[2]) * _MIX[1]) ^ ((w[:, 2] ^ _MIX[0]) * _MIX[2])
+            h ^= h >> np.uint64(29)
+            acc_sum = acc_sum + h.sum(dtype=np.uint64)
+            acc_xor = acc_xor ^ np.bitwise_xor.reduce(h) if len(h) else acc_xor
+    return total, int(acc_sum), int(acc_xor)
+
+
+def combine_checksums(parts: list[tuple[int, int, int]]) -> tuple[int, int, int]:
+    n, s, x = 0, 0, 0
+    for pn, ps, px in parts:
+        n, s, x = n + pn, (s + ps) & 0xFFFFFFFFFFFFFFFF, x ^ px
+    return n, s, x
 
 
 def merge_sorted(parts: list[np.ndarray]) -> np.ndarray:
@@ -85,15 +89,14 @@ def gather_results(local: np.ndarray, dst: int = 0, group=None):
             for r, b in enumerate(bucket)]
 
 
-def king_distributed(evaluate_slice, total_tiles: int, max_results: int, group=None):
-    """Runs `evaluate_slice(tile_begin, tile_end) -> sorted results` on this rank's slice, gathers and merges on rank 0.
-    Applies the reference's overflow rule to the TOTAL count (cuking.cu:747-751).  Returns the merged array on rank 0,
-    None elsewhere."""
+def king_distributed(evaluate_part, max_results: int, group=None):
+    """Runs `evaluate_part(part_index, num_parts) -> sorted results` (Planes.king_view(part=...)) for this rank's part,
+    gathers and merges on rank 0.  Applies the reference's overflow rule to the TOTAL count (cuking.cu:747-751).
+    Returns the merged array on rank 0, None elsewhere."""
     import torch.distributed as dist
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    begin, end = tile_slice(total_tiles, rank, world)
-    local = evaluate_slice(begin, end)
+    local = evaluate_part(rank, world)
     parts = gather_results(local, 0, group)
     if rank != 0:
         return None
@@ -151,20 +154,29 @@ def king_host_bitset_allgather(planes, host_bits, words_per_sample: int, kin_thr
     piece_rows = -(-max_rows // world)
     stage = [torch.empty(piece_rows * world * words_per_sample, dtype=torch.int64, device=dev) for _ in range(len(chunks))]
     side.wait_stream(main)
-    planes.stream_begin(kin_threshold, max_results, part=(rank, world))
-    for c, (b, e) in enumerate(chunks):
-        pr, my_b, my_e = chunk_piece(b, e, rank, world)
-        buf = stage[c][: pr * world * words_per_sample]
-        with torch.cuda.stream(side):
-            mine = buf[rank * pr * words_per_sample: (rank + 1) * pr * words_per_sample]
-            if my_e > my_b:
-                mine[: (my_e - my_b) * words_per_sample].copy_(hb[my_b * words_per_sample: my_e * words_per_sample], non_blocking=True)
-            if world > 1:
-                dist.all_gather_into_tensor(buf, mine, group=group)
-            ready = torch.cuda.Event()
-            ready.record(side)
-        main.wait_event(ready)
-        planes.stream_rows(buf.data_ptr(), b, e)
-    res = planes.stream_end(max_results, out=out)
+    # The uploads and all-gathers are ordered against `main` (torch's current stream) with events; the library queues
+    # its transpose / code / pairwise kernels on the ctx's stream.  Those must be the same stream, or the kernels could
+    # read a chunk before it has landed: bind the ctx to `main` for the duration of the call.
+    ctx = planes.ctx
+    prev_stream = ctx.stream
+    ctx.set_stream(main.cuda_stream)
+    try:
+        planes.stream_begin(kin_threshold, max_results, part=(rank, world))
+        for c, (b, e) in enumerate(chunks):
+            pr, my_b, my_e = chunk_piece(b, e, rank, world)
+            buf = stage[c][: pr * world * words_per_sample]
+            with torch.cuda.stream(side):
+                mine = buf[rank * pr * words_per_sample: (rank + 1) * pr * words_per_sample]
+                if my_e > my_b:
+                    mine[: (my_e - my_b) * words_per_sample].copy_(hb[my_b * words_per_sample: my_e * words_per_sample], non_blocking=True)
+                if world > 1:
+                    dist.all_gather_into_tensor(buf, mine, group=group)
+                ready = torch.cuda.Event()
+                ready.record(side)
+            main.wait_event(ready)
+            planes.stream_rows(buf.data_ptr(), b, e)
+        res = planes.stream_end(max_results, out=out)
+    finally:
+        ctx.set_stream(prev_stream)
     del stage
     return res

@@ -25,6 +25,19 @@ def num_shards(split_factor: int) -> int:
     return int(capi.load().ck_num_shards(split_factor))
 
 
+def plan_work(num_samples: int, split_factor: int, num_gpus: int, first_shard: int = 0, num_run: int | None = None):
+    """Work items (shard, part, num_parts, gpu) of a multi-shard run on the GPUs of one box, LPT-scheduled
+    (ck_plan_work; the local counterpart of cloud_batch_submit.py:45,73)."""
+    L = capi.load()
+    if num_run is None:
+        num_run = int(L.ck_num_shards(split_factor)) - first_shard
+    n = C.c_uint32(0)
+    check(L.ck_plan_work(num_samples, split_factor, first_shard, num_run, num_gpus, None, 0, C.byref(n)))
+    items = (capi.WorkItem * max(1, n.value))()
+    check(L.ck_plan_work(num_samples, split_factor, first_shard, num_run, num_gpus, items, n.value, C.byref(n)))
+    return list(items[: n.value])
+
+
 def words_per_sample(num_sites: int) -> int:
     """uint64 words per sample of the reference bit set, cuking.cu:498-500,:513."""
     return int(capi.load().ck_words_per_sample(num_sites))
@@ -66,6 +79,7 @@ class Context:
         self._h = C.c_void_p()
         check(self._lib.ck_ctx_create(device, C.byref(self._h)))
         self.device = device
+        self.stream = None  # cudaStream_t the ctx is bound to (None = its own)
         if stream is not None:
             self.set_stream(stream)
         if king_variant is not None:
@@ -73,6 +87,14 @@ class Context:
 
     def set_stream(self, cuda_stream: int | None) -> None:
         check(self._lib.ck_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        self.stream = cuda_stream or None
+
+    def fp4_selftest(self) -> tuple[bool, str]:
+        """Runs the kind::mxf4 accumulation self-test on this GPU now: (exact, one-line report).  A failure routes
+        variant 3 to the int8 kernel on this ctx (ck_ctx_fp4_selftest)."""
+        exact = C.c_int(0)
+        check(self._lib.ck_ctx_fp4_selftest(self._h, C.byref(exact)))
+        return bool(exact.value), (self._lib.ck_last_error() or b"").decode()
 
     def set_king_variant(self, variant: int) -> None:
         check(self._lib.ck_ctx_set_king_variant(self._h, variant))
@@ -134,6 +156,13 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def and_reduce(planes: list["Planes"]) -> None:
+    """AND-all-reduce of the raw planes of one plane set per GPU over NVLink peer memory (ck_planes_and_reduce): after
+    it every GPU holds the planes of all the triples that were dealt among them."""
+    arr = (C.c_void_p * len(planes))(*[p._h for p in planes])
+    check(capi.load().ck_planes_and_reduce(arr, len(planes)))
 
 
 class Planes:
@@ -233,6 +262,42 @@ class Planes:
         self.last_count = int(n.value)
         check(rc)
         return out[: n.value] if isinstance(out, np.ndarray) else int(n.value)
+
+    def king_view(self, view: Submatrix | None, kin_threshold: float, max_results: int = 10 << 20,
+                  part: tuple[int, int] = (0, 1), sort: bool = True, out=None):
+        """One part of a shard given as a VIEW into these planes (ck_king_view): `view` is any sub-matrix inside the
+        planes' sample range (None = the planes' own), `part = (index, count)` the snake-dealt band partition across
+        the GPUs of a box.  Negative thresholds with room for every pair take the dense (sort-free) output path."""
+        n = C.c_uint32(0)
+        if out is None:
+            out = np.empty(max_results, dtype=RESULT_DTYPE)
+        addr, on_device = _ptr(out)
+        rc = self._lib.ck_king_view(self._h, C.byref(view) if view is not None else None, part[0], part[1],
+                                    C.c_float(kin_threshold), max_results, addr, int(on_device), C.byref(n), int(sort))
+        self.last_count = int(n.value)
+        check(rc)
+        return out[: n.value] if isinstance(out, np.ndarray) else int(n.value)
+
+    def king_view_sink(self, view: Submatrix | None, kin_threshold: float, sink, max_results: int = 10 << 20,
+                       part: tuple[int, int] = (0, 1), chunk_records: int = 0) -> int:
+        """The same with the sorted records handed to `sink(records: np.ndarray)` chunk by chunk (ck_king_view_sink);
+        the array is only valid during the call.  Returns the number of records delivered."""
+        def trampoline(_user, ptr, count):
+            try:
+                buf = (C.c_char * (count * RESULT_DTYPE.itemsize)).from_address(ptr)
+                sink(np.frombuffer(buf, dtype=RESULT_DTYPE, count=count))
+                return 0
+            except Exception:  # never unwind through the C frame
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        cb = capi.RESULT_SINK(trampoline)
+        n = C.c_uint64(0)
+        check(self._lib.ck_king_view_sink(self._h, C.byref(view) if view is not None else None, part[0], part[1],
+                                          C.c_float(kin_threshold), max_results, chunk_records, cb, None, C.byref(n)))
+        return int(n.value)
 
     def counts(self, sample_i, sample_j) -> tuple[np.ndarray, np.ndarray]:
         """Raw six counters + kin for explicit pairs (parity hook, ck_king_counts)."""

@@ -43,8 +43,11 @@ std::string Usage() {
          "  --kin_threshold=0.0884     keep pairs with kin strictly above this\n"
          "  --split_factor=1           k: split the relatedness matrix into k(k+1)/2 shards\n"
          "  --shard_index=0            which shard to compute\n"
-         "  --num_gpus=1               split the shard's tile grid across N GPUs of this box\n"
-         "  --all_shards=false         compute every shard (decoding the input once)\n"
+         "  --num_gpus=1               GPUs of this box: triples are dealt to them and packed once, the planes exchanged\n"
+         "                             over NVLink, shards scheduled across them (a lone shard is split into parts)\n"
+         "  --all_shards=false         compute every shard of --split_factor (decoding and packing the input once)\n"
+         "  --write_success_file=false with --all_shards: write <output>/_SUCCESS when every shard is written\n"
+         "  --row_group_rows=0         rows per Parquet row group of the output (0 = a single row group)\n"
          "  --device=0                 first CUDA device\n";
 }
 
@@ -67,16 +70,26 @@ std::string ParseFlags(int argc, char **argv, Flags *f) {
       f->help = true;
       continue;
     }
-    const bool is_bool = (name == "all_shards" || name == "noall_shards");
-    if (is_bool) {
-      if (name == "noall_shards") {
-        f->all_shards = false;
-      } else if (!has_value) {
-        f->all_shards = true;
-      } else if (!ParseBool(value, &f->all_shards)) {
-        return "Illegal value '" + value + "' specified for flag 'all_shards'";
+    {  // boolean flags, Abseil syntax: --flag, --noflag, --flag=true|false
+      bool *target = nullptr;
+      bool negate = false;
+      std::string base = name;
+      if (base.rfind("no", 0) == 0 && (base.substr(2) == "all_shards" || base.substr(2) == "write_success_file")) {
+        base = base.substr(2);
+        negate = true;
       }
-      continue;
+      if (base == "all_shards") target = &f->all_shards;
+      if (base == "write_success_file") target = &f->write_success_file;
+      if (target) {
+        if (negate) {
+          *target = false;
+        } else if (!has_value) {
+          *target = true;
+        } else if (!ParseBool(value, target)) {
+          return "Illegal value '" + value + "' specified for flag '" + base + "'";
+        }
+        continue;
+      }
     }
     if (!has_value) {
       if (a + 1 >= argc) return "Missing the value for the flag '" + name + "'";
@@ -111,6 +124,9 @@ std::string ParseFlags(int argc, char **argv, Flags *f) {
     } else if (name == "num_gpus") {
       if (!ParseU64(value, 64, &u) || u == 0) return bad();
       f->num_gpus = uint32_t(u);
+    } else if (name == "row_group_rows") {
+      if (!ParseU64(value, std::numeric_limits<uint64_t>::max(), &u)) return bad();
+      f->row_group_rows = u;
     } else if (name == "device") {
       if (!ParseU64(value, 1024, &u)) return bad();
       f->device = int(u);

@@ -18,8 +18,10 @@ struct Flags {
   uint32_t split_factor = 1;                // cuking.cu:46-48
   uint32_t shard_index = 0;                 // cuking.cu:49-52
   // extensions (default to reference behaviour)
-  uint32_t num_gpus = 1;    // split the shard's tile grid across this many GPUs of the box
+  uint32_t num_gpus = 1;    // GPUs of this box to use: shards are scheduled across them, a lone shard is split into parts
   bool all_shards = false;  // decode the input once and compute every shard of --split_factor (one part file each)
+  bool write_success_file = false;  // --all_shards: write <output>/_SUCCESS at the end (cloud_batch_submit.py:103-127)
+  uint64_t row_group_rows = 0;      // rows per Parquet row group; 0 = one row group (cuking.cu:804-805)
   int device = 0;           // first CUDA device to use
   bool help = false;
 };

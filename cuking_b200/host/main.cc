@@ -8,7 +8,17 @@
 //
 // Differences, all deliberate: local directories (or file://) replace gs:// (no google-cloud-cpp here; gs:// is
 // rejected with the reference's own "Unsupported URI" error class); every CUDA call is checked; extensions
-// --num_gpus / --all_shards default to the reference behaviour of one shard on one GPU.
+// --num_gpus / --all_shards / --write_success_file default to the reference behaviour of one shard on one GPU.
+//
+// Several GPUs (--num_gpus N) - the box-local form of cloud_batch_submit.py's one VM per shard:
+//   * the input is decoded ONCE; every decoded chunk goes to ONE GPU (round-robin), which packs it into its own
+//     full-size plane set; the N partial plane sets are then AND-reduced over NVLink (ck_planes_and_reduce), so every
+//     triple is packed once and every GPU ends up with all planes;
+//   * with --all_shards the planes hold the whole cohort and every shard is a view of them; the k(k+1)/2 shards
+//     (cloud_batch_submit.py:73) are cut into work items and scheduled longest-first onto the least loaded GPU
+//     (ck_plan_work), one worker thread per GPU, all GPUs busy at once; one part file per shard, then _SUCCESS;
+//   * a lone shard is split into N parts (bands of rows dealt in snake order), merged on the host.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -16,6 +26,7 @@
 #include <filesystem>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <mutex>
 #include <sstream>
 #include <string>
@@ -114,20 +125,35 @@ Status ReadMetadata(const std::string &dir, Metadata *md) {  // cuking.cu:475-50
 // One GPU of the box.  Calls on one ck_ctx are not thread-safe, so the decode threads serialise on `mu`.
 struct Gpu {
   ck_ctx *ctx = nullptr;
+  ck_planes *planes = nullptr;
   std::mutex mu;
 };
 
-// Planes of one shard on one GPU.
-struct ShardOnGpu {
-  Gpu *gpu = nullptr;
-  ck_planes *planes = nullptr;
-};
-
-struct ShardJob {
+// Results of one shard: written straight to the part file when the shard is one work item, else collected per part and
+// merged once the last part is in.
+struct ShardOutput {
   uint32_t shard_index = 0;
   ck_submatrix sm{};
-  std::vector<ShardOnGpu *> replicas;  // one per GPU that works on this shard
+  uint32_t num_parts = 1;
+  std::vector<std::vector<ck_result>> parts;
+  std::atomic<uint32_t> parts_done{0};
 };
+
+struct SinkState {
+  cuking::ResultWriter *writer = nullptr;  // single-part shard: append to the file
+  std::vector<ck_result> *collect = nullptr;  // part of a multi-part shard
+  std::string error;
+};
+
+int SinkTrampoline(void *user, const ck_result *records, size_t count) {
+  SinkState *st = static_cast<SinkState *>(user);
+  if (st->writer) {
+    st->error = st->writer->Append(records, count);
+    return st->error.empty() ? 0 : 1;
+  }
+  st->collect->insert(st->collect->end(), records, records + count);
+  return 0;
+}
 
 Status Run(const Flags &flags) {
   // ---- flag validation, cuking.cu:437-462 ----
@@ -140,6 +166,7 @@ Status Run(const Flags &flags) {
   if (flags.split_factor == 0) return InvalidArgument("Invalid split factor");
   const uint64_t num_shards = uint64_t(flags.split_factor) * (uint64_t(flags.split_factor) + 1) / 2;
   if (flags.shard_index >= num_shards) return InvalidArgument("Invalid shard index");
+  if (num_shards > 0xffffffffull) return InvalidArgument("Invalid split factor");
 
   StopWatch stop_watch;
   std::cout << "Reading metadata...";
@@ -157,53 +184,50 @@ Status Run(const Flags &flags) {
   if (device_count <= 0) return Internal("No CUDA device found (this program has no CPU fallback)");
   if (flags.device + int(flags.num_gpus) > device_count)
     return InvalidArgument("--device/--num_gpus exceed the " + std::to_string(device_count) + " visible CUDA devices");
-  std::vector<Gpu> gpus(flags.num_gpus);
-  struct CtxCloser {
+  const uint32_t num_gpus = flags.num_gpus;
+  std::vector<Gpu> gpus(num_gpus);
+  struct Closer {  // planes before their ctx
     std::vector<Gpu> *v;
-    ~CtxCloser() {
+    ~Closer() {
+      for (Gpu &g : *v) ck_planes_destroy(g.planes);
       for (Gpu &g : *v) ck_ctx_destroy(g.ctx);
     }
-  } ctx_closer{&gpus};
-  for (uint32_t g = 0; g < flags.num_gpus; ++g)
+  } closer{&gpus};
+  for (uint32_t g = 0; g < num_gpus; ++g)
     if (int rc = ck_ctx_create(flags.device + int(g), &gpus[g].ctx); rc != CK_OK) return FromCk(rc);
-  std::cout << " " << flags.num_gpus << " GPU(s) (" << stop_watch.ElapsedAndReset() << ")" << std::endl;
+  std::cout << " " << num_gpus << " GPU(s) (" << stop_watch.ElapsedAndReset() << ")" << std::endl;
 
   // ---- shard planning (cuking.cu:505) and plane allocation (:513-523) ----
-  // One shard: all GPUs hold its planes and split its tile grid.  --all_shards: shards are dealt round-robin to the
-  // GPUs, each shard living on one GPU; the input is decoded once for all of them (the reference decodes the whole
-  // input once per shard process, cuking.cu:677).
-  std::vector<ShardJob> jobs;
-  std::vector<std::unique_ptr<ShardOnGpu>> storage;
-  struct PlanesCloser {
-    std::vector<std::unique_ptr<ShardOnGpu>> *v;
-    ~PlanesCloser() {
-      for (auto &p : *v) ck_planes_destroy(p->planes);
-    }
-  } planes_closer{&storage};
-  uint64_t plane_bytes = 0;
+  // One shard: the planes hold the shard's samples (reference behaviour).  --all_shards: they hold the whole cohort and
+  // every shard is a view of them (the reference decodes and packs the whole input once per shard process, :677).
+  const uint32_t first_shard = flags.all_shards ? 0 : flags.shard_index;
+  const uint32_t shards_to_run = flags.all_shards ? uint32_t(num_shards) : 1;
+  ck_submatrix plane_sm{};
+  if (int rc = flags.all_shards ? ck_submatrix_init(num_samples, 1, 0, &plane_sm)
+                                : ck_submatrix_init(num_samples, flags.split_factor, flags.shard_index, &plane_sm);
+      rc != CK_OK)
+    return FromCk(rc);
   std::cout << "Allocating memory for bit set...";
   std::cout.flush();
-  const uint32_t first_shard = flags.all_shards ? 0 : flags.shard_index;
-  const uint32_t last_shard = flags.all_shards ? uint32_t(num_shards) : flags.shard_index + 1;
-  for (uint32_t shard = first_shard; shard < last_shard; ++shard) {
-    ShardJob job;
-    job.shard_index = shard;
-    if (int rc = ck_submatrix_init(num_samples, flags.split_factor, shard, &job.sm); rc != CK_OK) return FromCk(rc);
-    const uint32_t g_begin = flags.all_shards ? (shard - first_shard) % flags.num_gpus : 0;
-    const uint32_t g_end = flags.all_shards ? g_begin + 1 : flags.num_gpus;
-    for (uint32_t g = g_begin; g < g_end; ++g) {
-      auto rep = std::make_unique<ShardOnGpu>();
-      rep->gpu = &gpus[g];
-      if (int rc = ck_planes_create(gpus[g].ctx, &job.sm, md.num_sites, &rep->planes); rc != CK_OK) return FromCk(rc);
-      uint64_t b = 0;
-      ck_planes_device_bytes(rep->planes, &b);
-      plane_bytes += b;
-      job.replicas.push_back(rep.get());
-      storage.push_back(std::move(rep));
-    }
-    jobs.push_back(std::move(job));
+  uint64_t plane_bytes = 0;
+  for (Gpu &g : gpus) {
+    if (int rc = ck_planes_create(g.ctx, &plane_sm, md.num_sites, &g.planes); rc != CK_OK) return FromCk(rc);
+    uint64_t b = 0;
+    ck_planes_device_bytes(g.planes, &b);
+    plane_bytes += b;
   }
-  std::cout << " " << ((plane_bytes + (1 << 20) - 1) >> 20) << " MiB on " << flags.num_gpus << " GPU(s) ("
+  // Several GPUs: probe the NVLink exchange on the still all-missing planes (AND of all-ones changes nothing).  Without
+  // peer access every GPU packs every chunk itself instead.
+  bool exchange = num_gpus > 1;
+  if (exchange) {
+    std::vector<ck_planes *> all;
+    for (Gpu &g : gpus) all.push_back(g.planes);
+    if (ck_planes_and_reduce(all.data(), num_gpus) != CK_OK) {
+      exchange = false;
+      std::cout << " [no peer access between the GPUs: every GPU packs every chunk]";
+    }
+  }
+  std::cout << " " << ((plane_bytes + (1 << 20) - 1) >> 20) << " MiB on " << num_gpus << " GPU(s) ("
             << stop_watch.ElapsedAndReset() << ")" << std::endl;
 
   // ---- list and decode input files, pack on the GPU ----
@@ -218,7 +242,7 @@ Status Run(const Flags &flags) {
   std::cout << "Processing Parquet tables...";
   std::cout.flush();
   {
-    std::atomic<size_t> next(0), processed(0), total_triples(0);
+    std::atomic<size_t> next(0), processed(0), total_triples(0), next_chunk(0);
     std::mutex err_mu;
     Status first_error;  // first error wins, like ParallelFor (cuking.cu:415-433)
     constexpr size_t kChunkRows = size_t(1) << 20;  // 20 MiB of page-locked memory per reader thread
@@ -232,19 +256,22 @@ Status Run(const Flags &flags) {
           if (!first_error.ok()) return;
         }
         Status st;
-        // Stream the file through this thread's page-locked chunk buffer: decode a chunk, let every shard that needs it
-        // pack it on its GPU (the kernel reads the pinned chunk in place), decode the next chunk.
+        // Stream the file through this thread's page-locked chunk buffer: decode a chunk, let ONE GPU pack it (the
+        // kernel reads the pinned chunk in place over PCIe), decode the next chunk.
+        auto pack_on = [&](Gpu &g, size_t first_row) -> bool {
+          std::lock_guard<std::mutex> l(g.mu);
+          const int rc = ck_pack_triples(g.planes, t.row_idx, t.col_idx, t.n_alt_alleles, t.size, /*on_device=*/0);
+          if (rc == CK_OK) return true;
+          st = FromCk(rc);
+          st.message += " (chunk starting at row " + std::to_string(first_row) + ") in " + files[f];
+          return false;
+        };
         auto consume = [&](size_t first_row) -> std::string {
-          for (ShardJob &job : jobs) {
-            for (ShardOnGpu *rep : job.replicas) {
-              std::lock_guard<std::mutex> l(rep->gpu->mu);
-              const int rc = ck_pack_triples(rep->planes, t.row_idx, t.col_idx, t.n_alt_alleles, t.size, /*on_device=*/0);
-              if (rc != CK_OK) {
-                st = FromCk(rc);
-                st.message += " (chunk starting at row " + std::to_string(first_row) + ") in " + files[f];
-                return st.message;
-              }
-            }
+          if (exchange) {
+            if (!pack_on(gpus[next_chunk.fetch_add(1) % num_gpus], first_row)) return st.message;
+          } else {
+            for (Gpu &g : gpus)
+              if (!pack_on(g, first_row)) return st.message;
           }
           return "";
         };
@@ -270,75 +297,133 @@ Status Run(const Flags &flags) {
     if (!first_error.ok()) return first_error;
     std::cout << " " << total_triples.load() << " entries (" << stop_watch.ElapsedAndReset() << ")" << std::endl;
   }
-
-  // ---- pairwise kernel per shard ----
-  const uint32_t max_results = flags.max_results;
-  std::vector<ck_result> results(max_results);
-  for (ShardJob &job : jobs) {
-    const uint32_t rows = ck_submatrix_num_rows(&job.sm), cols = ck_submatrix_num_cols(&job.sm);
-    std::cout << "Running KING CUDA kernel for " << rows << " x " << cols << " matrix";
-    if (flags.all_shards) std::cout << " (shard " << job.shard_index << ")";
-    std::cout << "...";
+  if (exchange) {
+    std::cout << "Exchanging bit sets between " << num_gpus << " GPUs...";
     std::cout.flush();
-    uint32_t num_results = 0;
-    const size_t reps = job.replicas.size();
-    if (reps == 1) {
-      const int rc = ck_king(job.replicas[0]->planes, flags.kin_threshold, max_results, results.data(), 0, &num_results, 1);
-      if (rc != CK_OK) return FromCk(rc);
-    } else {
-      // split the tile grid across GPUs; each GPU returns its retained pairs, merged and sorted on the host
-      uint64_t tiles = 0;
-      ck_king_num_tiles(job.replicas[0]->planes, &tiles);
-      std::vector<std::vector<ck_result>> part(reps);
-      std::vector<uint32_t> counts(reps, 0);
-      std::vector<int> rcs(reps, CK_OK);
-      std::vector<std::string> errs(reps);
-      std::vector<std::thread> threads;
-      for (size_t g = 0; g < reps; ++g)
-        threads.emplace_back([&, g]() {
-          part[g].resize(max_results);
-          rcs[g] = ck_king_tiles(job.replicas[g]->planes, tiles * g / reps, tiles * (g + 1) / reps, flags.kin_threshold,
-                                 max_results, part[g].data(), 0, &counts[g], 1);
-          if (rcs[g] != CK_OK) errs[g] = ck_last_error();
-        });
-      for (auto &th : threads) th.join();
-      uint64_t total = 0;
-      for (size_t g = 0; g < reps; ++g) {
-        if (rcs[g] != CK_OK && rcs[g] != CK_ERR_RESULT_OVERFLOW) return Internal(errs[g]);
-        total += counts[g];
+    std::vector<ck_planes *> all;
+    for (Gpu &g : gpus) all.push_back(g.planes);
+    if (int rc = ck_planes_and_reduce(all.data(), num_gpus); rc != CK_OK) return FromCk(rc);
+    std::cout << " (" << stop_watch.ElapsedAndReset() << ")" << std::endl;
+  }
+
+  // ---- work items: (shard, part) scheduled onto the GPUs ----
+  uint32_t num_items = 0;
+  if (int rc = ck_plan_work(num_samples, flags.split_factor, first_shard, shards_to_run, num_gpus, nullptr, 0, &num_items); rc != CK_OK)
+    return FromCk(rc);
+  std::vector<ck_work_item> items(std::max<uint32_t>(num_items, 1));
+  if (int rc = ck_plan_work(num_samples, flags.split_factor, first_shard, shards_to_run, num_gpus, items.data(), num_items, &num_items);
+      rc != CK_OK)
+    return FromCk(rc);
+  items.resize(num_items);
+  std::vector<std::unique_ptr<ShardOutput>> outputs(shards_to_run);
+  for (uint32_t q = 0; q < shards_to_run; ++q) {
+    outputs[q] = std::make_unique<ShardOutput>();
+    outputs[q]->shard_index = first_shard + q;
+    if (int rc = ck_submatrix_init(num_samples, flags.split_factor, first_shard + q, &outputs[q]->sm); rc != CK_OK) return FromCk(rc);
+  }
+  for (const ck_work_item &it : items) {
+    ShardOutput &o = *outputs[it.shard_index - first_shard];
+    o.num_parts = it.num_parts;
+    o.parts.resize(it.num_parts);
+  }
+
+  // ---- pairwise kernel: one worker thread per GPU, every GPU runs its items in order ----
+  std::mutex log_mu, err_mu;
+  Status first_error;
+  auto fail_with = [&](const Status &st) {
+    std::lock_guard<std::mutex> l(err_mu);
+    if (first_error.ok()) first_error = st;
+  };
+  auto failed = [&]() {
+    std::lock_guard<std::mutex> l(err_mu);
+    return !first_error.ok();
+  };
+  // writes one shard's part file from its merged parts (k-way merge by (i, j): bands of different parts interleave)
+  auto write_merged = [&](ShardOutput &o) -> Status {
+    uint64_t total = 0;
+    for (const auto &p : o.parts) total += p.size();
+    if (total > flags.max_results)  // cuking.cu:747-751 applies to the shard as a whole
+      return ResourceExhausted("Could not store all results: try increasing the --max_results parameter.");
+    cuking::ResultWriter writer;
+    if (std::string e = writer.Open(output_dir, o.shard_index, &md.sample_ids, flags.row_group_rows); !e.empty()) return Unknown(e);
+    std::vector<size_t> pos(o.parts.size(), 0);
+    std::vector<ck_result> batch;
+    batch.reserve(1 << 16);
+    for (uint64_t done = 0; done < total; ++done) {
+      size_t best = o.parts.size();
+      for (size_t g = 0; g < o.parts.size(); ++g) {
+        if (pos[g] >= o.parts[g].size()) continue;
+        if (best == o.parts.size()) { best = g; continue; }
+        const ck_result &a = o.parts[g][pos[g]], &b = o.parts[best][pos[best]];
+        if (a.sample_i < b.sample_i || (a.sample_i == b.sample_i && a.sample_j < b.sample_j)) best = g;
       }
-      if (total > max_results)  // cuking.cu:747-751
-        return ResourceExhausted("Could not store all results: try increasing the --max_results parameter.");
-      // tile slices are contiguous in (row block, column block) order, but rows of one block interleave across
-      // slices only at slice boundaries: a k-way merge by (i, j) restores the global order
-      std::vector<size_t> pos(reps, 0);
-      for (uint64_t o = 0; o < total; ++o) {
-        size_t best = reps;
-        for (size_t g = 0; g < reps; ++g) {
-          if (pos[g] >= counts[g]) continue;
-          if (best == reps) { best = g; continue; }
-          const ck_result &a = part[g][pos[g]], &b = part[best][pos[best]];
-          if (a.sample_i < b.sample_i || (a.sample_i == b.sample_i && a.sample_j < b.sample_j)) best = g;
-        }
-        results[o] = part[best][pos[best]++];
+      batch.push_back(o.parts[best][pos[best]++]);
+      if (batch.size() == batch.capacity() || done + 1 == total) {
+        if (std::string e = writer.Append(batch.data(), batch.size()); !e.empty()) return Unknown(e);
+        batch.clear();
       }
-      num_results = uint32_t(total);
     }
-    ck_timings tm{};
-    ck_ctx_get_timings(job.replicas[0]->gpu->ctx, &tm);
-    std::cout << " (" << stop_watch.ElapsedAndReset() << "; kernel " << tm.king_ms << " ms on GPU " << flags.device << ")"
-              << std::endl;
-
-    std::cout << "Processing " << num_results << " results...";
-    std::cout.flush();
     std::string path;
     size_t bytes = 0;
-    if (std::string e = cuking::WriteResults(output_dir, job.shard_index, md.sample_ids, results.data(), num_results,
-                                             &path, &bytes);
-        !e.empty())
-      return Unknown(e);
-    std::cout << " (" << stop_watch.ElapsedAndReset() << ")" << std::endl;
-    std::cout << "Wrote " << ((bytes + (1 << 20) - 1) >> 20) << " MiB to " << path << "." << std::endl;
+    if (std::string e = writer.Close(&path, &bytes); !e.empty()) return Unknown(e);
+    std::lock_guard<std::mutex> l(log_mu);
+    std::cout << "Processing " << total << " results... shard " << o.shard_index << ": wrote " << ((bytes + (1 << 20) - 1) >> 20)
+              << " MiB to " << path << "." << std::endl;
+    return Ok();
+  };
+  auto gpu_worker = [&](uint32_t g) {
+    for (const ck_work_item &it : items) {
+      if (it.gpu != g || failed()) continue;
+      ShardOutput &o = *outputs[it.shard_index - first_shard];
+      const auto t0 = std::chrono::steady_clock::now();
+      SinkState sink;
+      cuking::ResultWriter writer;
+      if (it.num_parts == 1) {
+        if (std::string e = writer.Open(output_dir, o.shard_index, &md.sample_ids, flags.row_group_rows); !e.empty()) return fail_with(Unknown(e));
+        sink.writer = &writer;
+      } else {
+        sink.collect = &o.parts[it.part_index];
+      }
+      uint64_t count = 0;
+      const int rc = ck_king_view_sink(gpus[g].planes, flags.all_shards ? &o.sm : nullptr, it.part_index, it.num_parts,
+                                       flags.kin_threshold, flags.max_results, 0, SinkTrampoline, &sink, &count);
+      if (rc != CK_OK) return fail_with(sink.error.empty() ? FromCk(rc) : Unknown(sink.error));
+      ck_timings tm{};
+      ck_ctx_get_timings(gpus[g].ctx, &tm);
+      const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      std::string path;
+      size_t bytes = 0;
+      if (it.num_parts == 1)
+        if (std::string e = writer.Close(&path, &bytes); !e.empty()) return fail_with(Unknown(e));
+      {
+        std::lock_guard<std::mutex> l(log_mu);
+        std::cout << "Running KING CUDA kernel for " << ck_submatrix_num_rows(&o.sm) << " x " << ck_submatrix_num_cols(&o.sm) << " matrix";
+        if (flags.all_shards || it.num_parts > 1)
+          std::cout << " (shard " << o.shard_index << ", part " << it.part_index + 1 << "/" << it.num_parts << ")";
+        char buf[96];
+        snprintf(buf, sizeof(buf), "... (%.4gs; kernel %.4g ms on GPU %d)", secs, double(tm.king_ms), flags.device + int(g));
+        std::cout << buf << std::endl;
+        if (it.num_parts == 1)
+          std::cout << "Processing " << count << " results... wrote " << ((bytes + (1 << 20) - 1) >> 20) << " MiB to " << path << "." << std::endl;
+      }
+      if (it.num_parts > 1 && o.parts_done.fetch_add(1) + 1 == it.num_parts)  // the last part in merges and writes the shard
+        if (Status st = write_merged(o); !st.ok()) return fail_with(st);
+    }
+  };
+  {
+    std::vector<std::thread> threads;
+    for (uint32_t g = 0; g < num_gpus; ++g) threads.emplace_back(gpu_worker, g);
+    for (auto &th : threads) th.join();
+  }
+  if (!first_error.ok()) return first_error;
+  std::cout << "Computed " << shards_to_run << " shard(s) in " << items.size() << " work item(s) on " << num_gpus << " GPU(s) ("
+            << stop_watch.ElapsedAndReset() << ")" << std::endl;
+
+  if (flags.write_success_file) {  // cloud_batch_submit.py:103-127: an empty _SUCCESS once every shard is written
+    const std::string path = output_dir + "/_SUCCESS";
+    std::ofstream out(path, std::ios::binary | std::ios::trunc);
+    if (!out) return Unknown("Cannot write " + path);
+    std::cout << "Wrote " << path << "." << std::endl;
   }
   return Ok();
 }

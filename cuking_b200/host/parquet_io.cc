@@ -123,16 +123,49 @@ std::string ReadTriples(const std::string &path, size_t chunk_rows, Triples *buf
   return "";
 }
 
-std::string WriteResults(const std::string &dir, uint32_t shard_index, const std::vector<std::string> &sample_ids,
-                         const ck_result *results, size_t n, std::string *path_out, size_t *bytes_written) {
+struct ResultWriter::Impl {
+  std::string path, tmp;
+  const std::vector<std::string> *sample_ids = nullptr;
+  std::shared_ptr<arrow::io::FileOutputStream> sink;
+  std::shared_ptr<parquet::ParquetFileWriter> writer;
+  parquet::RowGroupWriter *rg = nullptr;
+  uint64_t row_group_rows = 0, rows_in_group = 0;
+  std::vector<parquet::ByteArray> strings;
+  std::vector<float> floats;
+  std::vector<int32_t> ints;
+  bool closed = false;
+};
+
+ResultWriter::ResultWriter() = default;
+
+ResultWriter::~ResultWriter() {
+  if (impl_ && !impl_->closed) {
+    try {
+      if (impl_->writer) impl_->writer->Close();
+      if (impl_->sink) (void)impl_->sink->Close();
+    } catch (...) {
+    }
+    std::error_code ec;
+    fs::remove(impl_->tmp, ec);
+  }
+  delete impl_;
+}
+
+std::string ResultWriter::Open(const std::string &dir, uint32_t shard_index, const std::vector<std::string> *sample_ids,
+                               uint64_t row_group_rows) {
   try {
+    delete impl_;
+    impl_ = new Impl();
+    rows_ = 0;
     std::error_code ec;
     fs::create_directories(dir, ec);
     if (ec) return "Cannot create output directory " + dir + ": " + ec.message();
     char name[64];
     snprintf(name, sizeof(name), "part-%05u.snappy.parquet", shard_index);  // cuking.cu:868-870
-    const std::string path = (fs::path(dir) / name).string();
-    const std::string tmp = path + ".tmp";
+    impl_->path = (fs::path(dir) / name).string();
+    impl_->tmp = impl_->path + ".tmp";
+    impl_->sample_ids = sample_ids;
+    impl_->row_group_rows = row_group_rows;
 
     using parquet::schema::PrimitiveNode;
     parquet::schema::NodeVector fields;  // cuking.cu:770-788
@@ -145,61 +178,92 @@ std::string WriteResults(const std::string &dir, uint32_t shard_index, const std
     auto schema = std::static_pointer_cast<parquet::schema::GroupNode>(
         parquet::schema::GroupNode::Make("schema", parquet::Repetition::REQUIRED, fields));  // cuking.cu:789-791
 
-    auto sink_result = arrow::io::FileOutputStream::Open(tmp);
-    if (!sink_result.ok()) return "Cannot open " + tmp + ": " + sink_result.status().ToString();
-    std::shared_ptr<arrow::io::FileOutputStream> sink = *sink_result;
+    auto sink_result = arrow::io::FileOutputStream::Open(impl_->tmp);
+    if (!sink_result.ok()) return "Cannot open " + impl_->tmp + ": " + sink_result.status().ToString();
+    impl_->sink = *sink_result;
     parquet::WriterProperties::Builder props;
     props.compression(parquet::Compression::SNAPPY);  // Hail's libhadoop has no ZSTD, cuking.cu:797-798
     props.max_row_group_length(int64_t(1) << 62);
-    std::shared_ptr<parquet::ParquetFileWriter> writer = parquet::ParquetFileWriter::Open(sink, schema, props.build());
-    parquet::RowGroupWriter *rg = writer->AppendRowGroup();  // single row group, cuking.cu:804-805
-
-    constexpr size_t kBatch = 1 << 16;  // the reference writes one value per WriteBatch call (:810-859); batch instead
-    for (int which = 0; which < 2; ++which) {  // i, j
-      auto *col = static_cast<parquet::ByteArrayWriter *>(rg->NextColumn());
-      std::vector<parquet::ByteArray> batch(std::min(kBatch, std::max<size_t>(n, 1)));
-      for (size_t base = 0; base < n; base += kBatch) {
-        const size_t m = std::min(kBatch, n - base);
-        for (size_t q = 0; q < m; ++q) {
-          const uint32_t s = which == 0 ? results[base + q].sample_i : results[base + q].sample_j;
-          if (s >= sample_ids.size()) return "Result refers to sample " + std::to_string(s) + " beyond metadata.json";
-          batch[q] = parquet::ByteArray(uint32_t(sample_ids[s].size()), reinterpret_cast<const uint8_t *>(sample_ids[s].data()));
-        }
-        col->WriteBatch(int64_t(m), nullptr, nullptr, batch.data());
-      }
-    }
-    {  // kin
-      auto *col = static_cast<parquet::FloatWriter *>(rg->NextColumn());
-      std::vector<float> batch(std::min(kBatch, std::max<size_t>(n, 1)));
-      for (size_t base = 0; base < n; base += kBatch) {
-        const size_t m = std::min(kBatch, n - base);
-        for (size_t q = 0; q < m; ++q) batch[q] = results[base + q].kin;
-        col->WriteBatch(int64_t(m), nullptr, nullptr, batch.data());
-      }
-    }
-    for (int which = 0; which < 3; ++which) {  // ibs0, ibs1, ibs2
-      auto *col = static_cast<parquet::Int32Writer *>(rg->NextColumn());
-      std::vector<int32_t> batch(std::min(kBatch, std::max<size_t>(n, 1)));
-      for (size_t base = 0; base < n; base += kBatch) {
-        const size_t m = std::min(kBatch, n - base);
-        for (size_t q = 0; q < m; ++q) {
-          const ck_result &r = results[base + q];
-          batch[q] = int32_t(which == 0 ? r.ibs0 : which == 1 ? r.ibs1 : r.ibs2);
-        }
-        col->WriteBatch(int64_t(m), nullptr, nullptr, batch.data());
-      }
-    }
-    writer->Close();
-    auto st = sink->Close();
-    if (!st.ok()) return "Cannot close " + tmp + ": " + st.ToString();
-    fs::rename(tmp, path, ec);  // readers never see a partial part file
-    if (ec) return "Cannot rename " + tmp + ": " + ec.message();
-    if (path_out) *path_out = path;
-    if (bytes_written) *bytes_written = size_t(fs::file_size(path, ec));
+    impl_->writer = parquet::ParquetFileWriter::Open(impl_->sink, schema, props.build());
+    // a buffered row group takes values for all six columns chunk after chunk (pages are compressed as they fill)
+    impl_->rg = impl_->writer->AppendBufferedRowGroup();
   } catch (const std::exception &e) {
     return std::string("Error writing results: ") + e.what();
   }
   return "";
+}
+
+std::string ResultWriter::Append(const ck_result *results, size_t n) {
+  if (!impl_ || !impl_->rg) return "Error writing results: writer is not open";
+  Impl &w = *impl_;
+  try {
+    constexpr size_t kBatch = 1 << 16;  // the reference writes one value per WriteBatch call (:810-859); batch instead
+    for (size_t base = 0; base < n;) {
+      size_t m = std::min(kBatch, n - base);
+      if (w.row_group_rows > 0) {
+        if (w.rows_in_group == w.row_group_rows) {
+          w.rg->Close();
+          w.rg = w.writer->AppendBufferedRowGroup();
+          w.rows_in_group = 0;
+        }
+        m = size_t(std::min<uint64_t>(m, w.row_group_rows - w.rows_in_group));
+      }
+      const ck_result *r = results + base;
+      w.strings.resize(m);
+      for (int which = 0; which < 2; ++which) {  // i, j: sample_ids[sample_i], cuking.cu:811,:821
+        for (size_t q = 0; q < m; ++q) {
+          const uint32_t s = which == 0 ? r[q].sample_i : r[q].sample_j;
+          if (s >= w.sample_ids->size()) return "Result refers to sample " + std::to_string(s) + " beyond metadata.json";
+          const std::string &id = (*w.sample_ids)[s];
+          w.strings[q] = parquet::ByteArray(uint32_t(id.size()), reinterpret_cast<const uint8_t *>(id.data()));
+        }
+        static_cast<parquet::ByteArrayWriter *>(w.rg->column(which))->WriteBatch(int64_t(m), nullptr, nullptr, w.strings.data());
+      }
+      w.floats.resize(m);
+      for (size_t q = 0; q < m; ++q) w.floats[q] = r[q].kin;
+      static_cast<parquet::FloatWriter *>(w.rg->column(2))->WriteBatch(int64_t(m), nullptr, nullptr, w.floats.data());
+      w.ints.resize(m);
+      for (int which = 0; which < 3; ++which) {  // ibs0, ibs1, ibs2
+        for (size_t q = 0; q < m; ++q) w.ints[q] = int32_t(which == 0 ? r[q].ibs0 : which == 1 ? r[q].ibs1 : r[q].ibs2);
+        static_cast<parquet::Int32Writer *>(w.rg->column(3 + which))->WriteBatch(int64_t(m), nullptr, nullptr, w.ints.data());
+      }
+      w.rows_in_group += m;
+      rows_ += m;
+      base += m;
+    }
+  } catch (const std::exception &e) {
+    return std::string("Error writing results: ") + e.what();
+  }
+  return "";
+}
+
+std::string ResultWriter::Close(std::string *path_out, size_t *bytes_written) {
+  if (!impl_ || !impl_->writer) return "Error writing results: writer is not open";
+  Impl &w = *impl_;
+  try {
+    w.rg->Close();
+    w.rg = nullptr;
+    w.writer->Close();
+    auto st = w.sink->Close();
+    if (!st.ok()) return "Cannot close " + w.tmp + ": " + st.ToString();
+    std::error_code ec;
+    fs::rename(w.tmp, w.path, ec);  // readers never see a partial part file
+    if (ec) return "Cannot rename " + w.tmp + ": " + ec.message();
+    w.closed = true;
+    if (path_out) *path_out = w.path;
+    if (bytes_written) *bytes_written = size_t(fs::file_size(w.path, ec));
+  } catch (const std::exception &e) {
+    return std::string("Error writing results: ") + e.what();
+  }
+  return "";
+}
+
+std::string WriteResults(const std::string &dir, uint32_t shard_index, const std::vector<std::string> &sample_ids,
+                         const ck_result *results, size_t n, std::string *path_out, size_t *bytes_written) {
+  ResultWriter w;
+  if (std::string e = w.Open(dir, shard_index, &sample_ids, 0); !e.empty()) return e;
+  if (std::string e = w.Append(results, n); !e.empty()) return e;
+  return w.Close(path_out, bytes_written);
 }
 
 }  // namespace cuking

@@ -42,8 +42,31 @@ std::string ListParquetFiles(const std::string &dir, std::vector<std::string> *f
 std::string ReadTriples(const std::string &path, size_t chunk_rows, Triples *buf,
                         const std::function<std::string(size_t)> &consume, size_t *rows_out);
 
-// Writes <dir>/part-<%05d shard>.snappy.parquet with the reference schema (all REQUIRED): i, j BYTE_ARRAY/String,
-// kin FLOAT, ibs0, ibs1, ibs2 INT32; Snappy; one row group.  Returns "" or an error; *bytes_written = file size.
+// Writer of <dir>/part-<%05d shard>.snappy.parquet with the reference schema (all REQUIRED): i, j BYTE_ARRAY/String,
+// kin FLOAT, ibs0, ibs1, ibs2 INT32; Snappy (cuking.cu:770-798, :868-870).  Records are appended in sorted order chunk by
+// chunk, so a shard's output never has to sit in host memory as a whole (the reference sorts and writes from one
+// max_results-sized array, one value per WriteBatch call, :761-862).  One row group by default like the reference
+// (:804-805) - its column pages are buffered compressed until Close; `row_group_rows` > 0 closes a row group every that
+// many rows and bounds the buffering for outputs of billions of rows.  The file appears under its final name only on
+// a successful Close (written as .tmp, then renamed), so readers never see a partial part file.
+class ResultWriter {
+ public:
+  ResultWriter();
+  ~ResultWriter();  // abandons (deletes) an unfinished file
+  ResultWriter(const ResultWriter &) = delete;
+  ResultWriter &operator=(const ResultWriter &) = delete;
+  std::string Open(const std::string &dir, uint32_t shard_index, const std::vector<std::string> *sample_ids, uint64_t row_group_rows);
+  std::string Append(const ck_result *records, size_t n);
+  std::string Close(std::string *path_out, size_t *bytes_written);
+  uint64_t rows() const { return rows_; }
+
+ private:
+  struct Impl;
+  Impl *impl_ = nullptr;
+  uint64_t rows_ = 0;
+};
+
+// One-shot form: Open + Append + Close.
 std::string WriteResults(const std::string &dir, uint32_t shard_index, const std::vector<std::string> &sample_ids,
                          const ck_result *results, size_t num_results, std::string *path_out, size_t *bytes_written);
 

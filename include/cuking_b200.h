@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CK_ABI_VERSION 1
+#define CK_ABI_VERSION 2
 
 enum ck_status {
   CK_OK = 0,
@@ -100,6 +100,19 @@ uint32_t ck_submatrix_sample_offset(const ck_submatrix *sm, uint32_t s); /* cuki
 /* u64 words per sample in the REFERENCE layout: 2 * ceil(pad32(num_sites) / 64), cuking.cu:498-500, :513. */
 uint32_t ck_words_per_sample(uint32_t num_sites);
 
+/* Orchestration of several shards on the GPUs of one box - the local counterpart of one Cloud Batch task per shard,
+ * cloud_batch_submit.py:45,73.  Shards [first_shard, first_shard + num_run) of the split are cut into work items and
+ * assigned to GPUs: a shard whose pair count exceeds the per-GPU share is split into parts (ck_king_view's part_index /
+ * num_parts) so that no item is larger than the share, then the items go to the GPUs longest-first onto the least
+ * loaded GPU (LPT; diagonal shards cost about half an off-diagonal one).  `items` receives at most max_items entries,
+ * grouped by GPU in execution order; *num_items the number needed. */
+typedef struct ck_work_item {
+  uint32_t shard_index, part_index, num_parts, gpu;
+  uint64_t pairs; /* i < j pairs of the whole shard (an item's cost is pairs / num_parts) */
+} ck_work_item;
+int ck_plan_work(uint32_t num_samples, uint32_t split_factor, uint32_t first_shard, uint32_t num_run, uint32_t num_gpus,
+                 ck_work_item *items, uint32_t max_items, uint32_t *num_items);
+
 /* ---- context --------------------------------------------------------------------------------------------- */
 
 int ck_ctx_create(int device, ck_ctx **out);
@@ -112,6 +125,13 @@ int ck_ctx_set_stream(ck_ctx *ctx, void *cuda_stream);
  * with more than 2^23 sites are routed to variant 2), -1 = library default (= 3; also settable with the
  * CUKING_KING_VARIANT environment variable).  Results are bit-identical across variants. */
 int ck_ctx_set_king_variant(ck_ctx *ctx, int variant);
+/* Variant 3 relies on the tensor core adding E2M1 products into its fp32 accumulator without losing low bits, which the
+ * PTX ISA does not spell out.  The first use of variant 3 on a ctx therefore runs an on-device self-test (about a
+ * millisecond: accumulators pre-loaded just below 2^21 .. 2^24, addends of 1, 1/2 and 1/4, alternating signs, single
+ * non-zero operands, compared with integer arithmetic); if any accumulator differs, the ctx runs variant 2 (int8, s32
+ * accumulators, exact by specification) wherever variant 3 was asked for, and says so on stderr.  This call runs the
+ * self-test now: *exact = 1 / 0, and ck_last_error() holds a one-line report. */
+int ck_ctx_fp4_selftest(ck_ctx *ctx, int *exact);
 int ck_ctx_synchronize(ck_ctx *ctx);
 int ck_ctx_get_timings(ck_ctx *ctx, ck_timings *out);
 /* Measures, on this GPU and now, the sustained issue rate of POPC.32 and LOP3 (lane-ops per second, whole chip).
@@ -149,6 +169,14 @@ int ck_pack_triples(ck_planes *planes, const int64_t *row_idx, const int64_t *co
 int ck_host_alloc(size_t bytes, void **out);
 int ck_host_free(void *ptr);
 
+/* AND-all-reduce of the raw planes of `count` plane sets of identical shape, one per GPU, over NVLink peer memory.
+ * The pack only clears bits of an all-missing bit set (cuking.cu:689-696), so it distributes over AND: deal the triples
+ * to the GPUs (each triple to exactly one), let each pack its share into its own full-size planes, then call this:
+ * afterwards every GPU holds the planes of ALL triples.  One fused reduce-scatter + all-gather kernel per GPU (P2P
+ * loads and stores), nothing through the host.  Called by one host thread while no other call runs on the ctxs
+ * involved; fails with CK_ERR_CUDA when the GPUs have no peer access to each other. */
+int ck_planes_and_reduce(ck_planes *const *planes, uint32_t count);
+
 /* Exchange with the reference bit-set layout (cuking.cu:204-212, :507-523): sample-major uint64 words, slot o at
  * [o*W, (o+1)*W), het plane first, hom-alt plane second, W = ck_words_per_sample(num_sites); site r is bit r&63 of
  * word r>>6; (het, hom-alt) = (1,1) means missing, including the padding sites.  The buffer covers all
@@ -170,8 +198,32 @@ int ck_planes_synthesize(ck_planes *planes, const ck_synth_params *params);
 int ck_king(ck_planes *planes, float kin_threshold, uint32_t max_results, ck_result *results, int results_on_device,
             uint32_t *num_results, int sort);
 
+/* A shard as a VIEW into planes that hold a larger sample range, and one PART of it (cuking.cu:129-152 allocates and
+ * packs one bit set per shard process; here a cohort is packed once and every shard of a --split_factor run reads it):
+ *   planes      created over a diagonal sub-matrix, i.e. one contiguous sample range (the whole cohort, typically);
+ *   view        any sub-matrix inside that range whose rows and columns are identical (diagonal shard) or disjoint with
+ *               the rows first (off-diagonal shard) - exactly what ck_submatrix_init yields; NULL = the planes' own
+ *               sub-matrix (then off-diagonal planes work too);
+ *   part_index  of num_parts: the bands of 1024 rows of the view are dealt to the parts in snake order, so the parts
+ *               carry equal work; the parts are disjoint and their union is the whole view (one part per GPU of a box;
+ *               max_results bounds each part).
+ * Everything else as ck_king.  Views need kernel variant 2 or 3.
+ * Dense output: when kin_threshold < 0 and max_results >= the number of i < j pairs of the part (BASELINE configs[4],
+ * --kin_threshold -1), sorted host results are produced WITHOUT the append counter or a sort: every pair is written to
+ * the position it has in the sorted output, the rare below-threshold pairs are squeezed out afterwards, and finished
+ * rows are copied to the host (page-locked `results` recommended: ck_host_alloc) while later rows are still computed. */
+int ck_king_view(ck_planes *planes, const ck_submatrix *view, uint32_t part_index, uint32_t num_parts, float kin_threshold,
+                 uint32_t max_results, ck_result *results, int results_on_device, uint32_t *num_results, int sort);
+/* The same with the sorted records delivered chunk by chunk (at most chunk_records per call, 0 = 4 Mi) to `sink`, in
+ * order, through a page-locked double buffer the library owns: host memory stays bounded whatever the result size, and
+ * the copy of the next chunk overlaps the sink's work on this one (cuking.cu:761-862 sorts and writes from one
+ * max_results-sized managed array).  A non-zero return value of the sink aborts the call. */
+typedef int (*ck_result_sink)(void *user, const ck_result *records, size_t count);
+int ck_king_view_sink(ck_planes *planes, const ck_submatrix *view, uint32_t part_index, uint32_t num_parts, float kin_threshold,
+                      uint32_t max_results, size_t chunk_records, ck_result_sink sink, void *user, uint64_t *num_results);
+
 /* The pairwise kernel variant that ck_king* will run on these planes (the ctx's variant, except that variant 3 falls
- * back to 2 beyond 2^23 sites). */
+ * back to 2 beyond 2^23 sites or when the ctx's GPU failed the kind::mxf4 self-test). */
 int ck_planes_king_variant(const ck_planes *pl, int *variant);
 /* Same, restricted to the linear range [tile_begin, tile_end) of the sub-matrix's tile grid (row-major over the tiles
  * that can contain an i < j pair; the tile shape belongs to the active kernel variant, so tile counts are only

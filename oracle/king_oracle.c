@@ -224,3 +224,100 @@ int ko_num_threads(void) {
   return 1;
 #endif
 }
+
+void ko_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+/* ---- the synthetic cohort of SURVEY.md section 8d, for the CPU baseline's inputs -------------------------------------
+ * Restatement in plain C of the bench generator (cuking_b200/csrc/synth.cuh - the repo's own definition, not reference
+ * code) so that bench.py's --impl reference arm can build its sample of the workload without loading the product
+ * library: splitmix64-keyed streams, per-site allele frequency 0.05 + 0.45 u, HWE founders, pedigrees in blocks of 8
+ * samples (members 0, 1, 4, 6 founders; 2, 3 children of (0, 1); 5 child of (2, 4); 7 child of (5, 6)), independent
+ * missingness.  tests/test_oracle.py pins it against ck_synth_genotypes_host cell by cell. */
+static uint64_t syn_mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+static uint64_t syn_key(uint64_t seed, uint32_t tag, uint32_t sample) {
+  return syn_mix64(seed ^ syn_mix64(((uint64_t)tag << 32) | sample));
+}
+static uint64_t syn_at(uint64_t key, uint32_t site) { return syn_mix64(key + 0x9e3779b97f4a7c15ull * ((uint64_t)site + 1)); }
+
+static void syn_block(uint64_t seed, uint32_t block, uint32_t site, uint32_t miss_thr, int8_t g[8]) {
+  enum { TAG_AF = 1, TAG_HAP = 2, TAG_SEL = 3, TAG_MISS = 4 };
+  static const int founder[8] = {1, 1, 0, 0, 1, 0, 1, 0};
+  static const int pa[8] = {0, 0, 0, 0, 0, 2, 0, 5}, pb[8] = {0, 0, 1, 1, 0, 4, 0, 6};
+  static const int order[8] = {0, 1, 4, 6, 2, 3, 5, 7}; /* parents before children */
+  const uint32_t p = 214748365u + (uint32_t)(((syn_at(syn_key(seed, TAG_AF, 0), site) >> 32) * 1932735283ull) >> 32);
+  uint8_t h[8][2];
+  for (int q = 0; q < 8; ++q) {
+    const int m = order[q];
+    const uint64_t x = syn_at(syn_key(seed, founder[m] ? TAG_HAP : TAG_SEL, block * 8 + (uint32_t)m), site);
+    if (founder[m]) {
+      h[m][0] = (uint32_t)x < p;
+      h[m][1] = (uint32_t)(x >> 32) < p;
+    } else {
+      h[m][0] = h[pa[m]][x & 1];
+      h[m][1] = h[pb[m]][(x >> 1) & 1];
+    }
+  }
+  for (int m = 0; m < 8; ++m) {
+    const int missing = (uint32_t)(syn_at(syn_key(seed, TAG_MISS, block * 8 + (uint32_t)m), site) >> 32) < miss_thr;
+    g[m] = missing ? (int8_t)-1 : (int8_t)(h[m][0] + h[m][1]);
+  }
+}
+
+static uint32_t syn_missing_threshold(double m) {
+  if (!(m > 0.0)) return 0u;
+  if (m >= 1.0) return 0xffffffffu;
+  return (uint32_t)(m * 4294967296.0);
+}
+
+/* dense genotypes out[(s - sample_begin) * sites + (r - site_begin)] in {0, 1, 2} or -1 */
+void ko_synth_genotypes(uint64_t seed, double missing_rate, uint32_t sample_begin, uint32_t sample_end, uint32_t site_begin,
+                        uint32_t site_end, int8_t *out) {
+  if (sample_end <= sample_begin || site_end <= site_begin) return;
+  const uint32_t thr = syn_missing_threshold(missing_rate);
+  const size_t sites = site_end - site_begin;
+#pragma omp parallel for schedule(static)
+  for (int64_t block = sample_begin / 8; block <= (int64_t)((sample_end - 1) / 8); ++block)
+    for (uint32_t site = site_begin; site < site_end; ++site) {
+      int8_t g[8];
+      syn_block(seed, (uint32_t)block, site, thr, g);
+      for (uint32_t m = 0; m < 8; ++m) {
+        const uint32_t s = (uint32_t)block * 8 + m;
+        if (s >= sample_begin && s < sample_end) out[(size_t)(s - sample_begin) * sites + (site - site_begin)] = g[m];
+      }
+    }
+}
+
+/* the same cohort straight into a reference-layout bit set (cuking.cu:507-523) for samples [sample_begin, sample_end) at
+ * slots 0 .. n-1: bit_sets must hold n * words_per_sample words; padding sites stay missing */
+void ko_synth_bitset(uint64_t seed, double missing_rate, uint32_t sample_begin, uint32_t sample_end, uint32_t num_sites,
+                     uint64_t *bit_sets) {
+  if (sample_end <= sample_begin) return;
+  const uint32_t thr = syn_missing_threshold(missing_rate);
+  const uint32_t wps = ko_words_per_sample(ko_padded_sites(num_sites)), half = wps / 2;
+  memset(bit_sets, 0xff, (size_t)(sample_end - sample_begin) * wps * sizeof(uint64_t)); /* cuking.cu:519-523 */
+#pragma omp parallel for schedule(static)
+  for (int64_t block = sample_begin / 8; block <= (int64_t)((sample_end - 1) / 8); ++block)
+    for (uint32_t site = 0; site < num_sites; ++site) {
+      int8_t g[8];
+      syn_block(seed, (uint32_t)block, site, thr, g);
+      for (uint32_t m = 0; m < 8; ++m) {
+        const uint32_t s = (uint32_t)block * 8 + m;
+        if (s < sample_begin || s >= sample_end || g[m] < 0) continue;
+        uint64_t *het = bit_sets + (size_t)(s - sample_begin) * wps, *alt = het + half;
+        const uint64_t bit = 1ull << (site & 63);
+        if (g[m] != 1) het[site >> 6] &= ~bit; /* cuking.cu:689, :696 */
+        if (g[m] != 2) alt[site >> 6] &= ~bit; /* cuking.cu:690, :693 */
+      }
+    }
+}

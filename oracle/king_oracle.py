@@ -100,6 +100,12 @@ def lib(native: bool = False) -> C.CDLL:
     L.ko_bench_rect.restype = C.c_uint64
     L.ko_num_threads.argtypes = []
     L.ko_num_threads.restype = C.c_int
+    L.ko_set_num_threads.argtypes = [C.c_int]
+    L.ko_set_num_threads.restype = None
+    L.ko_synth_genotypes.argtypes = [C.c_uint64, C.c_double, u32, u32, u32, u32, C.c_void_p]
+    L.ko_synth_genotypes.restype = None
+    L.ko_synth_bitset.argtypes = [C.c_uint64, C.c_double, u32, u32, u32, C.c_void_p]
+    L.ko_synth_bitset.restype = None
     _LIBS[native] = L
     return L
 
@@ -165,3 +171,19 @@ def king(bit_set: np.ndarray, num_sites: int, sm: Submatrix, kin_threshold: floa
     if sort:
         L.ko_sort(res.ctypes.data, n)
     return res, int(idx.value), bool(ovf.value)
+
+
+def synth_genotypes(seed: int, missing_rate: float, sample_begin: int, sample_end: int, site_begin: int, site_end: int,
+                    native: bool = False) -> np.ndarray:
+    """Dense int8 genotypes (-1 = missing) of the bench's synthetic cohort, [samples, sites]."""
+    out = np.empty((sample_end - sample_begin, site_end - site_begin), dtype=np.int8)
+    lib(native).ko_synth_genotypes(seed, missing_rate, sample_begin, sample_end, site_begin, site_end, out.ctypes.data)
+    return out
+
+
+def synth_bitset(seed: int, missing_rate: float, sample_begin: int, sample_end: int, num_sites: int,
+                 native: bool = False) -> np.ndarray:
+    """Reference-layout bit set of samples [sample_begin, sample_end) of the synthetic cohort, slots 0 .. n-1."""
+    bs = np.empty(words_per_sample(num_sites) * (sample_end - sample_begin), dtype=np.uint64)
+    lib(native).ko_synth_bitset(seed, missing_rate, sample_begin, sample_end, num_sites, bs.ctypes.data)
+    return bs

@@ -1,6 +1,7 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: tile partition, result gather, merge, overflow rule.
-The per-slice evaluation is stood in for by the oracle restricted to the slice's tiles; on a GPU box the same
-functions drive Planes.king(tiles=...) (tests/test_gpu_parity.py::test_tile_slices_union_equals_full)."""
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: band partition, shard scheduling, result gather, merge,
+overflow rule, record checksums.  The per-part evaluation is stood in for by the oracle restricted to the part's
+bands; on a GPU box the same functions drive Planes.king_view(part=...)
+(tests/test_gpu_views.py::test_parts_are_disjoint_and_their_union_is_the_shard)."""
 import os
 import socket
 
@@ -13,28 +14,69 @@ from oracle import king_oracle as ko
 from tests.helpers import random_genotypes, oracle_bitset
 
 
-@pytest.mark.parametrize("n,tri", [(1, True), (5, True), (37, True), (1563, True)])
-def test_tile_coords_enumerates_upper_triangle(n, tri):
-    total = n * (n + 1) // 2
-    probe = range(total) if total < 2000 else list(range(0, total, 997)) + [total - 1]
-    seen = set()
-    for t in probe:
-        bi, bj = ckd.tile_coords(t, n, n, True)
-        assert 0 <= bi <= bj < n
-        assert ckd.tile_of_pair(bi * 64, bj * 64, n, n, True) == t
-        seen.add((bi, bj))
-    assert len(seen) == len(list(probe))
-    assert ckd.tile_coords(0, n, n, True) == (0, 0) and ckd.tile_coords(total - 1, n, n, True) == (n - 1, n - 1)
+def test_band_owner_deals_bands_in_snake_order_and_balances_triangular_work():
+    for parts in (1, 2, 3, 8):
+        owners = [ckd.band_owner(b, parts) for b in range(4 * parts)]
+        assert owners[: 2 * parts] == list(range(parts)) + list(range(parts - 1, -1, -1))
+        assert owners[2 * parts:] == owners[: 2 * parts]
+    # triangular shard: band b holds ~ (num_bands - b) units of work; the parts differ by less than one band's work
+    for bands, parts in [(977, 8), (49, 8), (98, 2), (293, 4)]:
+        load = [0] * parts
+        for b in range(bands):
+            load[ckd.band_owner(b, parts)] += bands - b
+        assert max(load) - min(load) <= bands, (bands, parts, load)
+        assert sum(load) / parts / max(load) > 0.97 or bands < 100
 
 
-def test_tile_slices_partition_the_grid():
-    for tiles in (0, 1, 7, 1222266):
-        for world in (1, 2, 3, 8):
-            cuts = [ckd.tile_slice(tiles, r, world) for r in range(world)]
-            assert cuts[0][0] == 0 and cuts[-1][1] == tiles
-            assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
-            sizes = [e - b for b, e in cuts]
-            assert max(sizes) - min(sizes) <= 1
+def test_record_checksum_is_order_independent_and_sensitive():
+    rng = np.random.default_rng(3)
+    rec = np.zeros(5000, dtype=ckd.RESULT_DTYPE)
+    for f in ("sample_i", "sample_j", "ibs0", "ibs1", "ibs2"):
+        rec[f] = rng.integers(0, 1 << 20, len(rec))
+    rec["kin"] = rng.random(len(rec), dtype=np.float32)
+    whole = ckd.record_checksum(rec, chunk=777)
+    assert whole == ckd.record_checksum(rec[rng.permutation(len(rec))])
+    cut = [0, 100, 100, 3210, 5000]
+    assert ckd.combine_checksums([ckd.record_checksum(rec[a:b]) for a, b in zip(cut, cut[1:])]) == whole
+    for f in ckd.RESULT_DTYPE.names:  # one changed field of one record changes the checksum
+        other = rec.copy()
+        other[f][1234] = other[f][1234] + 1
+        assert ckd.record_checksum(other) != whole
+    swapped = rec.copy()
+    swapped["ibs0"][7], swapped["ibs1"][7] = rec["ibs1"][7], rec["ibs0"][7]
+    assert ckd.record_checksum(swapped) != whole or rec["ibs0"][7] == rec["ibs1"][7]
+    assert ckd.record_checksum(rec[:0]) == (0, 0, 0)
+
+
+def test_work_plan_covers_every_shard_and_balances_the_gpus():
+    import cuking_b200 as ck
+
+    for n, k, gpus in [(300_000, 4, 8), (1_000_000, 1, 8), (100_000, 2, 8), (100_000, 1, 1), (50_000, 1, 8), (5_000, 5, 3)]:
+        items = ck.plan_work(n, k, gpus)
+        seen = {}
+        load = [0.0] * gpus
+        for it in items:
+            assert it.gpu < gpus and it.part_index < it.num_parts
+            seen.setdefault(it.shard_index, set()).add(it.part_index)
+            load[it.gpu] += it.pairs / it.num_parts
+        assert sorted(seen) == list(range(ck.num_shards(k)))
+        for it in items:
+            assert seen[it.shard_index] == set(range(it.num_parts))  # every part of every shard exactly once
+        assert [it.gpu for it in items] == sorted(it.gpu for it in items)  # grouped by GPU, in execution order
+        if n >= 50_000:
+            assert sum(load) / gpus / max(load) > 0.95, (n, k, gpus, load)
+    # BASELINE configs[2]: 300k samples, split_factor 4 -> 10 shards on 8 GPUs: six off-diagonal shards alone, the four
+    # (half-cost) diagonal ones in pairs
+    items = ck.plan_work(300_000, 4, 8)
+    assert len(items) == 10 and all(it.num_parts == 1 for it in items)
+    per_gpu = {}
+    for it in items:
+        per_gpu.setdefault(it.gpu, []).append(it.shard_index)
+    assert sorted(len(v) for v in per_gpu.values()) == [1] * 6 + [2] * 2
+    # a sub-range of the shards (one task per shard, cloud_batch_submit.py:45) and validation
+    assert [it.shard_index for it in ck.plan_work(1000, 3, 1, first_shard=4, num_run=1)] == [4]
+    with pytest.raises(ck.CukingError):
+        ck.plan_work(1000, 3, 1, first_shard=5, num_run=2)
 
 
 def _free_port():
@@ -53,17 +95,14 @@ def _worker(rank, world, port, n, sites, k, shard, thr, cap, out_dir):
         g = random_genotypes(np.random.default_rng(99), n, sites)
         sm = ko.submatrix(n, k, shard)
         full, _, _ = ko.king(oracle_bitset(g, sm), sites, sm, thr, 1 << 20)
-        rows, cols = sm.i_end - sm.i_begin, sm.j_end - sm.j_begin
-        tri = sm.i_begin == sm.j_begin
-        rb, cb = -(-rows // 64), -(-cols // 64)
-        tile = np.array([ckd.tile_of_pair(int(r["sample_i"]) - sm.i_begin, int(r["sample_j"]) - sm.j_begin, rb, cb, tri)
-                         for r in full], dtype=np.int64)
 
-        def evaluate_slice(b, e):  # what Planes.king(tiles=(b, e)) returns on a GPU
-            return full[(tile >= b) & (tile < e)]
+        def evaluate_part(part, parts):  # what Planes.king_view(part=(part, parts)) returns on a GPU
+            band = (full["sample_i"].astype(np.int64) - sm.i_begin) // ckd.BAND_ROWS
+            owner = np.array([ckd.band_owner(int(b), parts) for b in band], dtype=np.int64)
+            return full[owner == part]
 
         try:
-            merged = ckd.king_distributed(evaluate_slice, ckd.num_tiles(rows, cols, tri), cap)
+            merged = ckd.king_distributed(evaluate_part, cap)
             if rank == 0:
                 np.save(os.path.join(out_dir, "merged.npy"), merged)
                 np.save(os.path.join(out_dir, "full.npy"), full)
@@ -79,7 +118,7 @@ def _worker(rank, world, port, n, sites, k, shard, thr, cap, out_dir):
 def test_two_rank_gloo_union_equals_single(tmp_path, k, shard):
     import torch.multiprocessing as mp
 
-    mp.spawn(_worker, args=(2, _free_port(), 300, 400, k, shard, 0.02, 1 << 20, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), 2300, 200, k, shard, 0.02, 1 << 20, str(tmp_path)), nprocs=2, join=True)
     merged, full = np.load(tmp_path / "merged.npy"), np.load(tmp_path / "full.npy")
     assert len(full) > 10
     assert np.array_equal(merged, full)

@@ -358,17 +358,26 @@ def test_allgather_fed_seam_single_rank(ctx):
     host = torch.from_numpy(bs.view(np.int64)).pin_memory()
     created = not dist.is_initialized()
     if created:
-        try:
-            dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
-                                    device_id=torch.device("cuda", 0))
-        except Exception as exc:  # no loopback / port in use: the seam itself is covered by the streaming test above
-            pytest.skip(f"cannot create a one-rank NCCL group here: {exc!r}")
+        # a GPU box that cannot create a one-rank NCCL group is broken for every multi-GPU path: fail, do not skip
+        # (a free port is chosen so that a stale listener cannot be the reason)
+        import socket
+
+        with socket.socket() as sock:
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
     try:
         stream = torch.cuda.Stream()
         with torch.cuda.stream(stream):
             with ck.Context(0, stream=stream.cuda_stream) as c2, c2.planes(ck.submatrix(n), s) as pl:
                 got = king_host_bitset_allgather(pl, host, ck.words_per_sample(s), 0.1, 1 << 20)
                 assert_results_equal(got, want)
+            # a ctx on its own stream: the function binds it to the stream it orders the uploads against
+            with ck.Context(0) as c3, c3.planes(ck.submatrix(n), s) as pl:
+                got = king_host_bitset_allgather(pl, host, ck.words_per_sample(s), 0.1, 1 << 20)
+                assert_results_equal(got, want)
+                assert c3.stream is None  # restored
     finally:
         if created:
             dist.destroy_process_group()

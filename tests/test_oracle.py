@@ -170,3 +170,19 @@ def test_shards_union_equals_full():
     merged = np.concatenate(parts)
     ko.lib().ko_sort(merged.ctypes.data, merged.size)
     assert np.array_equal(merged, full)
+
+
+def test_oracle_synth_cohort_equals_the_product_generator():
+    # bench.py's --impl reference arm builds its inputs with the oracle's own restatement of the synthetic cohort so that
+    # the reference process never loads the product library; the two generators must agree cell by cell
+    import cuking_b200 as ck
+
+    for seed, miss, s0, s1, r0, r1 in [(42, 0.01, 0, 64, 0, 500), (42, 0.05, 13, 150, 1000, 1300), (7, 0.0, 8, 16, 99_990, 100_010),
+                                       (42, 1.0, 3, 5, 0, 40)]:
+        a = ko.synth_genotypes(seed, miss, s0, s1, r0, r1)
+        b = ck.synth_genotypes_host(seed, miss, s0, s1, r0, r1)
+        assert np.array_equal(a, b), (seed, miss, s0, s1, r0, r1)
+    g = ko.synth_genotypes(42, 0.02, 24, 77, 0, 333)
+    bs = ko.synth_bitset(42, 0.02, 24, 77, 333)
+    want, _ = ko.pack_dense(g)
+    assert np.array_equal(bs, want)
