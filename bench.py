@@ -2,22 +2,29 @@
 """bench.py — sample-pair·sites / second of the pairwise KING hot path on B200 (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-  torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, NCCL only for barrier/max-reduce)
+  torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU)
 
 A *step* is one full pass of the hot path over the workload: every i<j sample pair evaluated at every site,
-kinship, threshold, compaction, device sort and copy-out of the retained pairs.  Workload at N = 1 is BASELINE.json
-configs[1]: 100,000 samples x 100,000 sites (synthetic cohort of SURVEY.md §8d, seed 42, 1 % missing, threshold
-0.0884).  For N > 1 the cohort grows to 100,000*sqrt(N) samples so that every GPU keeps the N = 1 amount of work
-(weak scaling); every rank holds all planes and takes a contiguous slice of the tile grid — no data-path collective.
+kinship, threshold, compaction (or dense placement), sort and copy-out of the retained pairs.  The headline workload is
+BASELINE.json configs[1]: 100,000 samples x 100,000 sites (synthetic cohort of SURVEY.md §8d, seed 42, 1 % missing,
+threshold 0.0884).  For N > 1 the cohort grows to 100,000*sqrt(N) samples so that every GPU keeps the N = 1 amount of
+work (weak scaling); every rank holds all planes and evaluates its PART of the shard (bands of 1024 rows dealt in snake
+order, ck_king_view) — no data-path collective.
 
 `value`   : planes already resident in HBM when the timed region starts (device-timed, max over ranks).
 `e2e`     : the same pass through the host-buffer C-ABI call ck_king_host_bitset: the reference-layout bit set starts
             in pinned HOST memory, H2D (overlapped with the kernel, last sample chunk first) + layout transpose + code
-            derivation + kernel + sort + D2H all inside the timed region.
+            derivation + kernel + sort + D2H all inside the timed region.  N > 1: every rank uploads 1/N of every chunk
+            and the chunks are all-gathered over NVLink (cuking_b200.distributed.king_host_bitset_allgather).
 `roofline`: the pairwise kernel against the tensor throughput it is bound by: 10 fp4 ops (5 exact E2M1 MACs) per
-            pair·site against the dense kind::mxf4 rate measured on this pool's B200 (tools/umma_mxf4_probe.cu); the
+            pair·site against the dense kind::mxf4 rate measured live on this GPU (ck_measure_fp4_peak); the
             SURVEY.md §8d view (0.1875 POPC.32 lane-ops per pair·site against the POPC issue rate measured live on
             this GPU) is reported beside it as `popc_equivalent`, and is the roofline of --variant 0/1.
+`checks`  : order-independent record checksums (all six fields): resident leg == e2e leg, and the records of the first
+            2048 samples == a single-GPU evaluation of that block.
+`fixed_configs`: BASELINE.json configs[2..4] on this N: cfg3 (300k samples, split_factor 4: 10 shards LPT-scheduled over
+            the GPUs as views of one resident cohort), cfg4 (1M x 100k, fixed cohort, strong scaling: its ms_per_step is
+            the metric's "wall-time for 1M x 100k"), cfg5 (50k x 1M sites, threshold -1: dense output).
 `cpu_baseline` / --impl reference: the oracle's OpenMP restatement of the reference loop on this box's host cores, on
             a bounded sample of the same workload (the reference has no CPU implementation; kind = "port").
 """
@@ -39,18 +46,22 @@ METRIC = "sample-pair·sites/sec"
 UNIT = "pair·sites/s"
 SEED = 42
 ALGO_POPC_PER_UNIT = 12.0 / 64.0  # reference formulation: 6 __popcll per 64 sites = 12 POPC.32 (cuking.cu:232-239)
+DEFAULT_MAX_RESULTS = 10 << 20    # the reference's default --max_results (cuking.cu:40)
 
 WORKLOADS = {
-    # name: (samples at N=1, sites, missing, threshold)
-    "cfg2": (100_000, 100_000, 0.01, 0.0884),   # BASELINE.json configs[1]
-    "cfg1": (1_000, 10_000, 0.02, 0.05),        # configs[0] (parity-test case; selectable for quick runs)
-    "mid": (20_000, 100_000, 0.01, 0.0884),     # quick smoke of the bench itself
-    "prof": (8_192, 100_000, 0.01, 0.0884),     # short kernel for ncu captures (profiles/)
-    "cfg5": (50_000, 1_000_000, 0.01, -1.0),    # BASELINE.json configs[4]: dense output, every finite-kin pair is emitted
-    "cfg4": (1_000_000, 100_000, 0.05, 0.0442), # BASELINE.json configs[3]: fixed cohort at every N (strong scaling): its
-                                                # ms_per_step is the metric's "wall-time for 1M x 100k"
+    # name: (samples at N=1, sites, missing, threshold, split_factor)
+    "cfg2": (100_000, 100_000, 0.01, 0.0884, 1),   # BASELINE.json configs[1]
+    "cfg1": (1_000, 10_000, 0.02, 0.05, 1),        # configs[0] (parity-test case; selectable for quick runs)
+    "mid": (20_000, 100_000, 0.01, 0.0884, 1),     # quick smoke of the bench itself
+    "prof": (8_192, 100_000, 0.01, 0.0884, 1),     # short kernel for ncu captures (profiles/)
+    "cfg3": (300_000, 100_000, 0.01, 0.05, 4),     # configs[2]: 10 triangular shards across the GPUs
+    "cfg4": (1_000_000, 100_000, 0.05, 0.0442, 1), # configs[3]: fixed cohort at every N (strong scaling)
+    "cfg5": (50_000, 1_000_000, 0.01, -1.0, 1),    # configs[4]: dense output, every finite-kin pair is emitted
+    "cfg3s": (30_000, 20_000, 0.01, 0.05, 4),      # small stand-ins of the three fixed configs (bench self-test)
+    "cfg4s": (40_000, 20_000, 0.05, 0.0442, 1),
+    "cfg5s": (12_000, 100_000, 0.01, -1.0, 1),
 }
-FIXED_SIZE = {"cfg4", "cfg5"}  # BASELINE.json quotes these on a fixed cohort spread over the 8 GPUs
+FIXED_SIZE = {"cfg3", "cfg4", "cfg5", "cfg3s", "cfg4s", "cfg5s"}  # BASELINE.json quotes these on a fixed cohort spread over the GPUs
 
 
 def parse_args():
@@ -66,8 +77,12 @@ def parse_args():
     ap.add_argument("--clock-sample-ms", type=float, default=200.0, help="NVML sampling period during the timed region (0 = off)")
     ap.add_argument("--e2e-mode", choices=["allgather", "host"], default="allgather",
                     help="N > 1 host-buffer leg: planes replicated by NCCL all-gather (default) or N full host uploads")
+    ap.add_argument("--fixed", default="auto",
+                    help="fixed-cohort configs appended as `fixed_configs`: auto (cfg3,cfg4,cfg5 with the cfg2 headline), "
+                         "none, or a comma list of workload names")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-ref-gpu", action="store_true")
+    ap.add_argument("--skip-exchange", action="store_true", help="skip the host-load vs NCCL-broadcast measurement at N > 1")
     return ap.parse_args()
 
 
@@ -77,6 +92,35 @@ def dist_env():
 
 def units(n_samples: int, n_sites: int) -> float:
     return n_samples * (n_samples - 1) / 2.0 * n_sites
+
+
+def workload_samples(name: str, n_gpus: int) -> int:
+    n1 = WORKLOADS[name][0]
+    if n_gpus > 1 and name not in FIXED_SIZE:
+        return int(round(n1 * (n_gpus ** 0.5) / 64.0)) * 64  # weak scaling: pairs ~ N
+    return n1
+
+
+def workload_max_results(name: str, n_gpus: int) -> int:
+    n, thr = workload_samples(name, n_gpus), WORKLOADS[name][3]
+    if thr < 0:  # dense-output stress: room for every pair of one rank's part
+        return int(n * (n - 1) // 2 // max(1, n_gpus) * 1.02) + 4096
+    return DEFAULT_MAX_RESULTS
+
+
+def workload_config(name: str, n_gpus: int) -> dict:
+    """`config` of the JSON line: a function of (workload, N) only, so both arms print the identical object."""
+    n1, s, missing, thr, k = WORKLOADS[name]
+    n = workload_samples(name, n_gpus)
+    words = -(-(-(-s // 32)) // 16) * 16
+    text = f"{name}: {n} samples x {s} sites, missing {missing}, kin_threshold {thr}, max_results {workload_max_results(name, n_gpus)}"
+    if k > 1:
+        text += f", split_factor {k} ({k * (k + 1) // 2} shards)"
+    if n_gpus > 1:
+        text += (f" (fixed cohort spread over {n_gpus} GPUs)" if name in FIXED_SIZE
+                 else f" (weak scaling: {n1}*sqrt({n_gpus}) samples, one part per GPU)")
+    return {"workload": text,
+            "l2": f"inputs larger than L2: {(-(-n // 64) * 64 * words * 16) >> 20} MiB of genotype codes streamed per step"}
 
 
 class ClockSampler(threading.Thread):
@@ -132,32 +176,35 @@ class ClockSampler(threading.Thread):
 # ---- CPU baseline (oracle port, bounded sample) ------------------------------------------------------------------
 
 
-def cpu_sample_bitset(n_sample: int, n_sites: int, missing: float):
-    """Reference-layout bit set of the first n_sample samples of the workload cohort.  Built by the product's GPU
-    generator when a GPU is present (identical data to the timed workload), else by the host generator."""
-    from oracle import king_oracle as ko
-    import cuking_b200 as ck
-
+def host_threads() -> int:
     try:
-        with ck.Context(int(os.environ.get("LOCAL_RANK", "0"))) as ctx, ctx.planes(ck.submatrix(n_sample), n_sites) as pl:
-            pl.synthesize(SEED, missing)
-            return pl.export_bitset()
-    except ck.CukingError:
-        g = ck.synth_genotypes_host(SEED, missing, 0, n_sample, 0, n_sites)
-        bs, _ = ko.pack_dense(g)
-        return bs
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
-def run_cpu_baseline(n_sites: int, missing: float, thr: float, target_s: float, steps: int = 1, warmup: int = 0):
-    """Times the oracle (OpenMP, all host threads) on an r x r off-diagonal rectangle of the workload sized for
-    ~target_s seconds; returns (pair·sites/s, cores, sample description, per-step seconds)."""
+def load_oracle_all_threads():
+    """The oracle's native build with every host thread this process may use.  torchrun exports OMP_NUM_THREADS=1 to its
+    workers; the CPU arm runs on one rank only and is entitled to the whole box."""
+    threads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)  # before libgomp initialises
     from oracle import king_oracle as ko
 
     L = ko.lib(native=True)
+    L.ko_set_num_threads(threads)
+    return ko, L
+
+
+def run_cpu_baseline(n_sites: int, missing: float, thr: float, target_s: float, steps: int = 1, warmup: int = 0):
+    """Times the oracle (OpenMP, all host threads) on an r x r off-diagonal rectangle of the workload cohort sized for
+    ~target_s seconds; the sample's bit set is built by the oracle's own generator (no product code in this path).
+    Returns (pair·sites/s, cores, sample description, per-step seconds)."""
+    ko, L = load_oracle_all_threads()
     cores = int(L.ko_num_threads())
     wps = ko.words_per_sample(n_sites)
     cal = 256
-    bs = cpu_sample_bitset(2 * cal, n_sites, missing)
+    bs = ko.synth_bitset(SEED, missing, 0, 2 * cal, n_sites, native=True)
+    L.ko_bench_rect(bs.ctypes.data, wps, 0, 64, cal, 64, thr)  # thread pool start-up
     t0 = time.perf_counter()
     L.ko_bench_rect(bs.ctypes.data, wps, 0, cal, cal, cal, thr)
     t_cal = max(time.perf_counter() - t0, 1e-4)
@@ -165,7 +212,7 @@ def run_cpu_baseline(n_sites: int, missing: float, thr: float, target_s: float, 
     r = int(min(8192, max(cal, (target_s * rate / n_sites) ** 0.5)))
     r = max(64, (r // 64) * 64)
     if r != cal:
-        bs = cpu_sample_bitset(2 * r, n_sites, missing)
+        bs = ko.synth_bitset(SEED, missing, 0, 2 * r, n_sites, native=True)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -180,18 +227,21 @@ def run_cpu_baseline(n_sites: int, missing: float, thr: float, target_s: float, 
 
 def run_reference_impl(args, rank: int):
     """--impl reference: the reference's path on the host CPU.  The reference has no CPU implementation (it is one
-    CUDA kernel), so this is the oracle's OpenMP port of cuking.cu:216-307 with all host threads."""
+    CUDA kernel), so this is the oracle's OpenMP port of cuking.cu:216-307 with all host threads.  Nothing of the
+    product is imported or loaded here."""
     if rank != 0:
         return
-    n, s, missing, thr = WORKLOADS[args.workload]
+    _, s, missing, thr, _ = WORKLOADS[args.workload]
     per_step = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
     value, cores, sample, times = run_cpu_baseline(s, missing, thr, per_step, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64 popcount + fp32 kinship", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {n} samples x {s} sites, missing {missing}, kin_threshold {thr}",
-                   "note": "CPU port of the reference loop (the reference itself is GPU-only); each step is a bounded sample"},
+        "scaling": "strong" if args.workload in FIXED_SIZE else "weak", "vs_baseline": None,
+        "dtype": "u64 popcount + fp32 kinship", "data": "synthetic",
+        "config": workload_config(args.workload, args.gpus),
+        "note": "CPU port of the reference loop (the reference itself is GPU-only); each step is a bounded sample of the "
+                "workload, extrapolated by units",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -253,241 +303,275 @@ def run_pack_bench(ctx, n_samples: int, missing: float, hbm_peak_gbs):
 # ---- our arm ------------------------------------------------------------------------------------------------------
 
 
-def main():
-    args = parse_args()
-    rank, local_rank, world = dist_env()
-    if args.impl == "reference":
-        run_reference_impl(args, rank)
-        return
+class Bench:
+    """State shared by the headline workload and the fixed-cohort configs of one bench.py process."""
 
-    import torch
-    import cuking_b200 as ck
+    def __init__(self, args):
+        import torch
+        import cuking_b200 as ck
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
-    n_gpus = args.gpus
-    distributed = world > 1
-    if distributed:
-        import torch.distributed as dist
+        self.args, self.torch, self.ck = args, torch, ck
+        self.rank, self.local_rank, self.world = dist_env()
+        self.n_gpus = args.gpus
+        self.distributed = self.world > 1
+        if self.distributed:
+            import torch.distributed as dist
 
-        torch.cuda.set_device(local_rank)
-        # NCCL kernels of the plane replication run beside the pairwise kernel, which fills every SM: give them priority
+            self.dist = dist
+            torch.cuda.set_device(self.local_rank)
+            # NCCL kernels of the plane replication run beside the pairwise kernel, which fills every SM: give them priority
+            try:
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank), pg_options=opts)
+            except (AttributeError, TypeError):  # older torch: default-priority NCCL streams still work, only slower to get SMs
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            assert self.world == self.n_gpus, f"--gpus {self.n_gpus} but WORLD_SIZE={self.world}"
+        elif self.n_gpus != 1:
+            raise SystemExit("for --gpus N > 1 launch with torchrun (one rank per GPU)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        # a dedicated stream: the library launches on it and the timing events are recorded on it
+        self.stream = torch.cuda.Stream(self.dev)
+        torch.cuda.set_stream(self.stream)
+        self.ctx = ck.Context(self.local_rank, stream=self.stream.cuda_stream)
+        if args.variant >= 0:
+            self.ctx.set_king_variant(args.variant)
+        self.fp4_exact, self.fp4_report = self.ctx.fp4_selftest()
+        self.peaks = self.ctx.measure_int_peaks()
+        self.fp4_peak_ops = self.ctx.measure_fp4_peak()
+        self.measured = None
         try:
-            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
-        except (AttributeError, TypeError):  # older torch: default-priority NCCL streams still work, only slower to get SMs
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        assert world == n_gpus, f"--gpus {n_gpus} but WORLD_SIZE={world}"
-    elif n_gpus != 1:
-        raise SystemExit("for --gpus N > 1 launch with torchrun (one rank per GPU)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                self.measured = json.load(f)
+        except OSError:
+            pass
+        self.side = torch.cuda.Stream(self.dev, priority=-1) if self.distributed else None
+        self.ev0, self.ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    n1, n_sites, missing, thr = WORKLOADS[args.workload]
-    fixed = args.workload in FIXED_SIZE
-    n_samples = int(round(n1 * (n_gpus ** 0.5) / 64.0)) * 64 if (n_gpus > 1 and not fixed) else n1  # weak scaling: pairs ~ N
-    max_results = 10 << 20  # the reference's default --max_results (cuking.cu:40)
-    if thr < 0:  # dense-output stress: room for every pair of this rank's slice
-        max_results = int(n_samples * (n_samples - 1) // 2 // max(1, n_gpus) * 1.02) + 1024
+    # -- helpers -----------------------------------------------------------------------------------------------------
+    def barrier(self):
+        if self.distributed:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
 
-    # a dedicated stream: the library launches on it and the timing events are recorded on it
-    stream = torch.cuda.Stream(dev)
-    torch.cuda.set_stream(stream)
-    ctx = ck.Context(local_rank, stream=stream.cuda_stream)
-    if args.variant >= 0:
-        ctx.set_king_variant(args.variant)
-    peaks = ctx.measure_int_peaks()
+    def max_over_ranks(self, x: float) -> float:
+        if not self.distributed:
+            return x
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- inputs resident in HBM (outside the timed region) ----
-    sm = ck.submatrix(n_samples)
-    planes = ctx.planes(sm, n_sites)
-    t0 = time.perf_counter()
-    planes.synthesize(SEED, missing)
-    planes.finalize()
-    synth_s = time.perf_counter() - t0
-    tiles = planes.num_tiles()
-    t_begin, t_end = tiles * rank // world, tiles * (rank + 1) // world
-    results = np.empty(max_results, dtype=ck.RESULT_DTYPE)
+    def sum_over_ranks(self, x: float) -> float:
+        if not self.distributed:
+            return x
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
 
-    def barrier():
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    def pinned_results(self, records: int):
+        """Page-locked result buffer (the dense path copies finished rows out while later ones are computed)."""
+        from cuking_b200.capi import RESULT_DTYPE
 
-    def step():
-        return planes.king(thr, max_results, sort=True, tiles=(t_begin, t_end), out=results)
+        buf = self.torch.empty(records * RESULT_DTYPE.itemsize, dtype=self.torch.uint8).pin_memory()
+        return buf, buf.numpy().view(RESULT_DTYPE)
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank, args.clock_sample_ms / 1e3)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    king_ms, launches, retained = [], 0, 0
-    ev0.record(stream)
-    for _ in range(args.steps):
-        res = step()
-        t = ctx.timings()
-        king_ms.append(t["king_ms"])
-        launches += int(t["king_launches"])
-        retained = len(res)
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    if distributed:
-        tmax = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tmax.item())
-        tot = torch.tensor([float(retained)], device=dev, dtype=torch.float64)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        retained = int(tot.item())
-    total_units = units(n_samples, n_sites)
-    ms_per_step = elapsed_ms / args.steps
-    value = total_units / (ms_per_step * 1e-3)
+    def my_items(self, name: str, n_samples: int):
+        """(view, part_index, num_parts, pairs) this rank evaluates per step.  One shard: this rank's part.  A split
+        (cfg3): the shards ck_plan_work assigns to this rank's GPU, as views of the resident cohort."""
+        ck, k = self.ck, WORKLOADS[name][4]
+        if k == 1:
+            return [(None, self.rank, self.world, n_samples * (n_samples - 1) // 2)]
+        return [(ck.submatrix(n_samples, k, it.shard_index), it.part_index, it.num_parts, it.pairs)
+                for it in ck.plan_work(n_samples, k, self.world) if it.gpu == self.rank]
 
-    # ---- roofline of the dominant kernel (this rank's slice, device events around the launch on its stream) ----
-    my_units = total_units * (t_end - t_begin) / max(1, tiles)
-    kernel_ms = float(np.mean(king_ms))
-    achieved = my_units * ALGO_POPC_PER_UNIT / (kernel_ms * 1e-3)
-    hbm_peak = None
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            hbm_peak = json.load(f).get("hbm_gbs")
-    except OSError:
-        pass
-    # algorithmic HBM bytes per launch: each tile streams its row samples and its column samples once
-    # (tcgen05 variant: 128 x 80 tiles of 4-bit genotype codes; LOP3+POPC variants: 64 x 64 tiles of 3 bit planes)
-    words = -(-(-(-n_sites // 32)) // 16) * 16
-    variant = args.variant if args.variant >= 0 else (3 if n_sites <= (1 << 23) else 2)  # the library's own choice
-    umma = variant in (2, 3)
-    tile_bytes = (128 + 80) * words * 16 if umma else 2 * 64 * words * 12
-    popc_view = {
-        "achieved": achieved / 1e9, "peak": peaks["popc_lane_ops_per_s"] / 1e9, "unit": "G POPC.32 lane-ops/s",
-        "frac": achieved / peaks["popc_lane_ops_per_s"],
-        "algorithmic_per_unit": "0.1875 POPC.32 lane-ops per pair-site (reference formulation: 6 popcounts per site-bit, cuking.cu:232-239)",
-        "peak_source": "POPC.32 issue rate measured live on this GPU by ck_measure_int_peaks (16 lanes/clk/SM)",
-        "lop3_peak": peaks["lop3_lane_ops_per_s"] / 1e9,
-    }
-    hbm_view = {"algorithmic_gbs": (t_end - t_begin) * tile_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                "note": "tile operand streaming (each tile reads its row and column samples once); mostly L2 hits"}
-    bf16 = None
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            bf16 = json.load(f)
-    except OSError:
-        pass
-    # DRAM bytes of one king_fp4_kernel launch on the single-GPU cfg2 shape: dram__bytes_read.sum + dram__bytes_write.sum
-    # of the ncu --set full capture in profiles/r01_king_fp4_cfg2_ncu.txt (425.06 GB + 0.16 GB; 7 % of the DRAM peak - the
-    # codes are re-read from L2, hit rate 77 %; compulsory traffic is 5 GB).  Other shapes were not captured: null.
-    fp4_traffic = 425.21e9 if (args.workload == "cfg2" and n_gpus == 1) else None
-    if variant == 3:
-        # 5 exact E2M1 MACs = 10 ops per pair-site (xx, yy, yh, hy, hh) on the FP4 tensor path (kind::mxf4, unit block
-        # scales, fp32 accumulation).  Peak = the dense FP4 rate measured on this pool's B200 by tools/umma_mxf4_probe.cu
-        # (15,595 MAC/clk/SM, 8481 TOP/s at the burst clock; nominal 9000) - MEASURED_PEAKS.json only holds bf16
-        # (FP4 is nominally 4x bf16: 4 x 1657 burst = 6626, 4 x 1390 sustained = 5562 TOP/s).
-        tops = my_units * 10.0 / (kernel_ms * 1e-3) / 1e12
-        roofline = {
-            "bound": "tensor", "kernel": "king_fp4_kernel", "achieved": tops, "peak": 8481.0, "unit": "TOP/s (fp4 e2m1, dense)",
-            "frac": tops / 8481.0, "traffic": fp4_traffic, "kernel_ms": kernel_ms, "units_per_launch": my_units,
-            "algorithmic_per_unit": "10 fp4 ops (5 MACs: xx, yy, yh, hy, hh) per pair-site, fp32 accumulation (exact: counts <= 2^23)",
-            "peak_source": "measured: tools/umma_mxf4_probe.cu on this pool's B200 (profiles/r01_mxf4_probe.txt), "
-                           "kind::mxf4 M=128 N=208, 15595 MAC/clk/SM = 8481 TOP/s at the burst clock (nominal dense fp4: 9000)",
-            "vs_4x_measured_bf16_burst": (tops / (4 * bf16["bf16_tflops"])) if bf16 else None,
-            "vs_4x_measured_bf16_sustained": (tops / (4 * bf16["bf16_tflops_sustained"])) if bf16 else None,
-            "int8_equivalent": {"peak": 4075.0, "frac": tops / 4075.0,
-                                "note": "the same 10 ops per pair-site against the measured int8 tensor peak (the round's first tensor kernel, variant 2)"},
-            "popc_equivalent": popc_view, "hbm": hbm_view,
+    # -- one workload ------------------------------------------------------------------------------------------------
+    def run_workload(self, name: str, steps: int, warmup: int, e2e_steps: int, partial_warmup: bool = False) -> dict:
+        torch, ck, ctx, args = self.torch, self.ck, self.ctx, self.args
+        _, n_sites, missing, thr, k = WORKLOADS[name]
+        n_samples = workload_samples(name, self.n_gpus)
+        max_results = workload_max_results(name, self.n_gpus)
+        sm = ck.submatrix(n_samples)
+        planes = ctx.planes(sm, n_sites)
+        t0 = time.perf_counter()
+        planes.synthesize(SEED, missing)
+        planes.finalize()
+        synth_s = time.perf_counter() - t0
+        variant = planes.king_variant()
+        items = self.my_items(name, n_samples)
+        pinned, results = self.pinned_results(max_results)
+
+        def step(parts_scale: int = 1):
+            out = []
+            for view, part, parts, _ in items:
+                if parts_scale > 1:  # warm-up of a very long pass: the same kernel on 1/parts_scale of this rank's bands
+                    part, parts = part * parts_scale, parts * parts_scale
+                out.append(planes.king_view(view, thr, max_results, part=(part, parts), out=results))
+            return out
+
+        scale = 16 if partial_warmup else 1
+        for _ in range(warmup):
+            step(scale)
+        self.barrier()
+        sampler = ClockSampler(self.local_rank, args.clock_sample_ms / 1e3)
+        sampler.start()
+        king_ms, launches, d2h_tail_ms, last = [], 0, [], []
+        self.ev0.record(self.stream)
+        for _ in range(steps):
+            t_k, t_d, last = 0.0, 0.0, []
+            for view, part, parts, _ in items:
+                res = planes.king_view(view, thr, max_results, part=(part, parts), out=results)
+                # several items share the result buffer: keep a copy of the (sparse, small) records of all but a lone item
+                last.append(res if len(items) == 1 else res.copy())
+                t = ctx.timings()
+                t_k += t["king_ms"]
+                t_d += t["sort_ms"] + t["d2h_ms"]
+                launches += int(t["king_launches"])
+            king_ms.append(t_k)
+            d2h_tail_ms.append(t_d)
+        self.ev1.record(self.stream)
+        self.barrier()
+        clocks = sampler.stop()
+        elapsed_ms = self.max_over_ranks(self.ev0.elapsed_time(self.ev1))
+        # checksum of the last timed pass's records (outside the timed region)
+        retained, check_parts, block_parts = 0, [], []
+        from cuking_b200.distributed import record_checksum, combine_checksums
+
+        check_block = min(2048, n_samples)
+        for res in last:
+            retained += len(res)
+            check_parts.append(record_checksum(res))
+            block_parts.append(record_checksum(res[res["sample_j"] < check_block]))
+        del last
+        retained = int(self.sum_over_ranks(float(retained)))
+        my_check = combine_checksums(check_parts)
+        checksum = self._gather_checksum(my_check)
+        block_checksum = self._gather_checksum(combine_checksums(block_parts))
+        total_units = units(n_samples, n_sites)
+        ms_per_step = elapsed_ms / steps
+        value = total_units / (ms_per_step * 1e-3)
+        my_units = float(sum(p // parts for _, _, parts, p in items)) * n_sites
+        kernel_ms = max(float(np.mean(king_ms)), 1e-6)
+
+        # single-GPU evaluation of the first block of samples, on rank 0, against the same records of the distributed pass
+        checks = {"resident_checksum": "%d:%016x:%016x" % checksum}
+        if self.rank == 0:
+            blk = planes.king_view(ck.submatrix(check_block), thr, max_results, out=results)
+            single = record_checksum(blk)
+            checks["first_block"] = {"samples": check_block, "single_gpu": "%d:%016x:%016x" % single,
+                                     "distributed": "%d:%016x:%016x" % block_checksum, "equal": single == block_checksum}
+            if single != block_checksum:
+                raise SystemExit(f"{name}: records of the first {check_block} samples differ between the {self.world}-rank pass "
+                                 f"({block_checksum}) and a single-GPU evaluation ({single})")
+
+        # ---- e2e: host buffers through the reference-facing C-ABI call ----
+        e2e, exchange = None, None
+        if e2e_steps > 0:
+            e2e, exchange = self.run_e2e(name, planes, sm, n_samples, n_sites, thr, max_results, k, items, results, total_units,
+                                         e2e_steps, checksum, checks)
+        out = {
+            "name": name, "n_samples": n_samples, "n_sites": n_sites, "steps": steps, "warmup": warmup,
+            "warmup_note": ("each warm-up step runs the same kernels over 1/16 of this rank's bands (a full pass of the largest "
+                            "config takes over a minute at N = 1); allocations, tile tables and clocks are warm when the timed "
+                            "passes start") if partial_warmup else None,
+            "ms_per_step": ms_per_step, "value": value, "kernel_ms": kernel_ms, "sort_d2h_ms": float(np.mean(d2h_tail_ms)),
+            "retained_pairs": retained, "gpu_launches": launches, "kernel_variant": variant, "my_units": my_units,
+            "total_units": total_units, "clocks": clocks, "e2e": e2e, "exchange": exchange, "checks": checks,
+            "input_synthesis_s": round(synth_s, 3), "items_this_rank": len(items), "max_results": max_results,
+            "config": workload_config(name, self.n_gpus),
         }
-    elif umma:
-        # 5 exact int8 MACs = 10 ops per pair-site (xx, yy, yh, hy, hh); peak = dense int8 tcgen05 rate measured on this
-        # pool's B200 by tools/umma_i8_probe.cu (8190 MAC/clk/SM, 4075 TOP/s burst at N=256) - MEASURED_PEAKS.json only
-        # holds bf16 (int8 is nominally 2x bf16: 2 x 1390 sustained = 2781, 2 x 1657 burst = 3313 TOP/s)
-        tops = my_units * 10.0 / (kernel_ms * 1e-3) / 1e12
-        roofline = {
-            "bound": "tensor", "kernel": "king_umma_kernel", "achieved": tops, "peak": 4075.0, "unit": "TOP/s (int8, dense)",
-            "frac": tops / 4075.0, "traffic": None, "kernel_ms": kernel_ms, "units_per_launch": my_units,
-            "algorithmic_per_unit": "10 int8 ops (5 MACs: xx, yy, yh, hy, hh) per pair-site, s32 accumulation",
-            "peak_source": "measured: tools/umma_i8_probe.cu on this pool's B200 (profiles/r01_umma_probe.txt), "
-                           "kind::i8 M=128 N=256, 8190 MAC/clk/SM = 4075 TOP/s at the burst clock",
-            "vs_2x_measured_bf16_sustained": (tops / (2 * bf16["bf16_tflops_sustained"])) if bf16 else None,
-            "popc_equivalent": popc_view, "hbm": hbm_view,
-        }
-    else:
-        roofline = dict(popc_view, bound="popc", kernel="king_tile_kernel", traffic=None, kernel_ms=kernel_ms,
-                        units_per_launch=my_units, hbm=hbm_view)
+        planes.close()
+        del results, pinned
+        return out
 
-    # ---- e2e: host buffers through the reference-facing C-ABI call (rank-local slice is the whole shard at N=1) ----
-    e2e, exchange = None, None
-    e2e_steps = args.steps if args.e2e_steps < 0 else args.e2e_steps
-    if e2e_steps > 0:
+    def _gather_checksum(self, mine):
+        from cuking_b200.distributed import combine_checksums
+
+        if not self.distributed:
+            return mine
+        torch = self.torch
+        as_i64 = [v - (1 << 64) if v >= (1 << 63) else v for v in mine]
+        t = torch.tensor(as_i64, device=self.dev, dtype=torch.int64)
+        allt = torch.empty(self.world * 3, device=self.dev, dtype=torch.int64)
+        self.dist.all_gather_into_tensor(allt, t)
+        vals = [int(v) & 0xFFFFFFFFFFFFFFFF for v in allt.cpu().tolist()]
+        return combine_checksums([tuple(vals[3 * r: 3 * r + 3]) for r in range(self.world)])
+
+    def run_e2e(self, name, planes, sm, n_samples, n_sites, thr, max_results, k, items, results, total_units, e2e_steps,
+                resident_checksum, checks):
+        torch, ck, ctx, args = self.torch, self.ck, self.ctx, self.args
+        from cuking_b200.distributed import record_checksum, combine_checksums
+
         bits_np = planes.export_bitset()  # reference layout (cuking.cu:507-523), built once outside the timed region
         host_bits = torch.from_numpy(bits_np).pin_memory()
         del bits_np
         h2d = host_bits.numel() * 8
-        # N = 1: ck_king_host_bitset (upload overlapped with the kernel).  N > 1: the same schedule with the planes
-        # replicated over NVLink (every rank uploads 1/N of each chunk through its own PCIe link, NCCL all-gather,
-        # ck_king_stream_rows) - or, with --e2e-mode host, N independent full uploads through ck_king_host_bitset_part.
-        allgather = world > 1 and args.e2e_mode == "allgather"
-        if allgather:
-            from cuking_b200.distributed import king_host_bitset_allgather
-            side = torch.cuda.Stream(dev, priority=-1)
+        allgather = self.world > 1 and args.e2e_mode == "allgather" and k == 1
+        if k > 1:
+            # split_factor run: the cohort's bit set is uploaded and transposed once per step, then this rank's shards are
+            # evaluated as views (the reference uploads one bit set per shard process)
+            api = "ck_planes_import_bitset (whole cohort) + ck_king_view per shard"
 
             def e2e_step():
                 with ctx.planes(sm, n_sites) as pl:
-                    return king_host_bitset_allgather(pl, host_bits, ck.words_per_sample(n_sites), thr, max_results,
-                                                      out=results, side_stream=side)
-        else:
+                    pl.import_bitset(host_bits)
+                    return [pl.king_view(view, thr, max_results, part=(part, parts), out=results).copy()
+                            for view, part, parts, _ in items]
+        elif allgather:
+            from cuking_b200.distributed import king_host_bitset_allgather
+
+            api = (f"ck_king_stream_* fed by 1/{self.world} uploads + NCCL all-gather "
+                   "(cuking_b200.distributed.king_host_bitset_allgather)")
+
             def e2e_step():
-                return ctx.king_host_bitset(n_samples, 1, 0, n_sites, host_bits, thr, max_results, out=results, part=(rank, world))
+                with ctx.planes(sm, n_sites) as pl:
+                    return [king_host_bitset_allgather(pl, host_bits, ck.words_per_sample(n_sites), thr, max_results,
+                                                       out=results, side_stream=self.side)]
+        else:
+            api = "ck_king_host_bitset" if self.world == 1 else f"ck_king_host_bitset_part (part r of {self.world} on GPU r)"
+
+            def e2e_step():
+                return [ctx.king_host_bitset(n_samples, 1, 0, n_sites, host_bits, thr, max_results, out=results,
+                                             part=(self.rank, self.world))]
         e2e_step()  # warm-up (allocations)
-        barrier()
-        ev0.record(stream)
+        self.barrier()
+        self.ev0.record(self.stream)
         for _ in range(e2e_steps):
             r = e2e_step()
-        ev1.record(stream)
-        barrier()
-        e_ms = ev0.elapsed_time(ev1)
-        e2e_retained = len(r)
-        if distributed:
-            tmax = torch.tensor([e_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            e_ms = float(tmax.item())
-            tot = torch.tensor([float(e2e_retained)], device=dev, dtype=torch.float64)
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-            e2e_retained = int(tot.item())
-        if e2e_retained != retained:  # the host-buffer leg must keep exactly the pairs the resident leg kept
-            raise SystemExit(f"e2e leg retained {e2e_retained} pairs, resident leg {retained}")
+        self.ev1.record(self.stream)
+        self.barrier()
+        e_ms = self.max_over_ranks(self.ev0.elapsed_time(self.ev1))
+        d2h = sum(len(x) for x in r) * 24 + 8
+        e2e_checksum = self._gather_checksum(combine_checksums([record_checksum(x) for x in r]))
+        checks["e2e_checksum"] = "%d:%016x:%016x" % e2e_checksum
+        checks["e2e_equals_resident"] = e2e_checksum == resident_checksum
+        if e2e_checksum != resident_checksum:  # the host-buffer leg must produce exactly the records of the resident leg
+            raise SystemExit(f"{name}: e2e leg checksum {e2e_checksum} differs from the resident leg's {resident_checksum}")
         e2e = {"value": total_units / (e_ms / e2e_steps * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d // world) if allgather else int(h2d),  # per rank
-               "d2h_bytes_per_step": int(len(r) * 24 + 8), "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps,
-               "api": ("ck_king_host_bitset" if world == 1 else
-                       f"ck_king_stream_* fed by 1/{world} uploads + NCCL all-gather (cuking_b200.distributed.king_host_bitset_allgather)"
-                       if allgather else f"ck_king_host_bitset_part (part r of {world} on GPU r)")
-                      + " (pinned host bit set in the reference layout -> sorted KingResult[] on the host)"}
+               "h2d_bytes_per_step": int(h2d // self.world) if allgather else int(h2d),  # per rank
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps,
+               "api": api + " (pinned host bit set in the reference layout -> sorted KingResult[] in pinned host memory)"}
+        exchange = None
         # north_star: replicate the planes with an NCCL broadcast over NVLink "only if it beats per-GPU host loading".
         # Measured here on the e2e call's own bytes: (a) every rank copies the whole pinned bit set to its GPU at the
         # same time (what ck_king_host_bitset_part does, hidden behind its kernel), (b) rank 0 alone copies it,
         # (c) rank 0 broadcasts the device copy to the other GPUs.  Device-timed, max over ranks.
-        if distributed:
+        if self.distributed and not args.skip_exchange and name == args.workload:
             hb = host_bits.view(torch.int64)
-            dbuf = torch.empty_like(hb, device=dev)
+            dbuf = torch.empty_like(hb, device=self.dev)
 
             def timed(fn, reps=2):
                 fn()  # warm-up (NCCL channel setup, page-locking checks)
-                barrier()
-                ev0.record(stream)
+                self.barrier()
+                self.ev0.record(self.stream)
                 for _ in range(reps):
                     fn()
-                ev1.record(stream)
-                barrier()
-                t = torch.tensor([ev0.elapsed_time(ev1) / reps], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                return float(t.item())
+                self.ev1.record(self.stream)
+                self.barrier()
+                return self.max_over_ranks(self.ev0.elapsed_time(self.ev1) / reps)
 
             all_ms = timed(lambda: dbuf.copy_(hb, non_blocking=True))
-            one_ms = timed(lambda: dbuf.copy_(hb, non_blocking=True) if rank == 0 else None)
-            bcast_ms = timed(lambda: dist.broadcast(dbuf, src=0))
+            one_ms = timed(lambda: dbuf.copy_(hb, non_blocking=True) if self.rank == 0 else None)
+            bcast_ms = timed(lambda: self.dist.broadcast(dbuf, src=0))
             gb = h2d / 1e9
             exchange = {
                 "bytes": int(h2d), "per_gpu_host_load_ms": all_ms, "per_gpu_host_load_gbs_each": gb / (all_ms * 1e-3),
@@ -499,16 +583,126 @@ def main():
             }
             del dbuf, hb
         del host_bits
+        return e2e, exchange
+
+    # -- roofline of the dominant kernel -----------------------------------------------------------------------------
+    def roofline(self, w: dict) -> dict:
+        n_sites, n_samples = w["n_sites"], w["n_samples"]
+        my_units, kernel_ms, variant = w["my_units"], w["kernel_ms"], w["kernel_variant"]
+        peaks, measured = self.peaks, self.measured
+        hbm_peak = measured.get("hbm_gbs") if measured else None
+        words = -(-(-(-n_sites // 32)) // 16) * 16
+        achieved_popc = my_units * ALGO_POPC_PER_UNIT / (kernel_ms * 1e-3)
+        popc_view = {
+            "achieved": achieved_popc / 1e9, "peak": peaks["popc_lane_ops_per_s"] / 1e9, "unit": "G POPC.32 lane-ops/s",
+            "frac": achieved_popc / peaks["popc_lane_ops_per_s"],
+            "algorithmic_per_unit": "0.1875 POPC.32 lane-ops per pair-site (reference formulation: 6 popcounts per site-bit, cuking.cu:232-239)",
+            "peak_source": "POPC.32 issue rate measured live on this GPU by ck_measure_int_peaks (16 lanes/clk/SM)",
+            "lop3_peak": peaks["lop3_lane_ops_per_s"] / 1e9,
+        }
+        umma = variant in (2, 3)
+        # operand streaming: each 128 x 80 tile reads the genotype codes of its 208 samples once - from L2 mostly; the
+        # compulsory HBM traffic is every sample's codes once per pass
+        pairs = my_units / n_sites
+        tile_bytes = (128 + 80) * words * 16 if umma else 2 * 64 * words * 12
+        tiles = pairs / (128 * 80 if umma else 64 * 64)
+        mem_view = {"l2_to_sm_gbs": tiles * tile_bytes / (kernel_ms * 1e-3) / 1e9,
+                    "compulsory_hbm_bytes": int(-(-n_samples // 64) * 64 * words * (16 if umma else 12)),
+                    "compulsory_hbm_gbs": -(-n_samples // 64) * 64 * words * (16 if umma else 12) / (kernel_ms * 1e-3) / 1e9,
+                    "hbm_peak_gbs": hbm_peak,
+                    "note": "tile operand streaming (each tile reads its row and column samples once) is served by L2; "
+                            "HBM only has to deliver every sample's codes once per pass"}
+        # DRAM bytes of one king_fp4_kernel launch on the single-GPU cfg2 shape, from the committed ncu --set full capture
+        traffic = None
+        traffic_from = None
+        if variant == 3 and w["name"] == "cfg2" and self.n_gpus == 1:
+            traffic, traffic_from = 425.21e9, ("profiles/r01_king_fp4_cfg2_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                               "ncu --set full capture of this launch shape; not re-measured by this run)")
+        if variant == 3:
+            tops = my_units * 10.0 / (kernel_ms * 1e-3) / 1e12
+            peak = self.fp4_peak_ops / 1e12
+            return {
+                "bound": "tensor", "kernel": "king_fp4_kernel", "achieved": tops, "peak": peak, "unit": "TOP/s (fp4 e2m1, dense)",
+                "frac": tops / peak, "traffic": traffic, "traffic_from": traffic_from, "kernel_ms": kernel_ms, "units_per_launch": my_units,
+                "algorithmic_per_unit": "10 fp4 ops (5 MACs: xx, yy, yh, hy, hh) per pair-site, fp32 accumulation (exact: counts <= 2^23)",
+                "peak_source": "measured live on this GPU by ck_measure_fp4_peak: tcgen05.mma kind::mxf4 M=128 N=208 K=64 streamed from "
+                               "resident operands on every SM (MEASURED_PEAKS.json holds no fp4 figure; nominal dense fp4: 9000; "
+                               "tools/umma_mxf4_probe.cu measured 8481 in round 1)",
+                "vs_nominal_dense_fp4": tops / 9000.0,
+                "vs_4x_measured_bf16_burst": (tops / (4 * measured["bf16_tflops"])) if measured else None,
+                "vs_4x_measured_bf16_sustained": (tops / (4 * measured["bf16_tflops_sustained"])) if measured else None,
+                "fp4_accumulation_selftest": self.fp4_report,
+                "popc_equivalent": popc_view, "memory": mem_view,
+            }
+        if umma:
+            tops = my_units * 10.0 / (kernel_ms * 1e-3) / 1e12
+            return {
+                "bound": "tensor", "kernel": "king_umma_kernel", "achieved": tops, "peak": 4075.0, "unit": "TOP/s (int8, dense)",
+                "frac": tops / 4075.0, "traffic": None, "kernel_ms": kernel_ms, "units_per_launch": my_units,
+                "algorithmic_per_unit": "10 int8 ops (5 MACs: xx, yy, yh, hy, hh) per pair-site, s32 accumulation",
+                "peak_source": "measured: tools/umma_i8_probe.cu on this pool's B200 (profiles/r01_umma_probe.txt), "
+                               "kind::i8 M=128 N=256, 8190 MAC/clk/SM = 4075 TOP/s at the burst clock",
+                "vs_2x_measured_bf16_sustained": (tops / (2 * measured["bf16_tflops_sustained"])) if measured else None,
+                "popc_equivalent": popc_view, "memory": mem_view,
+            }
+        return dict(popc_view, bound="popc", kernel="king_tile_kernel", traffic=None, kernel_ms=kernel_ms,
+                    units_per_launch=my_units, memory=mem_view)
+
+
+def main():
+    args = parse_args()
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        run_reference_impl(args, rank)
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
+    b = Bench(args)
+    name = args.workload
+    fixed = name in FIXED_SIZE
+    e2e_steps = args.steps if args.e2e_steps < 0 else args.e2e_steps
+    long_pass = name == "cfg4" and b.n_gpus <= 2
+    head = b.run_workload(name, args.steps, args.warmup, e2e_steps, partial_warmup=long_pass)
+    roofline = b.roofline(head)
+
+    # ---- fixed-cohort configs of BASELINE.json on this N ----
+    fixed_names = []
+    if args.fixed == "auto":
+        fixed_names = ["cfg3", "cfg4", "cfg5"] if name == "cfg2" else []
+    elif args.fixed != "none":
+        fixed_names = [x for x in args.fixed.split(",") if x]
+    fixed_configs = {}
+    for fx in fixed_names:
+        n_fx = WORKLOADS[fx][0]
+        # a pass of cfg4 takes over a minute on one GPU: one timed pass, warm-up on 1/16 of the bands
+        slow = units(n_fx, WORKLOADS[fx][1]) / max(1, b.n_gpus) > 1.5e16
+        steps_fx, warm_fx = (1, 3) if slow else (2, 3)
+        w = b.run_workload(fx, steps_fx, warm_fx, e2e_steps=(0 if fx.startswith("cfg4") else 1), partial_warmup=True)
+        r = b.roofline(w)
+        fixed_configs[fx] = {
+            "config": w["config"], "scaling": "strong", "n_gpus": b.n_gpus, "steps": w["steps"], "warmup": w["warmup"],
+            "warmup_note": w["warmup_note"], "ms_per_step": w["ms_per_step"], "value": w["value"], "unit": UNIT,
+            "kernel_ms": w["kernel_ms"], "sort_d2h_ms_exposed": w["sort_d2h_ms"], "ms_per_step_over_kernel_ms": w["ms_per_step"] / w["kernel_ms"],
+            "retained_pairs": w["retained_pairs"], "gpu_launches": w["gpu_launches"], "items_on_rank0": w["items_this_rank"],
+            "roofline_frac": r["frac"], "roofline_achieved": r["achieved"], "roofline_peak": r["peak"], "e2e": w["e2e"],
+            "e2e_note": None if w["e2e"] else "resident inputs only: a pinned host copy of the 25 GB bit set per rank is not staged by the bench",
+            "checks": w["checks"], "clocks": w["clocks"], "input_synthesis_s": w["input_synthesis_s"],
+        }
 
     cpu_baseline, ref_gpu, pack = None, None, None
-    if rank == 0 and n_gpus == 1:
+    if rank == 0 and b.n_gpus == 1:
+        _, n_sites, missing, thr, _ = WORKLOADS[name]
+        hbm_peak = b.measured.get("hbm_gbs") if b.measured else None
         try:
-            pack = run_pack_bench(ctx, n_samples, missing, hbm_peak)
+            pack = run_pack_bench(b.ctx, head["n_samples"], missing, hbm_peak)
         except Exception as exc:
             pack = {"error": repr(exc)}
         if not args.skip_ref_gpu:
             try:
-                ref_gpu = run_reference_gpu_kernel(ctx, n_sites, missing, thr)
+                ref_gpu = run_reference_gpu_kernel(b.ctx, n_sites, missing, thr)
             except Exception as exc:  # the baseline must never take the bench down
                 ref_gpu = {"error": repr(exc)}
         if not args.skip_cpu:
@@ -516,29 +710,24 @@ def main():
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
+        variant = head["kernel_variant"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if fixed else "weak", "vs_baseline": None,
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": b.n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong" if fixed else "weak", "vs_baseline": None,
             "dtype": {3: "fp4 (e2m1 indicators, exact fp32 accumulation)", 2: "int8 (indicators, s32 accumulation)"}.get(variant, "u32 (bit planes, LOP3+POPC)"),
             "data": "synthetic",
-            "config": {
-                "workload": f"{args.workload}: {n_samples} samples x {n_sites} sites, missing {missing}, "
-                            f"kin_threshold {thr}, max_results {max_results}"
-                            + ((f" (fixed cohort, tile grid split over {n_gpus} GPUs)" if fixed else
-                                f" (weak scaling: {n1}*sqrt({n_gpus}) samples, tile grid split over {n_gpus} GPUs)") if n_gpus > 1 else ""),
-                "tiles": tiles, "retained_pairs": retained, "kernel_variant": variant,
-                "l2": (f"inputs larger than L2: {(-(-n_samples // 64) * 64 * words * 16) >> 20} MiB of genotype codes streamed per step" if umma else
-                       f"inputs larger than L2: {(-(-n_samples // 64) * 64 * words * 12) >> 20} MiB of compute planes streamed per step"),
-                "input_synthesis_s": round(synth_s, 3),
-            },
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "reference_gpu_kernel": ref_gpu, "pack": pack, "plane_exchange": exchange,
+            "config": head["config"],
+            "run": {"retained_pairs": head["retained_pairs"], "kernel_variant": variant, "input_synthesis_s": head["input_synthesis_s"],
+                    "work_items_on_rank0": head["items_this_rank"], "sort_d2h_ms_exposed": head["sort_d2h_ms"],
+                    "warmup_note": head["warmup_note"]},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "clocks": head["clocks"], "checks": head["checks"], "fixed_configs": fixed_configs or None,
+            "reference_gpu_kernel": ref_gpu, "pack": pack, "plane_exchange": head["exchange"],
         }
         print(json.dumps(line), flush=True)
-    planes.close()
-    ctx.close()
-    if distributed:
-        dist.destroy_process_group()
+    b.ctx.close()
+    if b.distributed:
+        b.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -7,6 +7,8 @@
 #include <cstdint>
 
 #include "internal.cuh"
+#include "king_common.cuh"
+#include "umma_common.cuh"
 
 namespace ck {
 namespace {
@@ -54,8 +56,91 @@ cudaError_t measure(ck_ctx *ctx, uint32_t *d_out, double *lane_ops_per_s) {
   return cudaGetLastError();
 }
 
+// ---- dense kind::mxf4 tensor rate: the denominator of the mxf4 pairwise kernel's roofline ------------------------------
+// Two issuer lanes per CTA, each streaming tcgen05.mma.kind::mxf4 (M = 128, N = 208, K = 64, A from TMEM, B from shared
+// memory, unit block scales) into its own accumulator, one CTA per SM, operands resident - nothing but the tensor pipe
+// can limit it.  This is the best configuration tools/umma_mxf4_probe.cu found on B200 (profiles/r01_mxf4_probe.txt).
+constexpr uint32_t kRateN = 208, kRateSteps = 20000, kRateKBytes = 128, kRateLBO = 128, kRateSBO = (kRateKBytes / 16) * 128;
+constexpr uint32_t kRateColA = 416, kRateColSF = 480;
+
+__global__ void __launch_bounds__(128) fp4_rate_kernel(uint32_t steps) {
+  __shared__ __align__(1024) uint8_t smem[256 * kRateKBytes];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 2);
+    mbar_fence_init();
+  }
+  for (uint32_t e = tid; e < 256 * kRateKBytes / 4; e += blockDim.x) reinterpret_cast<uint32_t *>(smem)[e] = 0x22222222u;  // all +1
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t lane_base = tmem_base + ((warp * 32u) << 16);
+  uint32_t v[8];
+#pragma unroll
+  for (uint32_t q = 0; q < 8; ++q) v[q] = 0x7f7f7f7fu;
+  for (uint32_t c = 0; c < 32; c += 8) tmem_store8(lane_base + kRateColSF + c, v);
+#pragma unroll
+  for (uint32_t q = 0; q < 8; ++q) v[q] = 0x22222222u;
+  for (uint32_t c = 0; c < 64; c += 8) tmem_store8(lane_base + kRateColA + c, v);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  if ((tid & 31) == 0 && warp < 2) {
+    const uint32_t idesc = (1u << 7) | (1u << 10) | ((kRateN >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+    const uint32_t d = tmem_base + warp * kRateN, sf = tmem_base + kRateColSF;
+    for (uint32_t st = 0; st < steps; ++st) {
+      const uint32_t ks = st & 3;
+      const uint64_t db = umma_smem_desc(smem_u32(smem) + ks * 2 * kRateLBO, kRateLBO, kRateSBO);
+      const uint32_t acc = st > 0 ? 1u : 0u;
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], [%1], %2, %3, [%5], [%5], p;\n\t"
+          "}\n" ::"r"(d),
+          "r"(tmem_base + kRateColA + ks * 8 + warp * 8), "l"(db), "r"(idesc), "r"(acc), "r"(sf)
+          : "memory");
+    }
+    umma_commit_arrive(&bar);
+  }
+  __syncwarp();
+  mbar_wait_suspend(&bar, 0);
+  tcgen05_after_sync();
+  tcgen05_before_sync();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+}
+
 }  // namespace
 }  // namespace ck
+
+extern "C" int ck_measure_fp4_peak(ck_ctx *ctx, double *ops_per_s) {
+  using namespace ck;
+  if (!ctx || !ops_per_s) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = ctx->stream;
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK_CUDA(cudaEventRecord(ctx->ev[0], s));
+    fp4_rate_kernel<<<ctx->num_sms, 128, 0, s>>>(kRateSteps);
+    CK_CUDA(cudaGetLastError());
+    CK_CUDA(cudaEventRecord(ctx->ev[1], s));
+    CK_CUDA(cudaEventSynchronize(ctx->ev[1]));
+    if (rep >= 1) best = std::min(best, elapsed_ms(ctx->ev[0], ctx->ev[1]));
+  }
+  // 2 issuers x 128 x 208 x 64 MACs per step and SM; 2 ops per MAC
+  *ops_per_s = 2.0 * 2.0 * 128.0 * kRateN * 64.0 * double(kRateSteps) * ctx->num_sms / (double(best) * 1e-3);
+  return CK_OK;
+}
 
 extern "C" int ck_measure_int_peaks(ck_ctx *ctx, double *popc_lane_ops_per_s, double *lop3_lane_ops_per_s) {
   using namespace ck;
@@ -64,7 +149,7 @@ extern "C" int ck_measure_int_peaks(ck_ctx *ctx, double *popc_lane_ops_per_s, do
   cudaGetDevice(&prev);
   cudaSetDevice(ctx->device);
   uint32_t *d_out = nullptr;
-  cudaError_t e = cudaMalloc(&d_out, size_t(ctx->num_sms) * 2 * 256 * 4);
+  cudaError_t e = dev_alloc(ctx, reinterpret_cast<void **>(&d_out), size_t(ctx->num_sms) * 2 * 256 * 4);
   if (e == cudaSuccess) e = measure<0>(ctx, d_out, popc_lane_ops_per_s);
   if (e == cudaSuccess) e = measure<1>(ctx, d_out, lop3_lane_ops_per_s);
   if (d_out) cudaFree(d_out);

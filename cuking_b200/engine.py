@@ -113,6 +113,12 @@ class Context:
         check(self._lib.ck_measure_int_peaks(self._h, C.byref(popc), C.byref(lop3)))
         return {"popc_lane_ops_per_s": popc.value, "lop3_lane_ops_per_s": lop3.value}
 
+    def measure_fp4_peak(self) -> float:
+        """Live dense kind::mxf4 tensor rate of this GPU in ops/s (ck_measure_fp4_peak)."""
+        v = C.c_double()
+        check(self._lib.ck_measure_fp4_peak(self._h, C.byref(v)))
+        return v.value
+
     def planes(self, sm: Submatrix, num_sites: int) -> "Planes":
         return Planes(self, sm, num_sites)
 

@@ -138,6 +138,11 @@ int ck_ctx_get_timings(ck_ctx *ctx, ck_timings *out);
  * The pairwise kernel is bound by these pipes, not by HBM or the tensor cores; bench.py quotes its roofline against
  * the POPC figure.  Takes a few milliseconds. */
 int ck_measure_int_peaks(ck_ctx *ctx, double *popc_lane_ops_per_s, double *lop3_lane_ops_per_s);
+/* Measures, on this GPU and now, the dense tcgen05 kind::mxf4 rate (E2M1 operands, ops = 2 x MACs per second, whole
+ * chip): every SM streams M = 128, N = 208, K = 64 instructions from resident operands for a few milliseconds.  This
+ * is what bounds pairwise kernel variant 3 (10 fp4 ops per pair-site); bench.py quotes its roofline against it because
+ * MEASURED_PEAKS.json holds no fp4 figure. */
+int ck_measure_fp4_peak(ck_ctx *ctx, double *ops_per_s);
 int ck_ctx_destroy(ck_ctx *ctx);
 
 /* ---- planes: replaces the managed bit_set of cuking.cu:513-523 --------------------------------------------- */
