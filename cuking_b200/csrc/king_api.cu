@@ -186,7 +186,9 @@ int plan_output(ck_planes *pl, const KingLaunch &k, uint32_t part, uint32_t part
     plan->part_pairs += dense_band_pairs(b * kDenseBandRows, k.num_rows, k.num_cols, k.triangular != 0);
   }
   plan->dense = allow_dense && want_dense(thr, plan->part_pairs, max_results);
-  int rc = ensure_result_buf(ctx, plan->dense ? size_t(plan->part_pairs) : size_t(max_results));
+  // max_results records either way (dense output needs part_pairs <= max_results of them): the buffer then keeps its
+  // size from part to part and call to call
+  int rc = ensure_result_buf(ctx, size_t(max_results));
   if (rc != CK_OK) return rc;
   events_reset(ctx);
   CK_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long) * (plan->dense ? 2 + ck_ctx::kHoleSlots : 1), s));
@@ -381,17 +383,23 @@ int finish_dense(ck_ctx *ctx, ResultPlan &plan, const Dest &dst, uint64_t *num_r
     *num_results = delivered;
     return CK_OK;
   }
+  static const bool dbg = getenv("CUKING_DEBUG_TIMING") != nullptr;
+  const auto tp0 = std::chrono::steady_clock::now();
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
   for (const OutRegion &r : plan.regions) {  // caller's host buffer: optimistic copies to the hole-free positions
     CK_CUDA(cudaStreamWaitEvent(ds, r.ready, 0));
     CK_CUDA(cudaMemcpyAsync(dst.results + r.offset, d_out + r.offset, size_t(r.count) * sizeof(ck_result), cudaMemcpyDeviceToHost, ds));
   }
+  if (dbg) fprintf(stderr, "[ck] dense: %zu regions, copies queued after %.2f ms\n", plan.regions.size(), ms_since(tp0));
   cudaEvent_t copied;
   CK_CUDA(cudaEventCreate(&copied));
   cudaEventRecord(copied, ds);
   const size_t slots = std::min<size_t>(plan.regions.size(), ck_ctx::kHoleSlots);
   if (slots) CK_CUDA(cudaMemcpyAsync(ctx->h_holes, ctx->d_counter + 2, slots * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   cudaError_t e = cudaStreamSynchronize(s);
+  if (dbg) fprintf(stderr, "[ck] dense: kernels done after %.2f ms\n", ms_since(tp0));
   if (e == cudaSuccess) e = cudaStreamSynchronize(ds);
+  if (dbg) fprintf(stderr, "[ck] dense: copies done after %.2f ms\n", ms_since(tp0));
   ctx->timings.king_ms = elapsed_ms(ctx->ev[0], ctx->ev[1]);
   ctx->timings.sort_ms = 0.f;
   ctx->timings.d2h_ms = std::max(0.f, elapsed_ms(ctx->ev[1], copied));  // what was not hidden behind the kernels
@@ -450,6 +458,9 @@ int eval_view(ck_planes *pl, const ck_submatrix *view, uint32_t part, uint32_t p
     return finish_sparse(ctx, d_emit, max_results, dst, num_results, sort);
   }
   // tensor-core kernels: bands of 1024 rows dealt to the parts in snake order
+  static const bool dbg = getenv("CUKING_DEBUG_TIMING") != nullptr;
+  const auto tp0 = std::chrono::steady_clock::now();
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
   std::vector<uint64_t> band_prefix;
   CK_CUDA(band_prepare(k, kBandTileCols, ctx, s, &band_prefix, nullptr));
   const uint32_t num_bands = uint32_t(band_prefix.size()) - 1;
@@ -460,12 +471,18 @@ int eval_view(ck_planes *pl, const ck_submatrix *view, uint32_t part, uint32_t p
   for (uint32_t b = 0; b < num_bands; ++b) owned += band_owner(b, parts) == part;
   const uint32_t max_run = plan.dense ? std::max<uint32_t>(1, ceil_div(owned, 24u)) : 0xffffffffu;
   CK_CUDA(cudaEventRecord(ctx->ev[0], s));
+  if (dbg) fprintf(stderr, "[ck] eval: planned after %.2f ms (dense %d, %llu pairs)\n", ms_since(tp0), int(plan.dense), plan.part_pairs);
   rc = launch_bands(pl, k, variant, band_prefix, 0, num_bands, part, parts, max_run, &plan);
   if (rc != CK_OK) {
     cudaStreamSynchronize(s);
     return rc;
   }
-  if (plan.dense) return finish_dense(ctx, plan, dst, num_results);
+  if (dbg) fprintf(stderr, "[ck] eval: launched after %.2f ms\n", ms_since(tp0));
+  if (plan.dense) {
+    rc = finish_dense(ctx, plan, dst, num_results);
+    if (dbg) fprintf(stderr, "[ck] eval: finished after %.2f ms (kernel %.2f ms)\n", ms_since(tp0), ctx->timings.king_ms);
+    return rc;
+  }
   CK_CUDA(cudaEventRecord(ctx->ev[1], s));
   return finish_sparse(ctx, ctx->result_buf, max_results, dst, num_results, sort);
 }
