@@ -209,16 +209,27 @@ int plan_output(ck_planes *pl, const KingLaunch &k, uint32_t part, uint32_t part
 // output: a run is also an output region - contiguous because consecutive owned bands are consecutive in the output -
 // capped in length so that the device -> host copies of finished regions overlap the kernels of the next ones.
 int launch_bands(ck_planes *pl, KingLaunch k, int variant, const std::vector<uint64_t> &band_prefix, uint32_t band_lo,
-                 uint32_t band_hi, uint32_t part, uint32_t parts, uint32_t max_run, ResultPlan *plan) {
+                 uint32_t band_hi, uint32_t part, uint32_t parts, uint32_t max_run, bool smallest_first, ResultPlan *plan) {
   ck_ctx *ctx = pl->ctx;
   cudaStream_t s = ctx->stream;
   k.results = ctx->result_buf;
   k.counter = ctx->d_counter;
   k.dense_band_base = plan->dense ? ctx->dense_table : nullptr;
+  std::vector<std::pair<uint32_t, uint32_t>> runs;
   for (uint32_t b = band_lo; b < band_hi;) {
     if (band_owner(b, parts) != part) { ++b; continue; }
     uint32_t e = b + 1;
     while (e < band_hi && e - b < max_run && band_owner(e, parts) == part) ++e;
+    runs.emplace_back(b, e);
+    b = e;
+  }
+  // The later bands of a triangular shard hold fewer pairs.  Launch order does not change the result; it decides how
+  // the copy-out of finished regions overlaps the kernels (a two-machine flow shop, compute then copy): when the copy
+  // is the slower machine - several GPUs sharing the host's ingest - the smallest regions go first (Johnson's rule),
+  // otherwise the largest, so that only a small region's copy is left exposed at the end.
+  if (smallest_first) std::reverse(runs.begin(), runs.end());
+  for (const auto &run : runs) {
+    const uint32_t b = run.first, e = run.second;
     k.tile_begin = band_prefix[b];
     k.tile_end = band_prefix[e];
     OutRegion region{};
@@ -234,7 +245,6 @@ int launch_bands(ck_planes *pl, KingLaunch k, int variant, const std::vector<uin
       CK_CUDA(cudaEventRecord(region.ready, s));
       plan->regions.push_back(region);
     }
-    b = e;
   }
   return CK_OK;
 }
@@ -472,7 +482,10 @@ int eval_view(ck_planes *pl, const ck_submatrix *view, uint32_t part, uint32_t p
   const uint32_t max_run = plan.dense ? std::max<uint32_t>(1, ceil_div(owned, 24u)) : 0xffffffffu;
   CK_CUDA(cudaEventRecord(ctx->ev[0], s));
   if (dbg) fprintf(stderr, "[ck] eval: planned after %.2f ms (dense %d, %llu pairs)\n", ms_since(tp0), int(plan.dense), plan.part_pairs);
-  rc = launch_bands(pl, k, variant, band_prefix, 0, num_bands, part, parts, max_run, &plan);
+  // dense output into a caller buffer with several parts (= several GPUs behind one host): the copy-out is the slower
+  // stage (measured: 8 concurrent device -> host streams get 11-18 GB/s each, profiles/r02_host_copy_probe_n8.txt)
+  const bool smallest_first = plan.dense && !dst.sink && parts > 1;
+  rc = launch_bands(pl, k, variant, band_prefix, 0, num_bands, part, parts, max_run, smallest_first, &plan);
   if (rc != CK_OK) {
     cudaStreamSynchronize(s);
     return rc;
@@ -542,7 +555,7 @@ int stream_rows_device(ck_planes *pl, const uint64_t *d_rows, uint32_t s0, uint3
   ctx->timings.king_launches += 2;
   const uint32_t band_lo = s0 / kFp4BandRows, band_hi = ceil_div(std::min(s1, n), kFp4BandRows);
   st->k.codes = pl->codes;
-  int rc = launch_bands(pl, st->k, st->variant, st->band_prefix, band_lo, band_hi, st->part_index, st->num_parts, 0xffffffffu, &st->plan);
+  int rc = launch_bands(pl, st->k, st->variant, st->band_prefix, band_lo, band_hi, st->part_index, st->num_parts, 0xffffffffu, false, &st->plan);
   if (rc != CK_OK) return rc;
   st->next_end = s0;
   return CK_OK;
