@@ -40,7 +40,9 @@ BandTable build_band_table(const KingLaunch &k, uint32_t tile_cols) {
   bt.band_prefix.assign(bt.num_bands + 1, 0);
   bt.band_first_col.assign(std::max<uint32_t>(bt.num_bands, 1), 0);
   for (uint32_t b = 0; b < bt.num_bands; ++b) {
-    const uint32_t rows = std::min(kBandRowTiles, bt.num_row_tiles - b * kBandRowTiles);
+    // an odd last band is padded with one phantom row tile (it exits at once) so that consecutive tiles (2m, 2m + 1) of a
+    // band always share their column tile: the CTA-pair kernel runs them as one 256-row tile
+    const uint32_t rows = band_rows_padded(bt.num_row_tiles - b * kBandRowTiles);
     const uint32_t first = first_alive_col(k, tile_cols, b * kBandRowTiles, bt.num_col_tiles);  // non-decreasing in the row tile
     bt.band_first_col[b] = first;
     bt.band_prefix[b + 1] = bt.band_prefix[b] + uint64_t(rows) * (bt.num_col_tiles - first);

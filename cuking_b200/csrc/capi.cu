@@ -148,8 +148,8 @@ namespace ck {
 // site count the probe verified (kFp4MaxSites) and only if this GPU passed the self-test; otherwise the int8 kernel.
 int planes_variant(const ck_planes *pl) {
   const int v = active_variant(pl->ctx);
-  if (v != 3) return v;
-  return (pl->num_sites > kFp4MaxSites || !fp4_usable(pl->ctx)) ? 2 : 3;
+  if (v < 3) return v;  // 3 = mxf4 kernel, 4 = its CTA-pair form: both rest on the fp32 accumulation of kind::mxf4
+  return (pl->num_sites > kFp4MaxSites || !fp4_usable(pl->ctx)) ? 2 : v;
 }
 }  // namespace ck
 
@@ -273,7 +273,7 @@ int ck_ctx_set_stream(ck_ctx *ctx, void *cuda_stream) {
 
 int ck_ctx_set_king_variant(ck_ctx *ctx, int variant) {
   if (!ctx) return fail(CK_ERR_INVALID_ARGUMENT, "ctx is NULL");
-  if (variant < -1 || variant > 3) return fail(CK_ERR_INVALID_ARGUMENT, "unknown pairwise kernel variant");
+  if (variant < -1 || variant > 4) return fail(CK_ERR_INVALID_ARGUMENT, "unknown pairwise kernel variant");
   ctx->king_variant = variant;
   return CK_OK;
 }
@@ -395,7 +395,8 @@ int ensure_compute(ck_planes *pl) {
   ck_ctx *ctx = pl->ctx;
   const int variant = planes_variant(pl);
   const bool want_codes = variant >= 2;
-  if (want_codes ? (!pl->codes_stale && pl->codes_kind == variant) : !pl->compute_stale) return CK_OK;
+  const int kind = variant >= 3 ? 3 : variant;  // nibble encoding: 2 = int8 selectors, 3 = E2M1 (both mxf4 kernels)
+  if (want_codes ? (!pl->codes_stale && pl->codes_kind == kind) : !pl->compute_stale) return CK_OK;
   if (want_codes && pl->codes == nullptr) {
     pl->codes_bytes = std::max<size_t>(pl->codes_words(), 1) * 4;
     CK_CUDA(ctx_alloc(ctx, reinterpret_cast<void **>(&pl->codes), pl->codes_bytes));
@@ -405,12 +406,12 @@ int ensure_compute(ck_planes *pl) {
     CK_CUDA(ctx_alloc(ctx, reinterpret_cast<void **>(&pl->compute), pl->compute_bytes));
   }
   CK_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  if (pl->raw_words()) CK_CUDA(want_codes ? launch_finalize_codes(*pl, variant, ctx->stream) : launch_finalize(*pl, ctx->stream));
+  if (pl->raw_words()) CK_CUDA(want_codes ? launch_finalize_codes(*pl, kind, ctx->stream) : launch_finalize(*pl, ctx->stream));
   CK_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   CK_CUDA(cudaEventSynchronize(ctx->ev[1]));
   ctx->timings.finalize_ms = elapsed_ms(ctx->ev[0], ctx->ev[1]);
   (want_codes ? pl->codes_stale : pl->compute_stale) = false;
-  if (want_codes) pl->codes_kind = variant;
+  if (want_codes) pl->codes_kind = kind;
   return CK_OK;
 }
 }  // namespace ck

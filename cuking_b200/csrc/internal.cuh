@@ -248,6 +248,10 @@ cudaError_t launch_king(const KingLaunch &k, int variant, cudaStream_t s, uint32
 // ---- band_tiles.cu: tile enumeration shared by the two tensor-core kernels ----
 constexpr uint32_t kBandTileRows = 128;  // tile rows (TMEM lanes)
 constexpr uint32_t kBandRowTiles = 8;    // row tiles per band
+__host__ __device__ inline uint32_t band_rows_padded(uint32_t remaining_row_tiles) {  // row tiles enumerated in a band
+  const uint32_t r = remaining_row_tiles < kBandRowTiles ? remaining_row_tiles : kBandRowTiles;
+  return (r + 1u) & ~1u;
+}
 constexpr uint32_t kBandTileCols = 80;   // tile columns of both tensor-core kernels (what the streaming seam assumes)
 struct BandTiles {                       // device view of the band table (ctx scratch)
   const unsigned long long *band_prefix;  // [num_bands + 1] tiles before band b
@@ -268,6 +272,8 @@ cudaError_t launch_king_umma(const KingLaunch &k, uint32_t total_blocks, ck_ctx 
 // ---- king_fp4_kernel.cu (variant 3: tcgen05 kind::mxf4 formulation, 128 x 80 tiles, band-ordered tile enumeration) ----
 uint64_t king_fp4_num_tiles(const KingLaunch &k);
 cudaError_t launch_king_fp4(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches);
+// king_fp4_pair_kernel.cu (variant 4: the same on CTA pairs, tcgen05 cta_group::2, 256 x 80 tiles sharing the B operand)
+cudaError_t launch_king_fp4_pair(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches);
 // band table of this launch geometry for the mxf4 kernel's tile shape (band_prepare)
 cudaError_t king_fp4_prepare(const KingLaunch &k, ck_ctx *ctx, cudaStream_t s, std::vector<uint64_t> *band_prefix);
 constexpr uint32_t kFp4BandRows = kBandRowTiles * kBandTileRows;

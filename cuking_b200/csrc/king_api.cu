@@ -98,12 +98,13 @@ int sort_results(ck_ctx *ctx, const ck_result *in, size_t n, ck_result *out, con
 }
 
 uint64_t variant_num_tiles(int variant, const KingLaunch &k) {
-  if (variant == 3) return king_fp4_num_tiles(k);
+  if (variant >= 3) return king_fp4_num_tiles(k);
   if (variant == 2) return king_umma_num_tiles(k);
   return king_num_tiles(k.num_row_blocks, k.num_col_blocks, k.triangular != 0);
 }
 
 cudaError_t dispatch_king(int variant, const ck_planes *pl, const KingLaunch &k, cudaStream_t s, uint32_t *launches) {
+  if (variant == 4) return launch_king_fp4_pair(k, pl->map.num_blocks, pl->ctx, s, launches);
   if (variant == 3) return launch_king_fp4(k, pl->map.num_blocks, pl->ctx, s, launches);
   if (variant == 2) return launch_king_umma(k, pl->map.num_blocks, pl->ctx, s, launches);
   return launch_king(k, variant, s, launches);
@@ -551,7 +552,7 @@ int stream_rows_device(ck_planes *pl, const uint64_t *d_rows, uint32_t s0, uint3
                                          "ck_king_stream_granularity()");
   const uint32_t block0 = s0 / kTileSamples, num_blocks = ceil_div(s1, kTileSamples) - block0;
   CK_CUDA(launch_import_ref_range(*pl, d_rows, s0, block0, num_blocks, s));
-  CK_CUDA(launch_finalize_codes_range(*pl, st->variant, block0, num_blocks, s));
+  CK_CUDA(launch_finalize_codes_range(*pl, st->variant >= 3 ? 3 : st->variant, block0, num_blocks, s));
   ctx->timings.king_launches += 2;
   const uint32_t band_lo = s0 / kFp4BandRows, band_hi = ceil_div(std::min(s1, n), kFp4BandRows);
   st->k.codes = pl->codes;
@@ -584,7 +585,7 @@ int stream_end_impl(ck_planes *pl, ck_result *results, uint64_t *num_results) {
   }
   pl->compute_stale = true;
   pl->codes_stale = false;
-  pl->codes_kind = variant;
+  pl->codes_kind = variant >= 3 ? 3 : variant;
   Dest dst;
   dst.results = results;
   if (plan.dense) return finish_dense(ctx, plan, dst, num_results);

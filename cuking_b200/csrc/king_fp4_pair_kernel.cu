@@ -1,34 +1,15 @@
-// Pairwise KING on the 5th-generation tensor cores at the FP4 rate: tcgen05.mma.kind::mxf4.block_scale over E2M1
-// indicator vectors with all block scales = 2^0 and fp32 accumulation (sm_100a only).  Variant 3, the default.
+// CTA-pair form of the mxf4 pairwise kernel (king_fp4_kernel.cu): tcgen05.mma.cta_group::2 over a 256 x 80 tile held by
+// the two SMs of a cluster.  Variant 4 (experimental; same records as every other variant).
 //
-// Same algebra as king_umma_kernel.cu (the six counters of ComputeKingKernel, /root/reference/cuking.cu:214-240, as
-// five bilinear forms of per-sample indicator vectors):
-//     x = [hom-alt] - [hom-ref]   y = [hom]   h = [het] / 2          (all 0 where the genotype is missing)
-//     D_xx = x_i.x_j = conc - opp            D_y = y_i.[y_j ; h_j] = (conc + opp | (i hom, j het) / 2)
-//     D_h = h_i.[y_j ; h_j] = ((i het, j hom) / 2 | both_het / 4)
-// kind::mxf4 multiplies 64 sites per instruction — twice kind::i8 — and the operands are 4 bits wide, so operand
-// expansion, TMEM stores and shared-memory traffic per site all halve as well.  Exactness: every operand is 0, 0.5 or
-// +-1 in E2M1, every product a multiple of 1/4, every partial sum a multiple of 1/4 below 2^24 / 4: exactly representable
-// in the fp32 accumulator.  tools/umma_mxf4_probe.cu measured the tensor core's accumulation to be exact for counts up
-// to 2^23 on this pool's B200s (profiles/r01_mxf4_probe.txt); capi.cu routes cohorts with more than 2^23 sites to the
-// int8 kernel (exact to 2^31) instead.
-//
-// Operands are expanded on the fly from 4-bit genotype codes (layout.cuh) chosen so that the expansion is ONE logic
-// instruction per operand per 8 genotypes: code = 1 het, 2 hom-alt, 0xA hom-ref, 0 missing, i.e. E2M1(0.5), E2M1(+1),
-// E2M1(-1), 0, and   x = z & 0xAAAAAAAA   y = z & 0x22222222   h = z & 0x11111111.
-//   * warps 0-7   A operands: one thread per row sample; the two groups of four warps take alternate A stages (two 64-site
-//                 steps each) and write straight into a 4-slot TMEM ring with tcgen05.st (thread = TMEM lane = row);
-//                 a slot is announced as soon as it is stored, a stage is released by one commit per issuer;
-//   * warps 8-12  B operands: two threads per column sample (32 sites each per step) write K-major no-swizzle canonical
-//                 shared-memory tiles, several steps per stage so the proxy fence and barrier round trip are amortised;
-//   * one lane of each of warps 13-15 issues one of the three MMAs per step (A from TMEM, B from shared memory) and
-//                 releases the A slot / B stage with tcgen05.commit;
-//   * epilogue    all 16 warps read the fp32 accumulators with tcgen05.ld, convert to the exact integer counts, compute
-//                 kinship in the reference's fp32 order and append through the warp-aggregated atomic.
-// TMEM: 400 accumulator columns + 4 x 24 A columns + 16 scale-factor columns (all 0x7F = 2^0; every byte is the same,
-// so the scale-factor layout is immaterial) = 512.
-// Tiles are enumerated in bands of 8 row tiles (band_tiles.cu), column-major inside a band, so that the ~148 tiles in flight share
-// 8 row blocks and ~19 column blocks and the genotype codes are served from L2.
+// Each CTA of the pair owns 128 rows: its A operands (TMEM ring) and its accumulators are exactly those of the single-CTA
+// kernel.  The B operand is SHARED: each CTA expands only 40 of the tile's 80 column samples into its own shared memory
+// and the pair instruction reads rows [0, N/2) of B from the leader's shared memory and [N/2, N) from its peer's (measured
+// by tools/umma_pair_probe.cu), so B expansion, B stores and B reads per SM halve - shared memory was 74 % busy in the
+// single-CTA kernel, next to the tensor core's own operand reads.  Only the leader's issuer lanes issue MMAs; their
+// commits are multicast to the barriers of both CTAs; the peer's expander warps announce their operands on the LEADER's
+// barriers (remote mbarrier arrive at cluster scope).  Stacked B for the y / h streams: a CTA's shared memory holds
+// [y(40 columns) ; h(40 columns)], hence the accumulator columns of D_y and D_h are [yy(0-39) | yh(0-39) | yy(40-79) |
+// yh(40-79)] - the epilogue undoes that.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -54,7 +35,10 @@ constexpr uint32_t kFGroups = 2;            // groups of four A warps; group g f
 constexpr uint32_t kFSub = 4;               // B expanders work in sub-stages of 4 steps (register prefetch unit)
 constexpr uint32_t kFLBO = 128;             // bytes between K-adjacent 8x16-byte core matrices
 constexpr uint32_t kFThreads = 512;
-constexpr uint32_t kFAWarps = 8, kFBWarps = (2 * kFN) / 32, kFExpWarps = kFAWarps + kFBWarps;  // 8 + 5
+constexpr uint32_t kFAWarps = 8, kFBWarps = (2 * kFN) / 32, kFExpWarps = kFAWarps + kFBWarps;  // 8 + 5 warp slots
+constexpr uint32_t kPN = kFN / 2;                        // B columns a CTA of the pair expands
+constexpr uint32_t kPBThreads = 2 * kPN;                 // two threads per column sample: 80 threads in warps 8, 9, 10
+constexpr uint32_t kPBWarps = (kPBThreads + 31) / 32;    // 3 (warp 10 is half empty); warps 11, 12 only join the epilogue
 constexpr uint32_t kFIssuers = 3;           // warps 13, 14, 15: x, y and h MMAs
 constexpr uint32_t kFAPrefetchSteps = 4;    // A register prefetch depth in steps of the group (= 8 steps ahead)
 constexpr uint32_t kFBPrefetch = 2;         // B register prefetch depth in sub-stages (= 8 steps ahead)
@@ -72,7 +56,7 @@ struct Fp4Geo {
   static_assert(BS % kFSub == 0 && BS % AS == 0 && kFSlots % AS == 0 && (AS == 1 || AS == 2), "stage geometry");
   static constexpr uint32_t kAStages = kFSlots / AS;        // A stages in the TMEM ring
   static constexpr uint32_t kSBO = BS * 2 * kFLBO;          // a stage holds 32 K-bytes (64 sites) per step
-  static constexpr uint32_t kTile = (kFN / 8) * kSBO;       // one B operand plane of one stage
+  static constexpr uint32_t kTile = (kPN / 8) * kSBO;       // one B operand plane (this CTA's 40 columns) of one stage
   static constexpr uint32_t kStageBytes = 3 * kTile;
   static constexpr size_t kSmem = size_t(NS) * kStageBytes + 1024;  // + alignment slack
 };
@@ -82,23 +66,66 @@ struct Fp4Geo {
 __host__ __device__ constexpr uint32_t make_idesc_mxf4(uint32_t M, uint32_t N) {
   return (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
 }
-// D[tmem] (+)= A[tmem] . B[smem]^T, fp32 accumulation, block scales read from TMEM
-__device__ __forceinline__ void umma_mxf4_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t tmem_sf,
-                                             uint32_t accumulate) {
+// D[tmem of both CTAs] (+)= A[tmem of both CTAs] . B[smem halves of both CTAs]^T, fp32 accumulation, block scales from TMEM
+__device__ __forceinline__ void umma2_mxf4_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t tmem_sf,
+                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], [%1], %2, %3, [%5], [%5], p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], [%1], %2, %3, [%5], [%5], p;\n\t"
       "}\n" ::"r"(tmem_d),
       "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(tmem_sf)
       : "memory");
 }
+// arrives on the mbarrier at this shared-memory offset in BOTH CTAs once every MMA this thread has issued so far has completed
+__device__ __forceinline__ void umma2_commit_both(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(uint16_t(3))
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster (the form CUTLASS' ClusterBarrier
+// uses for software-written operands of 2-SM MMAs).  CK_PAIR_STRICT selects explicit cluster-scope release / acquire.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+#ifdef CK_PAIR_STRICT
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#endif
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity, uint32_t hint_ns = 20000u) {
+#ifdef CK_PAIR_STRICT
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+  }
+#else
+  mbar_wait_suspend(bar, parity, hint_ns);
+#endif
+}
 
 #ifdef CK_UMMA_PROFILE
-__device__ unsigned long long g_fp4_prof[16];
+__device__ unsigned long long g_fp4_pair_prof[16];
 #define FPROF_T() clock64()
-#define FPROF_ADD(slot, dt) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_fp4_prof[slot], (unsigned long long)(dt)); } while (0)
+#define FPROF_ADD(slot, dt) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_fp4_pair_prof[slot], (unsigned long long)(dt)); } while (0)
 #else
 #define FPROF_T() 0ull
 #define FPROF_ADD(slot, dt) do { (void)(dt); } while (0)
@@ -116,7 +143,7 @@ __device__ __forceinline__ void expand_fp4(uint32_t z, uint32_t &x, uint32_t &y,
 }
 
 template <uint32_t AS, uint32_t BS, uint32_t NS>
-__global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch p, const BandTiles tiles) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1) king_fp4_pair_kernel(const KingLaunch p, const BandTiles tiles) {
   using G = Fp4Geo<AS, BS, NS>;
   constexpr uint32_t kAStages = G::kAStages;
   extern __shared__ uint8_t smem_raw[];
@@ -124,26 +151,32 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
 
-  // ---- which tile: band order (band_tiles.cu) ----
+  // ---- which tile: band order (band_tiles.cu); the two CTAs of a cluster hold consecutive linear tiles = row tiles
+  // 2m and 2m + 1 of the same column tile (bands are padded to an even number of row tiles) ----
   uint32_t ti, tj;
   band_decode(tiles, p.tile_begin + blockIdx.x, ti, tj);
   const uint32_t row0 = ti * kFM, col0 = tj * kFN;  // offsets inside the sub-matrix
-  if (row0 >= p.num_rows) return;  // phantom row tile that pads an odd last band (band_tiles.cu)
-  const uint32_t rows_here = min(kFM, p.num_rows - row0), cols_here = min(kFN, p.num_cols - col0);
+  const uint32_t pair_row0 = (ti & ~1u) * kFM;      // first row of the 256-row pair tile
+  if (pair_row0 >= p.num_rows) return;              // cluster-uniform exits only
+  const uint32_t rows_here = row0 < p.num_rows ? min(kFM, p.num_rows - row0) : 0u;  // 0: phantom half, computes nothing useful
+  const uint32_t cols_here = min(kFN, p.num_cols - col0);
   const uint32_t i0 = p.row_global0 + row0, j0 = p.col_global0 + col0;
-  if (j0 + cols_here - 1 <= i0) return;  // no i < j pair in this tile (below the diagonal): whole CTA leaves
+  if (j0 + cols_here - 1 <= p.row_global0 + pair_row0) return;  // no i < j pair in the whole pair tile
 
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   if (warp == kFExpWarps) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(kFTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(kFTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   if (tid == 0) {
-    for (uint32_t s = 0; s < kFSlots; ++s) mbar_init(&full_a[s], kFAWarps / kFGroups);  // per slot: the four warps of the filling group
-    for (uint32_t s = 0; s < kAStages; ++s) mbar_init(&empty_a[s], kFIssuers);             // per stage: one commit per issuer
+    // the leader's full barriers collect the expander warps of BOTH CTAs; empty / accumulator barriers get the
+    // issuers' commits multicast to both CTAs
+    for (uint32_t s = 0; s < kFSlots; ++s) mbar_init(&full_a[s], 2 * (kFAWarps / kFGroups));
+    for (uint32_t s = 0; s < kAStages; ++s) mbar_init(&empty_a[s], kFIssuers);
     for (uint32_t s = 0; s < NS; ++s) {
-      mbar_init(&full_b[s], kFBWarps);
+      mbar_init(&full_b[s], 2 * kPBWarps);
       mbar_init(&empty_b[s], kFIssuers);
     }
     mbar_init(&acc_bar, kFIssuers);
@@ -151,6 +184,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
   }
   tcgen05_before_sync();
   __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before anyone arrives remotely
   tcgen05_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t num_steps = p.words / 2;  // one 64-site step = two 32-site code words; p.words is a multiple of 16
@@ -162,7 +196,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     const uint32_t group = warp >> 2, srow = (warp & 3) * 32 + lane;
     // rows beyond the tile's edge re-read its first row (always allocated): their pairs are masked in the epilogue, and
     // the loads stay unconditional
-    const uint32_t slot = p.row_slot0 + row0 + (srow < rows_here ? srow : 0u);
+    const uint32_t slot = p.row_slot0 + (rows_here ? row0 + (srow < rows_here ? srow : 0u) : 0u);  // phantom half: any valid row
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
     const uint4 *src = reinterpret_cast<const uint4 *>(p.codes) + size_t(blk) * p.words * kTileSamples + ln;
     const uint32_t lane_base = tmem_base + ((uint32_t(warp & 3) * 32u) << 16);
@@ -228,7 +262,9 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tcgen05_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&full_a[aslot]);
+          if (lane == 0) {  // on the leader's barrier
+            if (rank == 0) mbar_arrive(&full_a[aslot]); else mbar_arrive_cluster(&full_a[aslot], 0);
+          }
         }
         const unsigned long long p3 = FPROF_T();
         FPROF_ADD(0, p1 - p0);
@@ -237,11 +273,15 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
         FPROF_ADD(3, 1);
       }
     }
-  } else if (warp < kFExpWarps) {
+  } else if (warp < kFAWarps + kPBWarps) {
     // ===== B expanders: two threads per column sample (32 sites of every step each), BS steps per stage =====
+    // this CTA's half of the tile's columns: [rank * 40, rank * 40 + 40); threads beyond 2 x 40 idle along (warp 10's upper half,
+    // warps 11 and 12) and only keep the warp-level synchronisation well formed
     const uint32_t idx = tid - kFAWarps * 32;
-    const uint32_t half = idx / kFN, srow = idx % kFN;  // half: K bytes 16*half .. 16*half+15 of every step
-    const uint32_t slot = p.col_slot0 + col0 + (srow < cols_here ? srow : 0u);  // see the A expanders
+    const bool b_active = idx < kPBThreads;
+    const uint32_t half = b_active ? idx / kPN : 0u, srow = b_active ? idx % kPN : 0u;  // half: K bytes 16*half .. 16*half+15 of every step
+    const uint32_t col = rank * kPN + srow;                                               // column inside the 80-column tile
+    const uint32_t slot = p.col_slot0 + col0 + (col < cols_here ? col : 0u);  // see the A expanders
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
     const uint4 *src = reinterpret_cast<const uint4 *>(p.codes) + (size_t(blk) * p.words + half) * kTileSamples + ln;
     const uint32_t b_off = (srow >> 3) * G::kSBO + (srow & 7) * 16 + half * kFLBO;
@@ -275,16 +315,20 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
         if (sub == 0 && fill > 0) mbar_wait_suspend(&empty_b[s], (fill - 1) & 1u);  // the MMAs that read this stage have completed
         const unsigned long long p2 = FPROF_T();
         const uint32_t stage = smem_base + s * G::kStageBytes + b_off + sub * kFSub * 2 * kFLBO;
+        if (b_active) {
 #pragma unroll
-        for (uint32_t q = 0; q < kFSub; ++q) {
-          sts128(stage + q * 2 * kFLBO, x[q][0], x[q][1], x[q][2], x[q][3]);
-          sts128(stage + G::kTile + q * 2 * kFLBO, y[q][0], y[q][1], y[q][2], y[q][3]);
-          sts128(stage + 2 * G::kTile + q * 2 * kFLBO, h[q][0], h[q][1], h[q][2], h[q][3]);
+          for (uint32_t q = 0; q < kFSub; ++q) {
+            sts128(stage + q * 2 * kFLBO, x[q][0], x[q][1], x[q][2], x[q][3]);
+            sts128(stage + G::kTile + q * 2 * kFLBO, y[q][0], y[q][1], y[q][2], y[q][3]);
+            sts128(stage + 2 * G::kTile + q * 2 * kFLBO, h[q][0], h[q][1], h[q][2], h[q][3]);
+          }
         }
         if (sub == kSubsPerStage - 1) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (tensor core)
           __syncwarp();
-          if (lane == 0) mbar_arrive(&full_b[s]);
+          if (lane == 0) {  // on the leader's barrier
+            if (rank == 0) mbar_arrive(&full_b[s]); else mbar_arrive_cluster(&full_b[s], 0);
+          }
         }
         const unsigned long long p3 = FPROF_T();
         FPROF_ADD(4, p1 - p0);
@@ -297,8 +341,8 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     // ===== MMA issuers: warps 13 (x.x), 14 (y.[y;h]), 15 (h.[y;h]).  The whole warp runs the loop (warp-uniform control
     // flow keeps the descriptor arithmetic in the uniform datapath); one elected lane issues the MMA and the commits.
     const uint32_t which = warp - kFExpWarps;
-    if (which < kFIssuers) {
-    const uint32_t idesc = which == 0 ? make_idesc_mxf4(kFM, kFN) : make_idesc_mxf4(kFM, 2 * kFN);
+    if (which < kFIssuers && rank == 0) {
+    const uint32_t idesc = which == 0 ? make_idesc_mxf4(2 * kFM, kFN) : make_idesc_mxf4(2 * kFM, 2 * kFN);
     const uint32_t d_addr = tmem_base + (which == 0 ? kFColXX : which == 1 ? kFColY : kFColH);
     const uint32_t a_addr = tmem_base + kFColA + which * 8;
     const uint32_t sf_addr = tmem_base + kFColSF;
@@ -307,30 +351,30 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     for (uint32_t step = 0; step < num_steps; step += AS) {
       const uint32_t stage_no = step / AS, astage = stage_no % kAStages, mb = step / BS, sb = mb % NS, q = step % BS;
       const unsigned long long q0 = FPROF_T();
-      if (q == 0) mbar_wait_suspend(&full_b[sb], (mb / NS) & 1u);
+      if (q == 0) mbar_wait_cluster(&full_b[sb], (mb / NS) & 1u);
       unsigned long long waited = FPROF_T() - q0;
 #pragma unroll
       for (uint32_t a = 0; a < AS; ++a) {
         const uint32_t aslot = astage * AS + a;
         const unsigned long long w0 = FPROF_T();
-        mbar_wait_suspend(&full_a[aslot], (stage_no / kAStages) & 1u);
+        mbar_wait_cluster(&full_a[aslot], (stage_no / kAStages) & 1u);
         waited += FPROF_T() - w0;
         tcgen05_after_sync();
         if (elected) {
           const uint32_t b_bytes = sb * G::kStageBytes + (q + a) * 2 * kFLBO;
-          umma_mxf4_ts(d_addr, a_addr + aslot * 24, b_desc0 + uint64_t(b_bytes >> 4), idesc, sf_addr, (step + a) > 0 ? 1u : 0u);
+          umma2_mxf4_ts(d_addr, a_addr + aslot * 24, b_desc0 + uint64_t(b_bytes >> 4), idesc, sf_addr, (step + a) > 0 ? 1u : 0u);
         }
       }
       if (elected) {
-        umma_commit_arrive(&empty_a[astage]);                       // arrives when this thread's MMAs so far have completed
-        if (q + AS == BS) umma_commit_arrive(&empty_b[sb]);         // last steps of the B stage
+        umma2_commit_both(&empty_a[astage]);                        // arrives (in both CTAs) when this thread's MMAs so far have completed
+        if (q + AS == BS) umma2_commit_both(&empty_b[sb]);          // last steps of the B stage
       }
       __syncwarp();
       const unsigned long long q1 = FPROF_T();
       FPROF_ADD(8 + which, waited);
       if (which == 1) FPROF_ADD(11, q1 - q0 - waited);
     }
-    if (elected) umma_commit_arrive(&acc_bar);  // this issuer's accumulator is final
+    if (elected) umma2_commit_both(&acc_bar);  // this issuer's accumulators (both CTAs' halves) are final
     }
   }
 
@@ -388,26 +432,29 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
       emit_pair(p, pair, cand, gi, gj, kin, opp, conc, both_het, shared);
     };
     constexpr uint32_t kColsPerGroup = kFN / 4;  // 20
-    static_assert(kColsPerGroup == 20 || kColsPerGroup == 16, "epilogue column split");
+    static_assert(kColsPerGroup == 20 && kPN == 2 * kColsPerGroup, "epilogue column split");
     const uint32_t c0 = group * kColsPerGroup;
+    // stacked accumulators: columns [yy(0-39) | yh(0-39) | yy(40-79) | yh(40-79)] (the leader's B rows, then the peer's)
+    const uint32_t bhalf = c0 / kPN, cc = c0 % kPN;
+    const uint32_t o_yy = kFColY + bhalf * 2 * kPN + cc, o_yh = o_yy + kPN, o_hy = kFColH + bhalf * 2 * kPN + cc, o_hh = o_hy + kPN;
     {
       uint32_t xx[16], yy[16], yh[16], hy[16], hh[16];
       tmem_load16(lane_base + kFColXX + c0, xx);
-      tmem_load16(lane_base + kFColY + c0, yy);
-      tmem_load16(lane_base + kFColY + kFN + c0, yh);
-      tmem_load16(lane_base + kFColH + c0, hy);
-      tmem_load16(lane_base + kFColH + kFN + c0, hh);
+      tmem_load16(lane_base + o_yy, yy);
+      tmem_load16(lane_base + o_yh, yh);
+      tmem_load16(lane_base + o_hy, hy);
+      tmem_load16(lane_base + o_hh, hh);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
       for (uint32_t q = 0; q < 16; ++q) finish(c0 + q, xx[q], yy[q], yh[q], hy[q], hh[q]);
     }
-    if constexpr (kColsPerGroup > 16) {
+    {
       uint32_t xx[4], yy[4], yh[4], hy[4], hh[4];
       tmem_load4(lane_base + kFColXX + c0 + 16, xx);
-      tmem_load4(lane_base + kFColY + c0 + 16, yy);
-      tmem_load4(lane_base + kFColY + kFN + c0 + 16, yh);
-      tmem_load4(lane_base + kFColH + c0 + 16, hy);
-      tmem_load4(lane_base + kFColH + kFN + c0 + 16, hh);
+      tmem_load4(lane_base + o_yy + 16, yy);
+      tmem_load4(lane_base + o_yh + 16, yh);
+      tmem_load4(lane_base + o_hy + 16, hy);
+      tmem_load4(lane_base + o_hh + 16, hh);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
       for (uint32_t q = 0; q < 4; ++q) finish(c0 + 16 + q, xx[q], yy[q], yh[q], hy[q], hh[q]);
@@ -416,65 +463,31 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
   }
   tcgen05_before_sync();
   __syncthreads();
-  __syncwarp();
-  if (warp == kFExpWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kFTmemCols));
+  cluster_sync_all();  // both CTAs have read their accumulators
+  if (warp == kFExpWarps) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kFTmemCols));
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
 
-struct Fp4Config { uint32_t as, bs, ns; };
-Fp4Config fp4_config() {  // stage geometry; CUKING_FP4_STAGE = "<steps per A stage>x<steps per B stage>x<B stages>" is a tuning knob
-  static Fp4Config cfg = [] {
-    Fp4Config c{2, 8, 3};
-    if (const char *v = getenv("CUKING_FP4_STAGE")) {
-      unsigned a = 0, b = 0, n = 0;
-      if (sscanf(v, "%ux%ux%u", &a, &b, &n) == 3 && (a == 1 || a == 2) && ((b == 4 && n == 4) || (b == 8 && n == 3))) c = Fp4Config{a, b, n};
-    }
-    return c;
-  }();
-  return cfg;
-}
-
-template <uint32_t AS, uint32_t BS, uint32_t NS>
-cudaError_t launch_cfg(const KingLaunch &part, const BandTiles &tiles, cudaStream_t s) {
-  static std::atomic<uint64_t> configured{0};  // one bit per device
-  if (cudaError_t e = optin_dynamic_smem(king_fp4_kernel<AS, BS, NS>, Fp4Geo<AS, BS, NS>::kSmem, configured); e != cudaSuccess) return e;
-  king_fp4_kernel<AS, BS, NS><<<unsigned(part.tile_end - part.tile_begin), kFThreads, Fp4Geo<AS, BS, NS>::kSmem, s>>>(part, tiles);
-  return cudaGetLastError();
-}
-
 }  // namespace
 
-#ifdef CK_UMMA_PROFILE
-extern "C" void ck_debug_fp4_prof(unsigned long long *out) {
-  cudaMemcpyFromSymbol(out, g_fp4_prof, sizeof(g_fp4_prof));
-  unsigned long long z[16] = {0};
-  cudaMemcpyToSymbol(g_fp4_prof, z, sizeof(z));
-}
-#endif
-
-uint64_t king_fp4_num_tiles(const KingLaunch &k) { return band_num_tiles(k, kFN); }
-
-cudaError_t king_fp4_prepare(const KingLaunch &k, ck_ctx *ctx, cudaStream_t s, std::vector<uint64_t> *band_prefix) {
-  return band_prepare(k, kFN, ctx, s, band_prefix, nullptr);
-}
-
-cudaError_t launch_king_fp4(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches) {
-  (void)total_blocks;  // every row / column a tile reads lies inside the shard's allocated blocks
+cudaError_t launch_king_fp4_pair(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches) {
+  (void)total_blocks;
   if (k.tile_end <= k.tile_begin) return cudaSuccess;
+  if ((k.tile_begin | k.tile_end) & 1ull) return cudaErrorInvalidValue;  // tile ranges of whole bands are even (band_tiles.cu)
   BandTiles tiles{};
   cudaError_t e = band_prepare(k, kFN, ctx, s, nullptr, &tiles);
   if (e != cudaSuccess) return e;
-  const Fp4Config cfg = fp4_config();
+  using G = Fp4Geo<2, 8, 3>;
+  static std::atomic<uint64_t> configured{0};  // one bit per device
+  if ((e = optin_dynamic_smem(king_fp4_pair_kernel<2, 8, 3>, G::kSmem, configured)) != cudaSuccess) return e;
   constexpr uint64_t kMaxGrid = 1ull << 30;
   for (uint64_t t = k.tile_begin; e == cudaSuccess && t < k.tile_end; t += kMaxGrid) {
     KingLaunch part = k;
     part.tile_begin = t;
     part.tile_end = (t + kMaxGrid < k.tile_end) ? t + kMaxGrid : k.tile_end;
-    if (cfg.as == 1 && cfg.bs == 4) e = launch_cfg<1, 4, 4>(part, tiles, s);
-    else if (cfg.as == 1) e = launch_cfg<1, 8, 3>(part, tiles, s);
-    else if (cfg.bs == 4) e = launch_cfg<2, 4, 4>(part, tiles, s);
-    else e = launch_cfg<2, 8, 3>(part, tiles, s);
+    king_fp4_pair_kernel<2, 8, 3><<<unsigned(part.tile_end - part.tile_begin), kFThreads, G::kSmem, s>>>(part, tiles);
+    e = cudaGetLastError();
     if (launches) ++*launches;
   }
   return e;

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kUThreads, 1) king_umma_kernel(const KingLaunc
   uint32_t ti, tj;
   band_decode(tiles, p.tile_begin + blockIdx.x, ti, tj);
   const uint32_t row0 = ti * kUM, col0 = tj * kUN;           // offsets inside the sub-matrix
+  if (row0 >= p.num_rows) return;  // phantom row tile that pads an odd last band (band_tiles.cu)
   const uint32_t rows_here = min(kUM, p.num_rows - row0), cols_here = min(kUN, p.num_cols - col0);
   const uint32_t i0 = p.row_global0 + row0, j0 = p.col_global0 + col0;
   if (j0 + cols_here - 1 <= i0) return;  // no i < j pair in this tile (below the diagonal): whole CTA leaves

@@ -59,7 +59,7 @@ __device__ __forceinline__ void band_decode(const BandTiles &tiles, unsigned lon
     const uint32_t mid = (lo + hi) >> 1;
     if (tiles.band_prefix[mid] <= t) lo = mid; else hi = mid;
   }
-  const uint32_t band_rows = min(kBandRowTiles, tiles.num_row_tiles - lo * kBandRowTiles);
+  const uint32_t band_rows = band_rows_padded(tiles.num_row_tiles - lo * kBandRowTiles);
   const uint32_t q = uint32_t(t - tiles.band_prefix[lo]);
   ti = lo * kBandRowTiles + q % band_rows;
   tj = tiles.band_first_col[lo] + q / band_rows;

@@ -29,30 +29,46 @@ ap.add_argument("--sites", type=int, default=100_000)
 ap.add_argument("--files", type=int, default=32)
 ap.add_argument("--threads", type=int, default=16)
 ap.add_argument("--threshold", type=float, default=0.0884)
+ap.add_argument("--num-gpus", default="1", help="comma list: the binary is run once per entry on the same input")
+ap.add_argument("--split-factor", type=int, default=1, help="> 1: --all_shards with this split factor")
 args = ap.parse_args()
 
 with tempfile.TemporaryDirectory() as tmp:
     t0 = time.perf_counter()
-    g = ck.synth_genotypes_host(42, 0.01, 0, args.samples, 0, args.sites)
+    from oracle import king_oracle as ko  # the OpenMP restatement of the same generator (tests pin the two against each other)
+
+    g = ko.synth_genotypes(42, 0.01, 0, args.samples, 0, args.sites)
     info = ckio.write_input_dir(os.path.join(tmp, "in"), g, num_files=args.files)
     gen_s = time.perf_counter() - t0
     in_bytes = sum(os.path.getsize(os.path.join(tmp, "in", f)) for f in os.listdir(os.path.join(tmp, "in"))
                    if f.endswith(".parquet"))
-    t0 = time.perf_counter()
-    p = subprocess.run([os.path.join(ROOT, "bin", "cuking"), f"--input_uri={tmp}/in", f"--output_uri={tmp}/out",
-                        f"--kin_threshold={args.threshold}", f"--num_reader_threads={args.threads}"],
-                       capture_output=True, text=True)
-    wall = time.perf_counter() - t0
-    if p.returncode != 0:
-        sys.exit(p.stderr)
-    phases = dict(re.findall(r"^(Reading metadata|Initializing CUDA|Allocating memory for bit set|Listing input files|Processing Parquet tables|"
-                             r"Running KING CUDA kernel[^.]*|Processing \d+ results)\.\.\..*\(([^;)]+)", p.stdout, re.M))
-    rows = ckio.read_output_dir(os.path.join(tmp, "out")).num_rows
     with ck.Context(0) as ctx, ctx.planes(ck.submatrix(args.samples), args.sites) as pl:
         pl.synthesize(42, 0.01)
         want = len(pl.king(args.threshold, 10 << 20))
-    assert rows == want, (rows, want)
-    print(json.dumps({"tool": "cli_bench", "samples": args.samples, "sites": args.sites, "triples": info["num_triples"],
-                      "parquet_bytes": in_bytes, "files": args.files, "reader_threads": args.threads,
-                      "generate_input_s": round(gen_s, 2), "cuking_wall_s": round(wall, 3), "phases": phases,
-                      "triples_per_s_end_to_end": info["num_triples"] / wall, "retained_pairs": rows}))
+    for gpus in [int(x) for x in args.num_gpus.split(",")]:
+        out = f"{tmp}/out{gpus}"
+        cmd = [os.path.join(ROOT, "bin", "cuking"), f"--input_uri={tmp}/in", f"--output_uri={out}",
+               f"--kin_threshold={args.threshold}", f"--num_reader_threads={args.threads}", f"--num_gpus={gpus}"]
+        if args.split_factor > 1:
+            cmd += [f"--split_factor={args.split_factor}", "--all_shards", "--write_success_file"]
+        t0 = time.perf_counter()
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        wall = time.perf_counter() - t0
+        if p.returncode != 0:
+            sys.exit(p.stderr)
+        phases = dict(re.findall(r"^(Reading metadata|Initializing CUDA|Allocating memory for bit set|Listing input files|Processing Parquet tables|"
+                                 r"Exchanging bit sets[^.]*|Computed [^(]*)(?:\.\.\.)?.*\(([^;)]+)\)$", p.stdout, re.M))
+        kernels = re.findall(r"^Running KING CUDA kernel for (.*?)\.\.\. \(([^;]+); kernel ([0-9.e+]+) ms on GPU (\d+)\)", p.stdout, re.M)
+        rows = ckio.read_output_dir(out, allow_row_groups=True).num_rows
+        assert rows == want, (rows, want)
+        decode_s = None
+        m = re.search(r"Processing Parquet tables\.\.\..* entries \(([0-9.]+)(ms|s)\)", p.stdout)
+        if m:
+            decode_s = float(m.group(1)) * (1e-3 if m.group(2) == "ms" else 1.0)
+        print(json.dumps({"tool": "cli_bench", "samples": args.samples, "sites": args.sites, "triples": info["num_triples"],
+                          "parquet_bytes": in_bytes, "files": args.files, "reader_threads": args.threads, "num_gpus": gpus,
+                          "split_factor": args.split_factor, "generate_input_s": round(gen_s, 2), "cuking_wall_s": round(wall, 3),
+                          "phases": phases, "kernels": [{"what": k[0], "wall": k[1], "kernel_ms": float(k[2]), "gpu": int(k[3])} for k in kernels],
+                          "triples_per_s_end_to_end": info["num_triples"] / wall,
+                          "triples_per_s_decode_and_pack": (info["num_triples"] / decode_s) if decode_s else None,
+                          "retained_pairs": rows}), flush=True)
