@@ -274,6 +274,8 @@ uint64_t king_fp4_num_tiles(const KingLaunch &k);
 cudaError_t launch_king_fp4(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches);
 // king_fp4_pair_kernel.cu (variant 4: the same on CTA pairs, tcgen05 cta_group::2, 256 x 80 tiles sharing the B operand)
 cudaError_t launch_king_fp4_pair(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches);
+uint64_t king_fp4_pair_num_tiles(const KingLaunch &k);
+constexpr uint32_t kPairTileCols = 64;  // 256 x 64 pair tiles
 // band table of this launch geometry for the mxf4 kernel's tile shape (band_prepare)
 cudaError_t king_fp4_prepare(const KingLaunch &k, ck_ctx *ctx, cudaStream_t s, std::vector<uint64_t> *band_prefix);
 constexpr uint32_t kFp4BandRows = kBandRowTiles * kBandTileRows;

@@ -97,8 +97,12 @@ int sort_results(ck_ctx *ctx, const ck_result *in, size_t n, ck_result *out, con
   return CK_OK;
 }
 
+// tile width the band table of a tensor-core variant is built for
+uint32_t variant_tile_cols(int variant) { return variant == 4 ? kPairTileCols : kBandTileCols; }
+
 uint64_t variant_num_tiles(int variant, const KingLaunch &k) {
-  if (variant >= 3) return king_fp4_num_tiles(k);
+  if (variant == 4) return king_fp4_pair_num_tiles(k);
+  if (variant == 3) return king_fp4_num_tiles(k);
   if (variant == 2) return king_umma_num_tiles(k);
   return king_num_tiles(k.num_row_blocks, k.num_col_blocks, k.triangular != 0);
 }
@@ -473,7 +477,7 @@ int eval_view(ck_planes *pl, const ck_submatrix *view, uint32_t part, uint32_t p
   const auto tp0 = std::chrono::steady_clock::now();
   auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
   std::vector<uint64_t> band_prefix;
-  CK_CUDA(band_prepare(k, kBandTileCols, ctx, s, &band_prefix, nullptr));
+  CK_CUDA(band_prepare(k, variant_tile_cols(variant), ctx, s, &band_prefix, nullptr));
   const uint32_t num_bands = uint32_t(band_prefix.size()) - 1;
   ResultPlan plan;
   rc = plan_output(pl, k, part, parts, thr, max_results, /*allow_dense=*/sort && (dst.sink || !dst.on_device), &plan);
@@ -526,7 +530,7 @@ int stream_begin_impl(ck_planes *pl, float kin_threshold, uint32_t max_results, 
     rc = plan_output(pl, st->k, part_index, num_parts, kin_threshold, max_results, /*allow_dense=*/true, &st->plan);
   }
   if (rc == CK_OK) {
-    cudaError_t e = band_prepare(st->k, kBandTileCols, ctx, ctx->stream, &st->band_prefix, nullptr);
+    cudaError_t e = band_prepare(st->k, variant_tile_cols(variant), ctx, ctx->stream, &st->band_prefix, nullptr);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[0], ctx->stream);
     if (e != cudaSuccess) rc = fail_cuda(e, "ck_king_stream_begin", __FILE__, __LINE__);
   }

@@ -25,20 +25,16 @@ namespace ck {
 
 namespace {
 
-#ifndef CK_FP4_TILE_N  // tile shape experiments: -DCK_FP4_TILE_N=64 -DCK_FP4_SLOTS=6 (profiles/r01_fp4_tuning.md)
-#define CK_FP4_TILE_N 80
-#define CK_FP4_SLOTS 4
-#endif
-constexpr uint32_t kFM = 128, kFN = CK_FP4_TILE_N;  // tile rows (A operand, TMEM lanes) x tile columns (B operand)
-constexpr uint32_t kFSlots = CK_FP4_SLOTS;  // A ring in TMEM: one 64-site step per slot; AS slots form one A stage (barrier pair)
+constexpr uint32_t kFM = 128, kFN = 64;     // rows per CTA (TMEM lanes; the pair tile has 256) x tile columns (B operand)
+constexpr uint32_t kFSlots = 6;             // A ring in TMEM: one 64-site step per slot; AS slots form one A stage (barrier pair)
 constexpr uint32_t kFGroups = 2;            // groups of four A warps; group g fills the A stages with stage % 2 == g
 constexpr uint32_t kFSub = 4;               // B expanders work in sub-stages of 4 steps (register prefetch unit)
 constexpr uint32_t kFLBO = 128;             // bytes between K-adjacent 8x16-byte core matrices
 constexpr uint32_t kFThreads = 512;
-constexpr uint32_t kFAWarps = 8, kFBWarps = (2 * kFN) / 32, kFExpWarps = kFAWarps + kFBWarps;  // 8 + 5 warp slots
-constexpr uint32_t kPN = kFN / 2;                        // B columns a CTA of the pair expands
-constexpr uint32_t kPBThreads = 2 * kPN;                 // two threads per column sample: 80 threads in warps 8, 9, 10
-constexpr uint32_t kPBWarps = (kPBThreads + 31) / 32;    // 3 (warp 10 is half empty); warps 11, 12 only join the epilogue
+constexpr uint32_t kFAWarps = 8, kFBWarpSlots = 5, kFExpWarps = kFAWarps + kFBWarpSlots;  // warps 8-12 are the B side's
+constexpr uint32_t kPN = kFN / 2;                        // B columns a CTA of the pair expands: 32
+constexpr uint32_t kPBThreads = 4 * kPN;                 // FOUR threads per column sample (16 sites of every step each): 128 threads
+constexpr uint32_t kPBWarps = kPBThreads / 32;           // warps 8-11; warp 12 only joins the epilogue
 constexpr uint32_t kFIssuers = 3;           // warps 13, 14, 15: x, y and h MMAs
 constexpr uint32_t kFAPrefetchSteps = 4;    // A register prefetch depth in steps of the group (= 8 steps ahead)
 constexpr uint32_t kFBPrefetch = 2;         // B register prefetch depth in sub-stages (= 8 steps ahead)
@@ -46,17 +42,17 @@ constexpr uint32_t kFColXX = 0, kFColY = kFN, kFColH = 3 * kFN;  // accumulators
 constexpr uint32_t kFColA = 5 * kFN;        // A ring: slot s at kFColA + 24 s: x, y, h (8 columns = 64 E2M1 each)
 constexpr uint32_t kFColSF = kFColA + 24 * kFSlots;  // 16 columns of scale factors
 constexpr uint32_t kFTmemCols = 512;
-static_assert(kFBWarps * 32 == 2 * kFN, "two threads per column sample must fill whole warps");
+static_assert(kPairTileCols == kFN, "band table width");
 static_assert(kFColSF + 16 <= kFTmemCols, "TMEM budget");
-static_assert(kFM == kBandTileRows && (kFN == kBandTileCols || CK_FP4_TILE_N != 80), "band enumeration tile shape");
-static_assert(kChunkWords % (2 * kFGroups * kFAPrefetchSteps) == 0 && kChunkWords % (2 * kFSub * kFBPrefetch) == 0, "loop unrolling");
+static_assert(kFM == kBandTileRows, "band enumeration tile shape");
+static_assert(kChunkWords % (2 * kFSub * kFBPrefetch) == 0, "loop unrolling");
 
 template <uint32_t AS, uint32_t BS, uint32_t NS>
 struct Fp4Geo {
   static_assert(BS % kFSub == 0 && BS % AS == 0 && kFSlots % AS == 0 && (AS == 1 || AS == 2), "stage geometry");
   static constexpr uint32_t kAStages = kFSlots / AS;        // A stages in the TMEM ring
   static constexpr uint32_t kSBO = BS * 2 * kFLBO;          // a stage holds 32 K-bytes (64 sites) per step
-  static constexpr uint32_t kTile = (kPN / 8) * kSBO;       // one B operand plane (this CTA's 40 columns) of one stage
+  static constexpr uint32_t kTile = (kPN / 8) * kSBO;       // one B operand plane (this CTA's 32 columns) of one stage
   static constexpr uint32_t kStageBytes = 3 * kTile;
   static constexpr size_t kSmem = size_t(NS) * kStageBytes + 1024;  // + alignment slack
 };
@@ -123,9 +119,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
 }
 
 #ifdef CK_UMMA_PROFILE
-__device__ unsigned long long g_fp4_pair_prof[16];
+__device__ unsigned long long g_fp4_pair_prof[32];  // [16 * cluster rank + slot], first cluster only
 #define FPROF_T() clock64()
-#define FPROF_ADD(slot, dt) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_fp4_pair_prof[slot], (unsigned long long)(dt)); } while (0)
+#define FPROF_ADD(slot, dt) do { if (blockIdx.x < 2 && lane == 0) atomicAdd(&g_fp4_pair_prof[16 * blockIdx.x + (slot)], (unsigned long long)(dt)); } while (0)
 #else
 #define FPROF_T() 0ull
 #define FPROF_ADD(slot, dt) do { (void)(dt); } while (0)
@@ -135,6 +131,9 @@ __device__ unsigned long long g_fp4_pair_prof[16];
 // expansion below the barrier wait that follows, i.e. onto the critical path of the A-slot refill.
 __device__ __forceinline__ void pin8(const uint32_t (&v)[8]) {
   asm volatile("" ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
+}
+__device__ __forceinline__ void sts64(uint32_t saddr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ void expand_fp4(uint32_t z, uint32_t &x, uint32_t &y, uint32_t &h) {
   x = z & 0xAAAAAAAAu;  // +1 hom-alt (0x2), -1 hom-ref (0xA)
@@ -278,20 +277,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1) king_f
     // this CTA's half of the tile's columns: [rank * 40, rank * 40 + 40); threads beyond 2 x 40 idle along (warp 10's upper half,
     // warps 11 and 12) and only keep the warp-level synchronisation well formed
     const uint32_t idx = tid - kFAWarps * 32;
-    const bool b_active = idx < kPBThreads;
-    const uint32_t half = b_active ? idx / kPN : 0u, srow = b_active ? idx % kPN : 0u;  // half: K bytes 16*half .. 16*half+15 of every step
-    const uint32_t col = rank * kPN + srow;                                               // column inside the 80-column tile
+    // idx = (half, srow, quarter): adjacent lanes hold the two 8-byte halves of one 16-byte code word, so a warp's loads are
+    // one contiguous 256-byte run and its stores fill whole 16-byte core-matrix rows
+    const uint32_t quarter = idx & 1u, srow = (idx >> 1) % kPN, half = idx / (2 * kPN);  // half: K bytes 16*half .. 16*half+15 of every step
+    const uint32_t col = rank * kPN + srow;                                              // column inside the 64-column tile
     const uint32_t slot = p.col_slot0 + col0 + (col < cols_here ? col : 0u);  // see the A expanders
     const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
-    const uint4 *src = reinterpret_cast<const uint4 *>(p.codes) + (size_t(blk) * p.words + half) * kTileSamples + ln;
-    const uint32_t b_off = (srow >> 3) * G::kSBO + (srow & 7) * 16 + half * kFLBO;
+    const uint2 *src = reinterpret_cast<const uint2 *>(p.codes) + ((size_t(blk) * p.words + half) * kTileSamples + ln) * 2 + quarter;
+    const uint32_t b_off = (srow >> 3) * G::kSBO + (srow & 7) * 16 + half * kFLBO + quarter * 8;
     const uint32_t num_subs = num_steps / kFSub;
     const uint32_t smem_base = smem_u32(smem);
     constexpr uint32_t kSubsPerStage = BS / kFSub;
-    uint4 z[kFBPrefetch][kFSub];
-    auto load_sub = [&](uint32_t m, uint4 (&dst)[kFSub]) {
+    uint2 z[kFBPrefetch][kFSub];
+    auto load_sub = [&](uint32_t m, uint2 (&dst)[kFSub]) {
 #pragma unroll
-      for (uint32_t q = 0; q < kFSub; ++q) dst[q] = __ldg(src + size_t(min(m, num_subs - 1) * kFSub + q) * (2 * kTileSamples));
+      for (uint32_t q = 0; q < kFSub; ++q) dst[q] = __ldg(src + size_t(min(m, num_subs - 1) * kFSub + q) * (2 * kTileSamples * 2));
     };
 #pragma unroll
     for (uint32_t u = 0; u < kFBPrefetch; ++u) load_sub(u, z[u]);
@@ -301,27 +301,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1) king_f
         const uint32_t m = m0 + u;
         const uint32_t st = m / kSubsPerStage, sub = m % kSubsPerStage;  // stage counter, sub-stage inside it
         const uint32_t s = st % NS, fill = st / NS;
-        uint32_t x[kFSub][4], y[kFSub][4], h[kFSub][4];
+        uint32_t x[kFSub][2], y[kFSub][2], h[kFSub][2];
         const unsigned long long p0 = FPROF_T();
 #pragma unroll
         for (uint32_t q = 0; q < kFSub; ++q) {
           expand_fp4(z[u][q].x, x[q][0], y[q][0], h[q][0]);
           expand_fp4(z[u][q].y, x[q][1], y[q][1], h[q][1]);
-          expand_fp4(z[u][q].z, x[q][2], y[q][2], h[q][2]);
-          expand_fp4(z[u][q].w, x[q][3], y[q][3], h[q][3]);
         }
         load_sub(m + kFBPrefetch, z[u]);
         const unsigned long long p1 = FPROF_T();
         if (sub == 0 && fill > 0) mbar_wait_suspend(&empty_b[s], (fill - 1) & 1u);  // the MMAs that read this stage have completed
         const unsigned long long p2 = FPROF_T();
         const uint32_t stage = smem_base + s * G::kStageBytes + b_off + sub * kFSub * 2 * kFLBO;
-        if (b_active) {
 #pragma unroll
-          for (uint32_t q = 0; q < kFSub; ++q) {
-            sts128(stage + q * 2 * kFLBO, x[q][0], x[q][1], x[q][2], x[q][3]);
-            sts128(stage + G::kTile + q * 2 * kFLBO, y[q][0], y[q][1], y[q][2], y[q][3]);
-            sts128(stage + 2 * G::kTile + q * 2 * kFLBO, h[q][0], h[q][1], h[q][2], h[q][3]);
-          }
+        for (uint32_t q = 0; q < kFSub; ++q) {
+          sts64(stage + q * 2 * kFLBO, x[q][0], x[q][1]);
+          sts64(stage + G::kTile + q * 2 * kFLBO, y[q][0], y[q][1]);
+          sts64(stage + 2 * G::kTile + q * 2 * kFLBO, h[q][0], h[q][1]);
         }
         if (sub == kSubsPerStage - 1) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (tensor core)
@@ -431,10 +427,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1) king_f
       }
       emit_pair(p, pair, cand, gi, gj, kin, opp, conc, both_het, shared);
     };
-    constexpr uint32_t kColsPerGroup = kFN / 4;  // 20
-    static_assert(kColsPerGroup == 20 && kPN == 2 * kColsPerGroup, "epilogue column split");
+    constexpr uint32_t kColsPerGroup = kFN / 4;  // 16
+    static_assert(kColsPerGroup == 16 && kPN == 2 * kColsPerGroup, "epilogue column split");
     const uint32_t c0 = group * kColsPerGroup;
-    // stacked accumulators: columns [yy(0-39) | yh(0-39) | yy(40-79) | yh(40-79)] (the leader's B rows, then the peer's)
+    // stacked accumulators: columns [yy(0-31) | yh(0-31) | yy(32-63) | yh(32-63)] (the leader's B rows, then the peer's)
     const uint32_t bhalf = c0 / kPN, cc = c0 % kPN;
     const uint32_t o_yy = kFColY + bhalf * 2 * kPN + cc, o_yh = o_yy + kPN, o_hy = kFColH + bhalf * 2 * kPN + cc, o_hh = o_hy + kPN;
     {
@@ -448,17 +444,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1) king_f
 #pragma unroll
       for (uint32_t q = 0; q < 16; ++q) finish(c0 + q, xx[q], yy[q], yh[q], hy[q], hh[q]);
     }
-    {
-      uint32_t xx[4], yy[4], yh[4], hy[4], hh[4];
-      tmem_load4(lane_base + kFColXX + c0 + 16, xx);
-      tmem_load4(lane_base + o_yy + 16, yy);
-      tmem_load4(lane_base + o_yh + 16, yh);
-      tmem_load4(lane_base + o_hy + 16, hy);
-      tmem_load4(lane_base + o_hh + 16, hh);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (uint32_t q = 0; q < 4; ++q) finish(c0 + 16 + q, xx[q], yy[q], yh[q], hy[q], hh[q]);
-    }
     if (tid == 0) FPROF_ADD(14, FPROF_T() - t_main);
   }
   tcgen05_before_sync();
@@ -471,22 +456,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1) king_f
 
 }  // namespace
 
+#ifdef CK_UMMA_PROFILE
+extern "C" void ck_debug_fp4_pair_prof(unsigned long long *out) {
+  cudaMemcpyFromSymbol(out, g_fp4_pair_prof, sizeof(g_fp4_pair_prof));
+  unsigned long long z[32] = {0};
+  cudaMemcpyToSymbol(g_fp4_pair_prof, z, sizeof(z));
+}
+#endif
+
+uint64_t king_fp4_pair_num_tiles(const KingLaunch &k) { return band_num_tiles(k, kPairTileCols); }
+
 cudaError_t launch_king_fp4_pair(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches) {
   (void)total_blocks;
   if (k.tile_end <= k.tile_begin) return cudaSuccess;
   if ((k.tile_begin | k.tile_end) & 1ull) return cudaErrorInvalidValue;  // tile ranges of whole bands are even (band_tiles.cu)
   BandTiles tiles{};
-  cudaError_t e = band_prepare(k, kFN, ctx, s, nullptr, &tiles);
+  cudaError_t e = band_prepare(k, kPairTileCols, ctx, s, nullptr, &tiles);
   if (e != cudaSuccess) return e;
-  using G = Fp4Geo<2, 8, 3>;
-  static std::atomic<uint64_t> configured{0};  // one bit per device
-  if ((e = optin_dynamic_smem(king_fp4_pair_kernel<2, 8, 3>, G::kSmem, configured)) != cudaSuccess) return e;
+  static const int as = [] { const char *v = getenv("CUKING_PAIR_AS"); return v ? atoi(v) : 2; }();  // steps per A stage (tuning knob)
+  static std::atomic<uint64_t> configured[2] = {{0}, {0}};  // one bit per device
+  if ((e = optin_dynamic_smem(king_fp4_pair_kernel<2, 8, 3>, Fp4Geo<2, 8, 3>::kSmem, configured[0])) != cudaSuccess) return e;
+  if ((e = optin_dynamic_smem(king_fp4_pair_kernel<1, 8, 3>, Fp4Geo<1, 8, 3>::kSmem, configured[1])) != cudaSuccess) return e;
   constexpr uint64_t kMaxGrid = 1ull << 30;
   for (uint64_t t = k.tile_begin; e == cudaSuccess && t < k.tile_end; t += kMaxGrid) {
     KingLaunch part = k;
     part.tile_begin = t;
     part.tile_end = (t + kMaxGrid < k.tile_end) ? t + kMaxGrid : k.tile_end;
-    king_fp4_pair_kernel<2, 8, 3><<<unsigned(part.tile_end - part.tile_begin), kFThreads, G::kSmem, s>>>(part, tiles);
+    if (as == 1) king_fp4_pair_kernel<1, 8, 3><<<unsigned(part.tile_end - part.tile_begin), kFThreads, Fp4Geo<1, 8, 3>::kSmem, s>>>(part, tiles);
+    else king_fp4_pair_kernel<2, 8, 3><<<unsigned(part.tile_end - part.tile_begin), kFThreads, Fp4Geo<2, 8, 3>::kSmem, s>>>(part, tiles);
     e = cudaGetLastError();
     if (launches) ++*launches;
   }
