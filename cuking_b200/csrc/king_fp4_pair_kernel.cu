@@ -1,15 +1,17 @@
-// CTA-pair form of the mxf4 pairwise kernel (king_fp4_kernel.cu): tcgen05.mma.cta_group::2 over a 256 x 80 tile held by
-// the two SMs of a cluster.  Variant 4 (experimental; same records as every other variant).
+// CTA-pair form of the mxf4 pairwise kernel (king_fp4_kernel.cu): tcgen05.mma.cta_group::2 over a 256 x 64 tile held by
+// the two SMs of a cluster.  Variant 4 - experimental: same records as every other variant, slower than variant 3 today
+// (profiles/r02_pair_kernel.md has the measurements and the analysis).
 //
-// Each CTA of the pair owns 128 rows: its A operands (TMEM ring) and its accumulators are exactly those of the single-CTA
-// kernel.  The B operand is SHARED: each CTA expands only 40 of the tile's 80 column samples into its own shared memory
-// and the pair instruction reads rows [0, N/2) of B from the leader's shared memory and [N/2, N) from its peer's (measured
-// by tools/umma_pair_probe.cu), so B expansion, B stores and B reads per SM halve - shared memory was 74 % busy in the
-// single-CTA kernel, next to the tensor core's own operand reads.  Only the leader's issuer lanes issue MMAs; their
-// commits are multicast to the barriers of both CTAs; the peer's expander warps announce their operands on the LEADER's
-// barriers (remote mbarrier arrive at cluster scope).  Stacked B for the y / h streams: a CTA's shared memory holds
-// [y(40 columns) ; h(40 columns)], hence the accumulator columns of D_y and D_h are [yy(0-39) | yh(0-39) | yy(40-79) |
-// yh(40-79)] - the epilogue undoes that.
+// Each CTA of the pair owns 128 rows: its A operands (a 6-slot TMEM ring, three stages of two 64-site steps) and its
+// accumulators (5 x 64 columns).  The B operand is SHARED: each CTA expands only 32 of the tile's 64 column samples into
+// its own shared memory (four threads per column, 16 sites of every step each) and the pair instruction reads rows
+// [0, N/2) of B from the leader's shared memory and [N/2, N) from its peer's (measured by tools/umma_pair_probe.cu), so B
+// expansion, B stores and B reads per SM halve - shared memory was 74 % busy in the single-CTA kernel.  Only the leader's
+// issuer lanes issue MMAs; their commits are multicast to the barriers of both CTAs; the peer's expander warps announce
+// their operands on the LEADER's barriers (remote mbarrier arrive, the form CUTLASS' ClusterBarrier uses).  Stacked B for
+// the y / h streams: a CTA's shared memory holds [y(32 columns) ; h(32 columns)], hence the accumulator columns of D_y and
+// D_h are [yy(0-31) | yh(0-31) | yy(32-63) | yh(32-63)] - the epilogue undoes that.  Tiles: consecutive linear tiles
+// (2m, 2m + 1) of the band enumeration are the two halves of a pair tile (bands are padded to even row-tile counts).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -273,9 +275,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1) king_f
       }
     }
   } else if (warp < kFAWarps + kPBWarps) {
-    // ===== B expanders: two threads per column sample (32 sites of every step each), BS steps per stage =====
-    // this CTA's half of the tile's columns: [rank * 40, rank * 40 + 40); threads beyond 2 x 40 idle along (warp 10's upper half,
-    // warps 11 and 12) and only keep the warp-level synchronisation well formed
+    // ===== B expanders: four threads per column sample (16 sites of every step each), BS steps per stage; this CTA's half of
+    // the tile's columns: [rank * 32, rank * 32 + 32) =====
     const uint32_t idx = tid - kFAWarps * 32;
     // idx = (half, srow, quarter): adjacent lanes hold the two 8-byte halves of one 16-byte code word, so a warp's loads are
     // one contiguous 256-byte run and its stores fill whole 16-byte core-matrix rows

@@ -142,6 +142,31 @@ extern "C" int ck_measure_fp4_peak(ck_ctx *ctx, double *ops_per_s) {
   return CK_OK;
 }
 
+extern "C" int ck_measure_fp4_peak_sustained(ck_ctx *ctx, double seconds, double *ops_per_s) {
+  using namespace ck;
+  if (!ctx || !ops_per_s || !(seconds > 0.0) || seconds > 30.0) return fail(CK_ERR_INVALID_ARGUMENT, "bad argument");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = ctx->stream;
+  // one launch takes about 2.3 ms; run them back to back for `seconds` and time the second half, when the board has
+  // settled at whatever clock its power limit allows under a saturated tensor pipe
+  CK_CUDA(cudaEventRecord(ctx->ev[0], s));
+  fp4_rate_kernel<<<ctx->num_sms, 128, 0, s>>>(kRateSteps);
+  CK_CUDA(cudaEventRecord(ctx->ev[1], s));
+  CK_CUDA(cudaEventSynchronize(ctx->ev[1]));
+  const double one_ms = std::max(0.1, double(elapsed_ms(ctx->ev[0], ctx->ev[1])));
+  const int launches = std::max(8, int(seconds * 1e3 / one_ms)), half = launches / 2;
+  for (int i = 0; i < launches; ++i) {
+    if (i == half) CK_CUDA(cudaEventRecord(ctx->ev[0], s));
+    fp4_rate_kernel<<<ctx->num_sms, 128, 0, s>>>(kRateSteps);
+  }
+  CK_CUDA(cudaGetLastError());
+  CK_CUDA(cudaEventRecord(ctx->ev[1], s));
+  CK_CUDA(cudaEventSynchronize(ctx->ev[1]));
+  const double ms = elapsed_ms(ctx->ev[0], ctx->ev[1]);
+  *ops_per_s = 2.0 * 2.0 * 128.0 * kRateN * 64.0 * double(kRateSteps) * ctx->num_sms * double(launches - half) / (ms * 1e-3);
+  return CK_OK;
+}
+
 extern "C" int ck_measure_int_peaks(ck_ctx *ctx, double *popc_lane_ops_per_s, double *lop3_lane_ops_per_s) {
   using namespace ck;
   if (!ctx || !popc_lane_ops_per_s || !lop3_lane_ops_per_s) return fail(CK_ERR_INVALID_ARGUMENT, "NULL argument");

@@ -119,6 +119,12 @@ class Context:
         check(self._lib.ck_measure_fp4_peak(self._h, C.byref(v)))
         return v.value
 
+    def measure_fp4_peak_sustained(self, seconds: float = 2.0) -> float:
+        """The same rate sustained for `seconds` (second half timed): the board's power-limited clock included."""
+        v = C.c_double()
+        check(self._lib.ck_measure_fp4_peak_sustained(self._h, C.c_double(seconds), C.byref(v)))
+        return v.value
+
     def planes(self, sm: Submatrix, num_sites: int) -> "Planes":
         return Planes(self, sm, num_sites)
 

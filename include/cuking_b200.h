@@ -122,8 +122,9 @@ int ck_ctx_set_stream(ck_ctx *ctx, void *cuda_stream);
 /* Pairwise kernel variant: 0 = LOP3 + 5 POPC per pair and 32 sites, 1 = carry-save (2.5 POPC + 5 more LOP3),
  * 2 = tcgen05 int8 tensor-core formulation (five exact s32 GEMMs of indicator vectors), 3 = the same five GEMMs on
  * the FP4 tensor path (kind::mxf4 E2M1 operands, unit block scales, fp32 accumulation - exact for counts <= 2^23; planes
- * with more than 2^23 sites are routed to variant 2), -1 = library default (= 3; also settable with the
- * CUKING_KING_VARIANT environment variable).  Results are bit-identical across variants. */
+ * with more than 2^23 sites are routed to variant 2), 4 = variant 3 on CTA pairs (tcgen05 cta_group::2, 256-row tiles
+ * sharing the B operand; experimental, slower today: profiles/r02_pair_kernel.md), -1 = library default (= 3; also
+ * settable with the CUKING_KING_VARIANT environment variable).  Results are bit-identical across variants. */
 int ck_ctx_set_king_variant(ck_ctx *ctx, int variant);
 /* Variant 3 relies on the tensor core adding E2M1 products into its fp32 accumulator without losing low bits, which the
  * PTX ISA does not spell out.  The first use of variant 3 on a ctx therefore runs an on-device self-test (about a
@@ -143,6 +144,10 @@ int ck_measure_int_peaks(ck_ctx *ctx, double *popc_lane_ops_per_s, double *lop3_
  * is what bounds pairwise kernel variant 3 (10 fp4 ops per pair-site); bench.py quotes its roofline against it because
  * MEASURED_PEAKS.json holds no fp4 figure. */
 int ck_measure_fp4_peak(ck_ctx *ctx, double *ops_per_s);
+/* The same rate sustained: the kernel is launched back to back for `seconds` (0 < seconds <= 30) and the second half is
+ * timed, i.e. at the clock the board settles at under its power limit with a saturated tensor pipe - the denominator
+ * for a pairwise pass that itself runs for a second or longer. */
+int ck_measure_fp4_peak_sustained(ck_ctx *ctx, double seconds, double *ops_per_s);
 int ck_ctx_destroy(ck_ctx *ctx);
 
 /* ---- planes: replaces the managed bit_set of cuking.cu:513-523 --------------------------------------------- */

@@ -87,6 +87,29 @@ def test_view_validation(ctx):
         assert_results_equal(pl.king_view(None, 0.0, 1 << 16), oracle_shard(g, 200, 2, 1, 0.0))
 
 
+def test_cta_pair_kernel_variant_matches_oracle(ctx):
+    # variant 4: the mxf4 kernel on CTA pairs (tcgen05 cta_group::2, 256 x 64 tiles sharing the B operand); odd and even
+    # numbers of 128-row tiles, ragged edges, off-diagonal shards, views, parts, dense output
+    rng = np.random.default_rng(44)
+    ctx.set_king_variant(4)
+    try:
+        for n, s in [(129, 333), (300, 1999), (1100, 700)]:
+            g = random_genotypes(rng, n, s)
+            for k, shard in [(1, 0), (2, 1), (3, 4)]:
+                with packed(ctx, g, ck.submatrix(n, k, shard)) as pl:
+                    assert pl.king_variant() == 4
+                    for thr in (0.03, -1.0):
+                        assert_results_equal(pl.king(thr, 1 << 21), oracle_shard(g, n, k, shard, thr))
+        g = random_genotypes(rng, 2600, 260)
+        with packed(ctx, g, ck.submatrix(2600)) as pl:
+            for shard in range(3):
+                parts = [pl.king_view(ck.submatrix(2600, 2, shard), 0.05, 1 << 21, part=(p, 3)).copy() for p in range(3)]
+                got = np.sort(np.concatenate(parts), order=["sample_i", "sample_j"])
+                assert_results_equal(got, oracle_shard(g, 2600, 2, shard, 0.05))
+    finally:
+        ctx.set_king_variant(-1)
+
+
 # ---- parts ---------------------------------------------------------------------------------------------------------
 
 
