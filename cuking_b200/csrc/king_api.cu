@@ -431,7 +431,7 @@ int finish_dense(ck_ctx *ctx, ResultPlan &plan, const Dest &dst, uint64_t *num_r
 
 bool host_bitset_can_pipeline(const ck_planes *pl) {
   static const bool off = getenv("CUKING_NO_PIPELINE") != nullptr;
-  return !off && planes_variant(pl) >= 2 && sm_diagonal(pl->map.sm) && sm_rows(pl->map.sm) >= 4 * kFp4BandRows;
+  return !off && planes_variant(pl) >= 2 && sm_rows(pl->map.sm) >= 4 * kFp4BandRows;
 }
 
 // One evaluation: the planes' sub-matrix or a view of it, one part of num_parts, into a buffer or a sink.
@@ -505,10 +505,11 @@ int eval_view(ck_planes *pl, const ck_submatrix *view, uint32_t part, uint32_t p
   return finish_sparse(ctx, ctx->result_buf, max_results, dst, num_results, sort);
 }
 
-int stream_begin_impl(ck_planes *pl, float kin_threshold, uint32_t max_results, uint32_t part_index, uint32_t num_parts) {
+int stream_begin_impl(ck_planes *pl, float kin_threshold, uint32_t max_results, uint32_t part_index, uint32_t num_parts,
+                      bool allow_rect = false) {
   ck_ctx *ctx = pl->ctx;
   if (num_parts == 0 || part_index >= num_parts) return fail(CK_ERR_INVALID_ARGUMENT, "part_index outside [0, num_parts)");
-  if (!sm_diagonal(pl->map.sm)) return fail(CK_ERR_INVALID_ARGUMENT, "streaming delivery needs a diagonal shard");
+  if (!sm_diagonal(pl->map.sm) && !allow_rect) return fail(CK_ERR_INVALID_ARGUMENT, "streaming delivery needs a diagonal shard");
   const int variant = planes_variant(pl);
   if (variant < 2) return fail(CK_ERR_INVALID_ARGUMENT, "streaming delivery needs a tensor-core kernel variant (2 or 3): their band-ordered tiles");
   if (pl->stream_state) return fail(CK_ERR_INVALID_ARGUMENT, "a stream session is already open on these planes");
@@ -597,20 +598,24 @@ int stream_end_impl(ck_planes *pl, ck_result *results, uint64_t *num_results) {
   return finish_sparse(ctx, ctx->result_buf, max_results, dst, num_results, 1);
 }
 
-// ck_king_host_bitset on a diagonal shard with a tensor-core kernel: the upload of the reference-layout bit set overlaps
-// the pairwise kernel instead of preceding it.  A band of the tile enumeration (kFp4BandRows rows) only needs the
-// samples at or after its first row (i < j), so the sample range is uploaded LAST CHUNK FIRST on the copy stream and
-// every chunk's bands are launched as soon as its rows have been transposed and coded - by then every column they
-// pair with is already on the device.  The bottom chunks hold few tiles, so only the first small upload is exposed.
+// ck_king_host_bitset with a tensor-core kernel: the upload of the reference-layout bit set overlaps the pairwise kernel
+// instead of preceding it.  Diagonal shard: a band of the tile enumeration (kFp4BandRows rows) only needs the samples at
+// or after its first row (i < j), so the sample range is uploaded LAST CHUNK FIRST on the copy stream and every chunk's
+// bands are launched as soon as its rows have been transposed and coded - by then every column they pair with is
+// already on the device; the bottom chunks hold few tiles, so only the first small upload is exposed.  Off-diagonal
+// shard: every band needs all the column samples, so those go first (one piece, exposed) and the row samples follow in
+// chunks behind the kernels of the chunks before them - half of the upload is hidden.
 int king_host_bitset_pipelined(ck_planes *pl, const uint64_t *bit_set, float kin_threshold, uint32_t max_results,
                                ck_result *results, uint64_t *num_results, uint32_t part_index, uint32_t num_parts) {
   *num_results = 0;
   ck_ctx *ctx = pl->ctx;
   DeviceGuard guard(ctx->device);
   cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
-  const uint32_t n = sm_rows(pl->map.sm);
+  const ck_submatrix &sm = pl->map.sm;
+  const bool rect = !sm_diagonal(sm);
+  const uint32_t n = sm_rows(sm);
   const size_t words_per_sample = ref_words_per_sample(pl->num_sites);  // u64
-  const size_t bytes = words_per_sample * n * 8;
+  const size_t bytes = words_per_sample * sm_samples(sm) * 8;
   struct Staging {  // device copy of the host bit set, returned to the ctx cache on scope exit
     ck_ctx *ctx;
     void *p = nullptr;
@@ -623,8 +628,13 @@ int king_host_bitset_pipelined(ck_planes *pl, const uint64_t *bit_set, float kin
   } st{ctx};
   CK_CUDA(ctx_alloc(ctx, &st.p, bytes));
   st.bytes = bytes;
-  int rc = stream_begin_impl(pl, kin_threshold, max_results, part_index, num_parts);
+  int rc = stream_begin_impl(pl, kin_threshold, max_results, part_index, num_parts, /*allow_rect=*/true);
   if (rc != CK_OK) return rc;
+  auto abandon = [&](int code) {
+    cudaStreamSynchronize(cs);
+    stream_discard(pl);
+    return code;
+  };
   const uint32_t num_bands = ceil_div(n, kFp4BandRows);
   const uint32_t chunk_bands = std::max<uint32_t>(1, ceil_div(num_bands, 24u));
 
@@ -634,6 +644,21 @@ int king_host_bitset_pipelined(ck_planes *pl, const uint64_t *bit_set, float kin
   st.events.push_back(fork);
   CK_CUDA(cudaEventRecord(fork, s));
   CK_CUDA(cudaStreamWaitEvent(cs, fork, 0));
+  uint64_t *d_bits = static_cast<uint64_t *>(st.p);
+  if (rect) {  // the column samples: reference slots [rows, rows + cols), plane blocks from col_slot0 on
+    const size_t off = size_t(n) * words_per_sample;
+    cudaEvent_t cols_ready;
+    CK_CUDA(cudaEventCreateWithFlags(&cols_ready, cudaEventDisableTiming));
+    st.events.push_back(cols_ready);
+    cudaError_t e = cudaMemcpyAsync(d_bits + off, bit_set + off, size_t(sm_cols(sm)) * words_per_sample * 8, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) e = cudaEventRecord(cols_ready, cs);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, cols_ready, 0);
+    const uint32_t col_block0 = pl->map.col_slot0 / kTileSamples, col_blocks = ceil_div(sm_cols(sm), kTileSamples);
+    if (e == cudaSuccess) e = launch_import_ref_range(*pl, d_bits + off, n, col_block0, col_blocks, s);
+    if (e == cudaSuccess) e = launch_finalize_codes_range(*pl, pl->stream_state->variant >= 3 ? 3 : pl->stream_state->variant, col_block0, col_blocks, s);
+    if (e != cudaSuccess) return abandon(fail_cuda(e, "column upload", __FILE__, __LINE__));
+    ctx->timings.king_launches += 2;
+  }
   struct Chunk { uint32_t s0, s1; cudaEvent_t ready; };
   std::vector<Chunk> chunks;
   for (uint32_t hi = num_bands; hi > 0;) {
@@ -642,21 +667,16 @@ int king_host_bitset_pipelined(ck_planes *pl, const uint64_t *bit_set, float kin
     CK_CUDA(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
     st.events.push_back(c.ready);
     const size_t off = size_t(c.s0) * words_per_sample;
-    CK_CUDA(cudaMemcpyAsync(static_cast<uint64_t *>(st.p) + off, bit_set + off, size_t(c.s1 - c.s0) * words_per_sample * 8,
-                            cudaMemcpyHostToDevice, cs));
+    CK_CUDA(cudaMemcpyAsync(d_bits + off, bit_set + off, size_t(c.s1 - c.s0) * words_per_sample * 8, cudaMemcpyHostToDevice, cs));
     CK_CUDA(cudaEventRecord(c.ready, cs));
     chunks.push_back(c);
     hi = lo;
   }
   for (const Chunk &c : chunks) {
     cudaError_t e = cudaStreamWaitEvent(s, c.ready, 0);
-    rc = e == cudaSuccess ? stream_rows_device(pl, static_cast<const uint64_t *>(st.p) + size_t(c.s0) * words_per_sample, c.s0, c.s1)
+    rc = e == cudaSuccess ? stream_rows_device(pl, d_bits + size_t(c.s0) * words_per_sample, c.s0, c.s1)
                           : fail_cuda(e, "cudaStreamWaitEvent", __FILE__, __LINE__);
-    if (rc != CK_OK) {
-      cudaStreamSynchronize(cs);
-      stream_discard(pl);
-      return rc;
-    }
+    if (rc != CK_OK) return abandon(rc);
   }
   rc = stream_end_impl(pl, results, num_results);
   ctx->timings.h2d_ms = 0.f;     // overlapped: the whole upload + transpose + kernel span is reported as king_ms

@@ -63,7 +63,20 @@ cudaError_t measure(ck_ctx *ctx, uint32_t *d_out, double *lane_ops_per_s) {
 constexpr uint32_t kRateN = 208, kRateSteps = 20000, kRateKBytes = 128, kRateLBO = 128, kRateSBO = (kRateKBytes / 16) * 128;
 constexpr uint32_t kRateColA = 416, kRateColSF = 480;
 
-__global__ void __launch_bounds__(128) fp4_rate_kernel(uint32_t steps) {
+// genotype-like operand words: eight E2M1 nibbles drawn from {0, 0.5, +1, -1} by a hash of the index
+__device__ __forceinline__ uint32_t rate_operand(uint32_t i, uint32_t random) {
+  if (!random) return 0x22222222u;  // all +1
+  uint32_t w = 0, x = i * 0x9e3779b9u + 0x7f4a7c15u;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    x ^= x >> 15; x *= 0x2c1b3c6du; x ^= x >> 12;
+    const uint32_t c = (x >> 7) & 3u;
+    w |= (c == 0 ? 0x0u : c == 1 ? 0x1u : c == 2 ? 0x2u : 0xAu) << (4 * q);
+  }
+  return w;
+}
+
+__global__ void __launch_bounds__(128) fp4_rate_kernel(uint32_t steps, uint32_t random_operands) {
   __shared__ __align__(1024) uint8_t smem[256 * kRateKBytes];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_smem;
@@ -76,7 +89,7 @@ __global__ void __launch_bounds__(128) fp4_rate_kernel(uint32_t steps) {
     mbar_init(&bar, 2);
     mbar_fence_init();
   }
-  for (uint32_t e = tid; e < 256 * kRateKBytes / 4; e += blockDim.x) reinterpret_cast<uint32_t *>(smem)[e] = 0x22222222u;  // all +1
+  for (uint32_t e = tid; e < 256 * kRateKBytes / 4; e += blockDim.x) reinterpret_cast<uint32_t *>(smem)[e] = rate_operand(e, random_operands);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tcgen05_before_sync();
   __syncthreads();
@@ -87,9 +100,11 @@ __global__ void __launch_bounds__(128) fp4_rate_kernel(uint32_t steps) {
 #pragma unroll
   for (uint32_t q = 0; q < 8; ++q) v[q] = 0x7f7f7f7fu;
   for (uint32_t c = 0; c < 32; c += 8) tmem_store8(lane_base + kRateColSF + c, v);
+  for (uint32_t c = 0; c < 64; c += 8) {
 #pragma unroll
-  for (uint32_t q = 0; q < 8; ++q) v[q] = 0x22222222u;
-  for (uint32_t c = 0; c < 64; c += 8) tmem_store8(lane_base + kRateColA + c, v);
+    for (uint32_t q = 0; q < 8; ++q) v[q] = rate_operand(0x10000u + tid * 64u + c + q, random_operands);
+    tmem_store8(lane_base + kRateColA + c, v);
+  }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   tcgen05_before_sync();
   __syncthreads();
@@ -131,7 +146,7 @@ extern "C" int ck_measure_fp4_peak(ck_ctx *ctx, double *ops_per_s) {
   float best = 1e30f;
   for (int rep = 0; rep < 6; ++rep) {
     CK_CUDA(cudaEventRecord(ctx->ev[0], s));
-    fp4_rate_kernel<<<ctx->num_sms, 128, 0, s>>>(kRateSteps);
+    fp4_rate_kernel<<<ctx->num_sms, 128, 0, s>>>(kRateSteps, 0u);
     CK_CUDA(cudaGetLastError());
     CK_CUDA(cudaEventRecord(ctx->ev[1], s));
     CK_CUDA(cudaEventSynchronize(ctx->ev[1]));
@@ -149,15 +164,16 @@ extern "C" int ck_measure_fp4_peak_sustained(ck_ctx *ctx, double seconds, double
   cudaStream_t s = ctx->stream;
   // one launch takes about 2.3 ms; run them back to back for `seconds` and time the second half, when the board has
   // settled at whatever clock its power limit allows under a saturated tensor pipe
+  // operands are genotype-like random E2M1 values here: the tensor core's power depends on how its operand bits toggle
   CK_CUDA(cudaEventRecord(ctx->ev[0], s));
-  fp4_rate_kernel<<<ctx->num_sms, 128, 0, s>>>(kRateSteps);
+  fp4_rate_kernel<<<ctx->num_sms, 128, 0, s>>>(kRateSteps, 1u);
   CK_CUDA(cudaEventRecord(ctx->ev[1], s));
   CK_CUDA(cudaEventSynchronize(ctx->ev[1]));
   const double one_ms = std::max(0.1, double(elapsed_ms(ctx->ev[0], ctx->ev[1])));
   const int launches = std::max(8, int(seconds * 1e3 / one_ms)), half = launches / 2;
   for (int i = 0; i < launches; ++i) {
     if (i == half) CK_CUDA(cudaEventRecord(ctx->ev[0], s));
-    fp4_rate_kernel<<<ctx->num_sms, 128, 0, s>>>(kRateSteps);
+    fp4_rate_kernel<<<ctx->num_sms, 128, 0, s>>>(kRateSteps, 1u);
   }
   CK_CUDA(cudaGetLastError());
   CK_CUDA(cudaEventRecord(ctx->ev[1], s));

@@ -202,6 +202,26 @@ def test_host_bitset_seam_dense_output(ctx):
         assert_results_equal(np.sort(np.concatenate(parts), order=["sample_i", "sample_j"]), want)
 
 
+def test_host_bitset_seam_off_diagonal_shard_is_pipelined_too(ctx):
+    # off-diagonal shard with >= 4 bands of rows: the column samples are uploaded first, the row samples in chunks behind
+    # the kernels of the chunks before them; parts and dense output included
+    rng = np.random.default_rng(29)
+    n, s = 9100, 120
+    g = random_genotypes(rng, n, s, related_blocks=False)
+    g[4600:4700] = g[100:200]  # duplicates across the two blocks so that the threshold keeps some pairs
+    osm = ko.submatrix(n, 2, 1)
+    assert osm.i_end - osm.i_begin >= 4096
+    bs = oracle_bitset(g, osm)
+    for thr, cap in ((0.2, 1 << 20), (-1.0, 1 << 25)):
+        want, count, _ = ko.king(bs, s, osm, thr, cap)
+        assert count > 50
+        got = ctx.king_host_bitset(n, 2, 1, s, bs, thr, cap)
+        assert_results_equal(got, want)
+    want, _, _ = ko.king(bs, s, osm, 0.2, 1 << 20)
+    parts = [ctx.king_host_bitset(n, 2, 1, s, bs, 0.2, 1 << 20, part=(p, 3)).copy() for p in range(3)]
+    assert_results_equal(np.sort(np.concatenate(parts), order=["sample_i", "sample_j"]), want)
+
+
 # ---- chunked delivery ----------------------------------------------------------------------------------------------
 
 
