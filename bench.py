@@ -706,7 +706,8 @@ def main():
             "warmup_note": w["warmup_note"], "ms_per_step": w["ms_per_step"], "value": w["value"], "unit": UNIT,
             "kernel_ms": w["kernel_ms"], "sort_d2h_ms_exposed": w["sort_d2h_ms"], "ms_per_step_over_kernel_ms": w["ms_per_step"] / w["kernel_ms"],
             "retained_pairs": w["retained_pairs"], "gpu_launches": w["gpu_launches"], "items_on_rank0": w["items_this_rank"],
-            "roofline_frac": r["frac"], "roofline_achieved": r["achieved"], "roofline_peak": r["peak"], "e2e": w["e2e"],
+            "roofline_frac": r["frac"], "roofline_peak_kind": r.get("peak_kind"), "roofline_frac_burst": (r.get("burst") or {}).get("frac"),
+            "roofline_achieved": r["achieved"], "roofline_peak": r["peak"], "e2e": w["e2e"],
             "e2e_note": None if w["e2e"] else "resident inputs only: a pinned host copy of the 25 GB bit set per rank is not staged by the bench",
             "checks": w["checks"], "clocks": w["clocks"], "input_synthesis_s": w["input_synthesis_s"],
         }

@@ -316,6 +316,16 @@ def test_adversarial_accumulation_patterns_through_the_kernel(ctx):
         assert_results_equal(got, want)
 
 
+def test_live_peak_measurements_are_sane(ctx):
+    # the denominators bench.py quotes its rooflines against, measured on this GPU now
+    burst = ctx.measure_fp4_peak()
+    sustained = ctx.measure_fp4_peak_sustained(0.3)
+    ints = ctx.measure_int_peaks()
+    assert 5e15 < burst < 1.1e16, burst              # nominal dense fp4: 9e15 ops/s
+    assert 4e15 < sustained <= burst * 1.02, (sustained, burst)
+    assert 2e12 < ints["popc_lane_ops_per_s"] < 6e12 and ints["lop3_lane_ops_per_s"] > 3 * ints["popc_lane_ops_per_s"]
+
+
 # ---- multi-GPU plane exchange --------------------------------------------------------------------------------------
 
 
