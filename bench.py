@@ -512,11 +512,18 @@ class Bench:
         if k > 1:
             # split_factor run: the cohort's bit set is uploaded and transposed once per step, then this rank's shards are
             # evaluated as views (the reference uploads one bit set per shard process)
-            api = "ck_planes_import_bitset (whole cohort) + ck_king_view per shard"
+            shared_upload = self.world > 1 and args.e2e_mode == "allgather"
+            api = ("ck_planes_import_bitset (whole cohort" + (f": 1/{self.world} upload per GPU + NCCL all-gather" if shared_upload else "")
+                   + ") + ck_king_view per shard")
 
             def e2e_step():
+                from cuking_b200.distributed import import_bitset_allgather
+
                 with ctx.planes(sm, n_sites) as pl:
-                    pl.import_bitset(host_bits)
+                    if shared_upload:
+                        import_bitset_allgather(pl, host_bits, ck.words_per_sample(n_sites))
+                    else:
+                        pl.import_bitset(host_bits)
                     return [pl.king_view(view, thr, max_results, part=(part, parts), out=results).copy()
                             for view, part, parts, _ in items]
         elif allgather:
@@ -550,7 +557,7 @@ class Bench:
         if e2e_checksum != resident_checksum:  # the host-buffer leg must produce exactly the records of the resident leg
             raise SystemExit(f"{name}: e2e leg checksum {e2e_checksum} differs from the resident leg's {resident_checksum}")
         e2e = {"value": total_units / (e_ms / e2e_steps * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d // self.world) if allgather else int(h2d),  # per rank
+               "h2d_bytes_per_step": int(h2d // self.world) if (allgather or (k > 1 and self.world > 1 and args.e2e_mode == "allgather")) else int(h2d),  # per rank
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps,
                "api": api + " (pinned host bit set in the reference layout -> sorted KingResult[] in pinned host memory)"}
         exchange = None

@@ -180,3 +180,34 @@ def king_host_bitset_allgather(planes, host_bits, words_per_sample: int, kin_thr
         ctx.set_stream(prev_stream)
     del stage
     return res
+
+
+def import_bitset_allgather(planes, host_bits, words_per_sample: int, group=None):
+    """Loads a whole-cohort bit set (reference layout, pinned host memory, the same on every rank) into this rank's planes
+    with the upload shared between the ranks: every rank copies 1/G of the samples through its own PCIe link, an NCCL
+    all-gather over NVLink hands every GPU the whole bit set, ck_planes_import_bitset transposes it on the device.  Eight
+    concurrent full uploads are host-limited (bench.py `plane_exchange`); this moves 1/8 of the bytes per link."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    hb = host_bits.view(torch.int64)
+    n = hb.numel() // words_per_sample
+    per = -(-n // world)  # samples per rank, the last ranks may be short or empty
+    dev = torch.device("cuda", torch.cuda.current_device())
+    full = torch.empty(per * world * words_per_sample, dtype=torch.int64, device=dev)
+    b, e = min(rank * per, n), min((rank + 1) * per, n)
+    mine = full[rank * per * words_per_sample: (rank + 1) * per * words_per_sample]
+    ctx = planes.ctx
+    main = torch.cuda.current_stream(dev)
+    prev_stream = ctx.stream
+    ctx.set_stream(main.cuda_stream)  # the import kernels must run behind the copies and the all-gather queued on `main`
+    try:
+        if e > b:
+            mine[: (e - b) * words_per_sample].copy_(hb[b * words_per_sample: e * words_per_sample], non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(full, mine, group=group)
+        planes.import_bitset(full[: n * words_per_sample])
+    finally:
+        ctx.set_stream(prev_stream)
+    del full

@@ -378,6 +378,13 @@ def test_allgather_fed_seam_single_rank(ctx):
                 got = king_host_bitset_allgather(pl, host, ck.words_per_sample(s), 0.1, 1 << 20)
                 assert_results_equal(got, want)
                 assert c3.stream is None  # restored
+            # whole-cohort import with the upload shared between the ranks (here: one)
+            from cuking_b200.distributed import import_bitset_allgather
+
+            with ck.Context(0) as c4, c4.planes(ck.submatrix(n), s) as pl:
+                import_bitset_allgather(pl, host, ck.words_per_sample(s))
+                assert np.array_equal(pl.export_bitset(), bs)
+                assert_results_equal(pl.king(0.1, 1 << 20), want)
     finally:
         if created:
             dist.destroy_process_group()
