@@ -214,7 +214,7 @@ int plan_output(ck_planes *pl, const KingLaunch &k, uint32_t part, uint32_t part
 // output: a run is also an output region - contiguous because consecutive owned bands are consecutive in the output -
 // capped in length so that the device -> host copies of finished regions overlap the kernels of the next ones.
 int launch_bands(ck_planes *pl, KingLaunch k, int variant, const std::vector<uint64_t> &band_prefix, uint32_t band_lo,
-                 uint32_t band_hi, uint32_t part, uint32_t parts, uint32_t max_run, bool smallest_first, ResultPlan *plan) {
+                 uint32_t band_hi, uint32_t part, uint32_t parts, uint32_t max_run, bool organ_pipe, ResultPlan *plan) {
   ck_ctx *ctx = pl->ctx;
   cudaStream_t s = ctx->stream;
   k.results = ctx->result_buf;
@@ -229,10 +229,18 @@ int launch_bands(ck_planes *pl, KingLaunch k, int variant, const std::vector<uin
     b = e;
   }
   // The later bands of a triangular shard hold fewer pairs.  Launch order does not change the result; it decides how
-  // the copy-out of finished regions overlaps the kernels (a two-machine flow shop, compute then copy): when the copy
-  // is the slower machine - several GPUs sharing the host's ingest - the smallest regions go first (Johnson's rule),
-  // otherwise the largest, so that only a small region's copy is left exposed at the end.
-  if (smallest_first) std::reverse(runs.begin(), runs.end());
+  // the copy-out of finished regions overlaps the kernels - a two-machine flow shop, compute then copy.  When the copy is
+  // the slower machine (several GPUs sharing the host's ingest) the regions should grow (Johnson's rule: the copy engine
+  // starts at once and never runs dry), when the kernels are slower they should shrink (only a small region's copy is
+  // left exposed at the end).  Which regime holds depends on the platform and on how many GPUs copy at once, so the
+  // order is an organ pipe - every other region in growing order, then the rest in shrinking order - which is within one
+  // small region of the best order in both regimes.
+  if (organ_pipe && runs.size() > 2) {
+    std::vector<std::pair<uint32_t, uint32_t>> up, down;  // runs are in shrinking order (band index ascending)
+    for (size_t q = runs.size(); q-- > 0;) ((runs.size() - 1 - q) % 2 == 0 ? up : down).push_back(runs[q]);
+    runs = up;
+    runs.insert(runs.end(), down.rbegin(), down.rend());
+  }
   for (const auto &run : runs) {
     const uint32_t b = run.first, e = run.second;
     k.tile_begin = band_prefix[b];
@@ -487,10 +495,10 @@ int eval_view(ck_planes *pl, const ck_submatrix *view, uint32_t part, uint32_t p
   const uint32_t max_run = plan.dense ? std::max<uint32_t>(1, ceil_div(owned, 24u)) : 0xffffffffu;
   CK_CUDA(cudaEventRecord(ctx->ev[0], s));
   if (dbg) fprintf(stderr, "[ck] eval: planned after %.2f ms (dense %d, %llu pairs)\n", ms_since(tp0), int(plan.dense), plan.part_pairs);
-  // dense output into a caller buffer with several parts (= several GPUs behind one host): the copy-out is the slower
-  // stage (measured: 8 concurrent device -> host streams get 11-18 GB/s each, profiles/r02_host_copy_probe_n8.txt)
-  const bool smallest_first = plan.dense && !dst.sink && parts > 1;
-  rc = launch_bands(pl, k, variant, band_prefix, 0, num_bands, part, parts, max_run, smallest_first, &plan);
+  // dense output into a caller buffer: launch order chosen for the overlap of the copy-out (see launch_bands); a sink
+  // wants the regions in output order
+  const bool organ_pipe = plan.dense && !dst.sink;
+  rc = launch_bands(pl, k, variant, band_prefix, 0, num_bands, part, parts, max_run, organ_pipe, &plan);
   if (rc != CK_OK) {
     cudaStreamSynchronize(s);
     return rc;
