@@ -77,7 +77,7 @@ EXPORTED_SYMBOLS = [
     "ck_pack_triples", "ck_host_alloc", "ck_host_free", "ck_planes_import_bitset", "ck_planes_export_bitset", "ck_planes_synthesize", "ck_king",
     "ck_king_num_tiles", "ck_planes_king_variant", "ck_king_tiles", "ck_king_counts", "ck_king_host_bitset", "ck_king_host_bitset_part", "ck_king_stream_granularity", "ck_king_stream_begin",
     "ck_king_stream_rows", "ck_king_stream_end", "ck_synth_genotypes_host",
-    "ck_synth_triples_device", "ck_ctx_fp4_selftest", "ck_planes_and_reduce", "ck_king_view", "ck_king_view_sink", "ck_plan_work", "ck_measure_fp4_peak", "ck_measure_fp4_peak_sustained",
+    "ck_synth_triples_device", "ck_ctx_fp4_selftest", "ck_planes_and_reduce", "ck_king_view", "ck_king_view_sink", "ck_plan_work", "ck_measure_fp4_peak", "ck_measure_fp4_peak_sustained", "ck_pack_triples_narrow",
 ]
 
 # typedef int (*ck_result_sink)(void *user, const ck_result *records, size_t count)
@@ -111,6 +111,7 @@ def load() -> C.CDLL:
         "ck_planes_destroy": ([vp], i32), "ck_planes_finalize": ([vp], i32),
         "ck_planes_num_sites": ([vp, C.POINTER(u32)], i32), "ck_planes_device_bytes": ([vp, C.POINTER(u64)], i32),
         "ck_pack_triples": ([vp, vp, vp, vp, C.c_size_t, i32], i32),
+        "ck_pack_triples_narrow": ([vp, vp, vp, vp, C.c_size_t, i32], i32),
         "ck_host_alloc": ([C.c_size_t, C.POINTER(vp)], i32), "ck_host_free": ([vp], i32),
         "ck_planes_import_bitset": ([vp, vp, i32], i32), "ck_planes_export_bitset": ([vp, vp, i32], i32),
         "ck_planes_synthesize": ([vp, C.POINTER(SynthParams)], i32),

@@ -509,6 +509,64 @@ int ck_pack_triples(ck_planes *pl, const int64_t *row_idx, const int64_t *col_id
   return CK_OK;
 }
 
+int ck_pack_triples_narrow(ck_planes *pl, const uint32_t *row_idx, const uint32_t *col_idx, const uint8_t *n_alt_alleles,
+                           size_t n, int on_device) {
+  if (!pl) return fail(CK_ERR_INVALID_ARGUMENT, "planes is NULL");
+  if (n == 0) return CK_OK;
+  if (!row_idx || !col_idx || !n_alt_alleles) return fail(CK_ERR_INVALID_ARGUMENT, "NULL triple array");
+  ck_ctx *ctx = pl->ctx;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = ctx->stream;
+  auto device_readable = [](const void *p) {  // device memory, or page-locked host memory mapped into the device
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return false;
+    }
+    return at.devicePointer != nullptr && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+  };
+  struct Staged {  // pageable host arrays: one device copy of the three arrays, returned to the ctx cache on scope exit
+    ck_ctx *ctx;
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~Staged() { ctx_release(ctx, p, bytes); }
+  } staged{ctx};
+  const uint32_t *d_row = row_idx, *d_col = col_idx;
+  const uint8_t *d_alt = n_alt_alleles;
+  CK_CUDA(cudaMemsetAsync(ctx->d_pack_err, 0xff, 2 * sizeof(unsigned long long), s));
+  pl->mark_stale();
+  CK_CUDA(cudaEventRecord(ctx->ev[0], s));
+  if (!on_device && !(device_readable(row_idx) && device_readable(col_idx) && device_readable(n_alt_alleles))) {
+    const size_t n4 = (n + 3) & ~size_t(3);
+    staged.bytes = n4 * 9;
+    CK_CUDA(ctx_alloc(ctx, &staged.p, staged.bytes));
+    char *d = static_cast<char *>(staged.p);
+    CK_CUDA(cudaMemcpyAsync(d, row_idx, n * 4, cudaMemcpyHostToDevice, s));
+    CK_CUDA(cudaMemcpyAsync(d + n4 * 4, col_idx, n * 4, cudaMemcpyHostToDevice, s));
+    CK_CUDA(cudaMemcpyAsync(d + n4 * 8, n_alt_alleles, n, cudaMemcpyHostToDevice, s));
+    d_row = reinterpret_cast<const uint32_t *>(d);
+    d_col = reinterpret_cast<const uint32_t *>(d + n4 * 4);
+    d_alt = reinterpret_cast<const uint8_t *>(d + n4 * 8);
+  }
+  CK_CUDA(launch_pack_narrow(*pl, d_row, d_col, d_alt, n, 0, ctx->d_pack_err, s));
+  CK_CUDA(cudaEventRecord(ctx->ev[1], s));
+  unsigned long long err[2];
+  CK_CUDA(cudaMemcpyAsync(err, ctx->d_pack_err, sizeof(err), cudaMemcpyDeviceToHost, s));
+  CK_CUDA(cudaStreamSynchronize(s));
+  ctx->timings.pack_ms = elapsed_ms(ctx->ev[0], ctx->ev[1]);
+  if (err[0] != ~0ull) {
+    const size_t idx = size_t(err[0]) - 1;
+    uint8_t value = 0;
+    if (on_device) cudaMemcpy(&value, n_alt_alleles + idx, 1, cudaMemcpyDeviceToHost);
+    else value = n_alt_alleles[idx];
+    return fail(CK_ERR_INVALID_GENOTYPE, "Invalid value for n_alt_alleles (" + std::to_string(unsigned(value)) +
+                                             ") encountered at triple " + std::to_string(idx));
+  }
+  if (err[1] != ~0ull)
+    return fail(CK_ERR_OUT_OF_RANGE, "row_idx out of range [0, num_sites) at triple " + std::to_string(size_t(err[1]) - 1));
+  return CK_OK;
+}
+
 int ck_host_alloc(size_t bytes, void **out) {
   if (!out) return fail(CK_ERR_INVALID_ARGUMENT, "out is NULL");
   *out = nullptr;

@@ -170,6 +170,8 @@ namespace ck {
 cudaError_t launch_fill_missing(uint32_t *raw, size_t num_words, cudaStream_t s);
 cudaError_t launch_pack(const ck_planes &pl, const int64_t *row, const int64_t *col, const int32_t *alt, size_t n,
                         size_t index_base, unsigned long long *d_err, cudaStream_t s);
+cudaError_t launch_pack_narrow(const ck_planes &pl, const uint32_t *row, const uint32_t *col, const uint8_t *alt, size_t n,
+                               size_t index_base, unsigned long long *d_err, cudaStream_t s);
 cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s);
 cudaError_t launch_finalize_codes(const ck_planes &pl, int kind, cudaStream_t s);
 // the same for the 64-sample blocks [block0, block0 + num_blocks) only (pipelined host-buffer path)

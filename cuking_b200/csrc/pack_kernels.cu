@@ -45,9 +45,13 @@ __device__ __forceinline__ void pack_one(uint32_t *raw, const SlotMap &map, uint
   if (n_alt != 2) atomicAnd(het + kTileSamples, mask);    // 0 and 1 clear the hom-alt bit  (cuking.cu:690, :693)
 }
 
+// RowT / ColT / AltT: int64 / int64 / int32 as decoded from the reference's Parquet columns (cuking.cu:603-672), or the narrow
+// form uint32 / uint32 / uint8 (the same values after the int32 truncation of cuking.cu:676,:680; 9 instead of 20 bytes per
+// triple over PCIe when the kernel reads page-locked host memory in place)
+template <typename RowT, typename ColT, typename AltT>
 __global__ void __launch_bounds__(256) pack_kernel(uint32_t *raw, SlotMap map, uint32_t words, uint32_t num_sites,
-                                                   const int64_t *__restrict__ row, const int64_t *__restrict__ col,
-                                                   const int32_t *__restrict__ alt, size_t n, size_t index_base,
+                                                   const RowT *__restrict__ row, const ColT *__restrict__ col,
+                                                   const AltT *__restrict__ alt, size_t n, size_t index_base,
                                                    unsigned long long *err) {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -59,8 +63,9 @@ __global__ void __launch_bounds__(256) pack_kernel(uint32_t *raw, SlotMap map, u
   constexpr int kUnroll = 8;
   size_t i = tid;
   for (; i + (kUnroll - 1) * stride < n; i += kUnroll * stride) {
-    int64_t r[kUnroll], c[kUnroll];
-    int32_t a[kUnroll];
+    RowT r[kUnroll];
+    ColT c[kUnroll];
+    AltT a[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       r[u] = __ldcs(row + i + u * stride);  // streaming: every triple is read exactly once
@@ -68,9 +73,11 @@ __global__ void __launch_bounds__(256) pack_kernel(uint32_t *raw, SlotMap map, u
       a[u] = __ldcs(alt + i + u * stride);
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) pack_one(raw, map, words, num_sites, r[u], c[u], a[u], index_base + i + u * stride, err);
+    for (int u = 0; u < kUnroll; ++u)
+      pack_one(raw, map, words, num_sites, int64_t(r[u]), int64_t(c[u]), int32_t(a[u]), index_base + i + u * stride, err);
   }
-  for (; i < n; i += stride) pack_one(raw, map, words, num_sites, __ldcs(row + i), __ldcs(col + i), __ldcs(alt + i), index_base + i, err);
+  for (; i < n; i += stride)
+    pack_one(raw, map, words, num_sites, int64_t(__ldcs(row + i)), int64_t(__ldcs(col + i)), int32_t(__ldcs(alt + i)), index_base + i, err);
 }
 
 // ---- finalize: raw (het, alt) -> compute (H, D, A) --------------------------------------------------------------
@@ -273,6 +280,14 @@ cudaError_t launch_fill_missing(uint32_t *raw, size_t num_words, cudaStream_t s)
 
 cudaError_t launch_pack(const ck_planes &pl, const int64_t *row, const int64_t *col, const int32_t *alt, size_t n,
                         size_t index_base, unsigned long long *d_err, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  pack_kernel<<<grid_for(n / 8 + 1, 256, 148 * 8), 256, 0, s>>>(pl.raw, pl.map, pl.words, pl.num_sites, row, col, alt, n,
+                                                              index_base, d_err);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_narrow(const ck_planes &pl, const uint32_t *row, const uint32_t *col, const uint8_t *alt, size_t n,
+                               size_t index_base, unsigned long long *d_err, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   pack_kernel<<<grid_for(n / 8 + 1, 256, 148 * 8), 256, 0, s>>>(pl.raw, pl.map, pl.words, pl.num_sites, row, col, alt, n,
                                                               index_base, d_err);

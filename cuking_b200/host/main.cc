@@ -22,6 +22,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <filesystem>
 #include <fstream>
@@ -246,8 +247,11 @@ Status Run(const Flags &flags) {
     std::mutex err_mu;
     Status first_error;  // first error wins, like ParallelFor (cuking.cu:415-433)
     constexpr size_t kChunkRows = size_t(1) << 20;  // 20 MiB of page-locked memory per reader thread
+    // CUKING_WIDE_TRIPLES=1: hand the pack kernel the columns at their physical widths (20 bytes per triple over PCIe, no
+    // narrowing pass on the host) instead of the narrowed 9 bytes
+    const bool narrow_triples = getenv("CUKING_WIDE_TRIPLES") == nullptr;
     auto worker = [&]() {
-      cuking::Triples t;
+      cuking::Triples t(narrow_triples);
       for (;;) {
         const size_t f = next.fetch_add(1);
         if (f >= files.size()) return;
@@ -256,13 +260,21 @@ Status Run(const Flags &flags) {
           if (!first_error.ok()) return;
         }
         Status st;
-        // Stream the file through this thread's page-locked chunk buffer: decode a chunk, let ONE GPU pack it (the
-        // kernel reads the pinned chunk in place over PCIe), decode the next chunk.
+        // Stream the file through this thread's chunk buffers: decode a chunk, narrow it to 9 bytes per triple in page-locked
+        // memory, let ONE GPU pack it (the kernel reads the pinned chunk in place over PCIe), decode the next chunk.
         auto pack_on = [&](Gpu &g, size_t first_row) -> bool {
           std::lock_guard<std::mutex> l(g.mu);
-          const int rc = ck_pack_triples(g.planes, t.row_idx, t.col_idx, t.n_alt_alleles, t.size, /*on_device=*/0);
+          const int rc = t.narrow() ? ck_pack_triples_narrow(g.planes, t.row32, t.col32, t.alt8, t.size, /*on_device=*/0)
+                                    : ck_pack_triples(g.planes, t.row_idx, t.col_idx, t.n_alt_alleles, t.size, /*on_device=*/0);
           if (rc == CK_OK) return true;
           st = FromCk(rc);
+          if (rc == CK_ERR_INVALID_GENOTYPE) {  // report the value as decoded (a byte cannot hold every int32), cuking.cu:698-701
+            const std::string msg = ck_last_error();
+            const size_t at = msg.rfind("triple ");
+            const size_t idx = at == std::string::npos ? t.size : size_t(strtoull(msg.c_str() + at + 7, nullptr, 10));
+            if (idx < t.size)
+              st.message = "Invalid value for n_alt_alleles (" + std::to_string(t.n_alt_alleles[idx]) + ") encountered at triple " + std::to_string(idx);
+          }
           st.message += " (chunk starting at row " + std::to_string(first_row) + ") in " + files[f];
           return false;
         };

@@ -19,15 +19,34 @@ std::string Triples::Reserve(size_t n) {
   ck_host_free(block_);
   block_ = nullptr;
   capacity_ = 0;
-  const size_t cap = std::max<size_t>(n, size_t(1) << 12);  // column starts stay 16-byte aligned
-  const size_t cap_pad = (cap + 1) & ~size_t(1);
-  if (ck_host_alloc(cap_pad * (8 + 8 + 4), &block_) != CK_OK) return std::string("Cannot allocate pinned host memory: ") + ck_last_error();
+  const size_t cap = std::max<size_t>(n, size_t(1) << 12);
+  const size_t cap_pad = (cap + 15) & ~size_t(15);  // column starts stay 16-byte aligned
+  const size_t per_row = narrow_ ? 4 + 4 + 1 : 8 + 8 + 4;
+  if (ck_host_alloc(cap_pad * per_row, &block_) != CK_OK) return std::string("Cannot allocate pinned host memory: ") + ck_last_error();
   capacity_ = cap_pad;
   char *base = static_cast<char *>(block_);
-  row_idx = reinterpret_cast<int64_t *>(base);
-  col_idx = reinterpret_cast<int64_t *>(base + cap_pad * 8);
-  n_alt_alleles = reinterpret_cast<int32_t *>(base + cap_pad * 16);
+  if (narrow_) {
+    row32 = reinterpret_cast<uint32_t *>(base);
+    col32 = reinterpret_cast<uint32_t *>(base + cap_pad * 4);
+    alt8 = reinterpret_cast<uint8_t *>(base + cap_pad * 8);
+    wide64_.resize(2 * cap_pad);
+    wide32_.resize(cap_pad);
+    row_idx = wide64_.data();
+    col_idx = wide64_.data() + cap_pad;
+    n_alt_alleles = wide32_.data();
+  } else {
+    row_idx = reinterpret_cast<int64_t *>(base);
+    col_idx = reinterpret_cast<int64_t *>(base + cap_pad * 8);
+    n_alt_alleles = reinterpret_cast<int32_t *>(base + cap_pad * 16);
+  }
   return "";
+}
+
+void Triples::Narrow() {
+  if (!narrow_) return;
+  for (size_t i = 0; i < size; ++i) row32[i] = uint32_t(row_idx[i]);  // the low 32 bits, like the casts at cuking.cu:676,:680
+  for (size_t i = 0; i < size; ++i) col32[i] = uint32_t(col_idx[i]);
+  for (size_t i = 0; i < size; ++i) alt8[i] = uint32_t(n_alt_alleles[i]) <= 255u ? uint8_t(n_alt_alleles[i]) : uint8_t(255);
 }
 
 std::string ListParquetFiles(const std::string &dir, std::vector<std::string> *files) {
@@ -110,6 +129,7 @@ std::string ReadTriples(const std::string &path, size_t chunk_rows, Triples *buf
         if (!(err = ReadValues(r2, o2, path, buf->n_alt_alleles, want, &g2, &def_scratch)).empty()) return err;
         if (g0 != want || g1 != want || g2 != want) return "Column lengths differ from the row count in " + path;
         buf->size = want;
+        buf->Narrow();
         if (!(err = consume(delivered)).empty()) return err;
         delivered += want;
         remaining -= want;

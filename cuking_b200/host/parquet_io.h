@@ -11,22 +11,37 @@
 
 namespace cuking {
 
-// Decoded columns of one file.  The arrays live in page-locked host memory (ck_host_alloc) that grows geometrically
-// and is reused from file to file by the owning reader thread, so the GPU pack kernel can read them in place.
+// One chunk of decoded triples.  libparquet decodes the three columns at their physical width (INT64, INT64, INT32,
+// cuking.cu:603-672) into pageable scratch; the chunk is then narrowed to what the pack step really uses - the 32-bit values
+// the reference truncates row_idx / col_idx to (cuking.cu:676,:680) and one byte of n_alt_alleles (values that do not fit a
+// byte become 255, which the pack rejects like any value other than 0, 1, 2) - in page-locked host memory (ck_host_alloc)
+// that the GPU pack kernel reads in place: 9 instead of 20 bytes per triple over PCIe, which is what bounds ingest.
+// Buffers grow geometrically and are reused from file to file by the owning reader thread.
 class Triples {
  public:
-  Triples() = default;
+  // narrow = true: decode into pageable scratch, then narrow into page-locked memory (9 bytes per triple over PCIe);
+  // narrow = false: decode straight into page-locked arrays of the physical column widths (20 bytes per triple, no extra
+  // pass over the chunk on the host)
+  explicit Triples(bool narrow = true) : narrow_(narrow) {}
   Triples(const Triples &) = delete;
   Triples &operator=(const Triples &) = delete;
   ~Triples();
   // Makes room for n rows (contents are not preserved).  Returns "" or an error message.
   std::string Reserve(size_t n);
-  int64_t *row_idx = nullptr, *col_idx = nullptr;
+  // Narrows rows [0, size) of the decode scratch into the page-locked arrays (no-op in wide mode).
+  void Narrow();
+  bool narrow() const { return narrow_; }
+  int64_t *row_idx = nullptr, *col_idx = nullptr;  // decoded columns (pageable scratch in narrow mode, page-locked in wide mode)
   int32_t *n_alt_alleles = nullptr;
+  uint32_t *row32 = nullptr, *col32 = nullptr;     // page-locked, what ck_pack_triples_narrow reads (narrow mode)
+  uint8_t *alt8 = nullptr;
   size_t size = 0;
 
  private:
+  bool narrow_;
   void *block_ = nullptr;
+  std::vector<int64_t> wide64_;
+  std::vector<int32_t> wide32_;
   size_t capacity_ = 0;
 };
 

@@ -173,6 +173,14 @@ int ck_planes_device_bytes(const ck_planes *planes, uint64_t *bytes);
 int ck_pack_triples(ck_planes *planes, const int64_t *row_idx, const int64_t *col_idx, const int32_t *n_alt_alleles,
                     size_t num_triples, int on_device);
 
+/* The same for triples already narrowed by the caller: row_idx and col_idx as the 32-bit values the reference truncates
+ * them to (cuking.cu:676,:680), n_alt_alleles as one byte (any value other than 0, 1, 2 - use 255 for an int32 that does
+ * not fit a byte - fails the call like ck_pack_triples).  9 instead of 20 bytes per triple: when the kernel reads
+ * page-locked host memory in place, ingest is bound by the PCIe link, so a host that decodes Parquet should narrow its
+ * columns once and use this entry point (host/parquet_io.cc does). */
+int ck_pack_triples_narrow(ck_planes *planes, const uint32_t *row_idx, const uint32_t *col_idx, const uint8_t *n_alt_alleles,
+                           size_t num_triples, int on_device);
+
 /* Page-locked host memory for triple buffers.  ck_pack_triples recognises it (and any other cudaHostAlloc /
  * cudaHostRegister memory) and lets the pack kernel stream the triples straight over PCIe, skipping the staging copy;
  * decode threads should read their Parquet columns directly into buffers from here. */

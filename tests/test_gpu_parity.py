@@ -83,6 +83,41 @@ def test_pack_device_pointers_and_unaligned(ctx):
             assert np.array_equal(pl.export_bitset(), want)
 
 
+def test_pack_narrow_equals_pack(ctx):
+    # ck_pack_triples_narrow: uint32 / uint32 / uint8 triples (9 bytes instead of 20) from pageable host memory, page-locked
+    # host memory (read in place by the kernel) and device memory; same planes, same errors
+    import torch
+
+    rng = np.random.default_rng(31)
+    g = random_genotypes(rng, 203, 1500)
+    for k, shard in [(1, 0), (3, 1), (3, 3)]:
+        sm = ck.submatrix(203, k, shard)
+        want = oracle_bitset(g, ko_sm(sm))
+        site, sample, alt = triples_of(g)
+        r32, c32, a8 = site.astype(np.uint32), sample.astype(np.uint32), alt.astype(np.uint8)
+        sources = {
+            "pageable": (r32, c32, a8),
+            "pinned": tuple(torch.from_numpy(x.view(np.int32 if x.dtype == np.uint32 else np.uint8)).pin_memory() for x in (r32, c32, a8)),
+            "device": tuple(torch.from_numpy(x.view(np.int32 if x.dtype == np.uint32 else np.uint8)).cuda() for x in (r32, c32, a8)),
+        }
+        for name, (r, c, a) in sources.items():
+            with ctx.planes(sm, 1500) as pl:
+                pl.pack_narrow(r, c, a)
+                assert np.array_equal(pl.export_bitset(), want), (name, k, shard)
+    with ctx.planes(ck.submatrix(203), 1500) as pl:
+        for bad in (3, 255):
+            a_bad = a8.copy()
+            a_bad[777] = bad
+            with pytest.raises(ck.CukingError, match=rf"n_alt_alleles \({bad}\) encountered at triple 777") as e:
+                pl.pack_narrow(r32, c32, a_bad)
+            assert e.value.code == capi.CK_ERR_INVALID_GENOTYPE
+        r_bad = r32.copy()
+        r_bad[5] = 1500
+        with pytest.raises(ck.CukingError) as e:
+            pl.pack_narrow(r_bad, c32, a8)
+        assert e.value.code == capi.CK_ERR_OUT_OF_RANGE
+
+
 def test_pack_rejects_bad_genotype_and_site(ctx):
     sm = ck.submatrix(4)
     with ctx.planes(sm, 100) as pl:

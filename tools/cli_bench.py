@@ -31,6 +31,8 @@ ap.add_argument("--threads", type=int, default=16)
 ap.add_argument("--threshold", type=float, default=0.0884)
 ap.add_argument("--num-gpus", default="1", help="comma list: the binary is run once per entry on the same input")
 ap.add_argument("--split-factor", type=int, default=1, help="> 1: --all_shards with this split factor")
+ap.add_argument("--repeat", type=int, default=1, help="runs per configuration (page cache warm after the first)")
+ap.add_argument("--modes", default="narrow", help="comma list of narrow,wide (CUKING_WIDE_TRIPLES)")
 args = ap.parse_args()
 
 with tempfile.TemporaryDirectory() as tmp:
@@ -45,14 +47,18 @@ with tempfile.TemporaryDirectory() as tmp:
     with ck.Context(0) as ctx, ctx.planes(ck.submatrix(args.samples), args.sites) as pl:
         pl.synthesize(42, 0.01)
         want = len(pl.king(args.threshold, 10 << 20))
-    for gpus in [int(x) for x in args.num_gpus.split(",")]:
-        out = f"{tmp}/out{gpus}"
+    runs = [(int(x), m, r) for x in args.num_gpus.split(",") for m in args.modes.split(",") for r in range(args.repeat)]
+    for gpus, mode, rep in runs:
+        out = f"{tmp}/out{gpus}{mode}{rep}"
         cmd = [os.path.join(ROOT, "bin", "cuking"), f"--input_uri={tmp}/in", f"--output_uri={out}",
                f"--kin_threshold={args.threshold}", f"--num_reader_threads={args.threads}", f"--num_gpus={gpus}"]
         if args.split_factor > 1:
             cmd += [f"--split_factor={args.split_factor}", "--all_shards", "--write_success_file"]
         t0 = time.perf_counter()
-        p = subprocess.run(cmd, capture_output=True, text=True)
+        env = dict(os.environ)
+        if mode == "wide":
+            env["CUKING_WIDE_TRIPLES"] = "1"
+        p = subprocess.run(cmd, capture_output=True, text=True, env=env)
         wall = time.perf_counter() - t0
         if p.returncode != 0:
             sys.exit(p.stderr)
@@ -66,7 +72,7 @@ with tempfile.TemporaryDirectory() as tmp:
         if m:
             decode_s = float(m.group(1)) * (1e-3 if m.group(2) == "ms" else 1.0)
         print(json.dumps({"tool": "cli_bench", "samples": args.samples, "sites": args.sites, "triples": info["num_triples"],
-                          "parquet_bytes": in_bytes, "files": args.files, "reader_threads": args.threads, "num_gpus": gpus,
+                          "parquet_bytes": in_bytes, "files": args.files, "reader_threads": args.threads, "num_gpus": gpus, "triples_mode": mode, "rep": rep,
                           "split_factor": args.split_factor, "generate_input_s": round(gen_s, 2), "cuking_wall_s": round(wall, 3),
                           "phases": phases, "kernels": [{"what": k[0], "wall": k[1], "kernel_ms": float(k[2]), "gpu": int(k[3])} for k in kernels],
                           "triples_per_s_end_to_end": info["num_triples"] / wall,
