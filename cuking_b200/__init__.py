@@ -6,7 +6,7 @@ include/cuking_b200.h.  The compute is hand-written CUDA for sm_100a in cuking_b
 pointers.  No CPU fallback exists.
 """
 from .capi import CukingError, Submatrix, RESULT_DTYPE, COUNTS_DTYPE, SynthParams  # noqa: F401
-from .engine import Context, Planes, submatrix, num_shards, words_per_sample, synth_genotypes_host, and_reduce, plan_work  # noqa: F401
+from .engine import Context, Planes, submatrix, num_shards, words_per_sample, synth_genotypes_host, and_reduce, plan_work, rle_scan  # noqa: F401
 
 __all__ = ["CukingError", "Submatrix", "RESULT_DTYPE", "COUNTS_DTYPE", "SynthParams", "Context", "Planes",
-           "submatrix", "num_shards", "words_per_sample", "synth_genotypes_host", "and_reduce", "plan_work"]
+           "submatrix", "num_shards", "words_per_sample", "synth_genotypes_host", "and_reduce", "plan_work", "rle_scan"]

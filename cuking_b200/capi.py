@@ -49,6 +49,23 @@ class WorkItem(C.Structure):
         return f"WorkItem(shard={self.shard_index}, part={self.part_index}/{self.num_parts}, gpu={self.gpu}, pairs={self.pairs})"
 
 
+class Run(C.Structure):
+    """ck_run: one run of a Parquet RLE / bit-packed hybrid stream, or a PLAIN page (ck_pack_encoded)."""
+
+    _fields_ = [("first_value", C.c_uint32), ("kind", C.c_uint32), ("bit_width", C.c_uint32), ("payload", C.c_uint32)]
+
+
+RUN_DTYPE = np.dtype([("first_value", "<u4"), ("kind", "<u4"), ("bit_width", "<u4"), ("payload", "<u4")])
+CK_RUN_RLE, CK_RUN_BITPACKED, CK_RUN_PLAIN = 0, 1, 2
+
+
+class EncodedColumn(C.Structure):
+    """ck_encoded_column: one column of one window of rows as page payloads + run table + dictionary."""
+
+    _fields_ = [("bytes", C.c_void_p), ("num_bytes", C.c_uint64), ("runs", C.c_void_p), ("num_runs", C.c_uint32),
+                ("dict", C.c_void_p), ("dict_len", C.c_uint32), ("value_width", C.c_uint32), ("skip", C.c_uint32)]
+
+
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("missing_rate", C.c_double)]
 
@@ -78,6 +95,7 @@ EXPORTED_SYMBOLS = [
     "ck_king_num_tiles", "ck_planes_king_variant", "ck_king_tiles", "ck_king_counts", "ck_king_host_bitset", "ck_king_host_bitset_part", "ck_king_stream_granularity", "ck_king_stream_begin",
     "ck_king_stream_rows", "ck_king_stream_end", "ck_synth_genotypes_host",
     "ck_synth_triples_device", "ck_ctx_fp4_selftest", "ck_planes_and_reduce", "ck_king_view", "ck_king_view_sink", "ck_plan_work", "ck_measure_fp4_peak", "ck_measure_fp4_peak_sustained", "ck_pack_triples_narrow",
+    "ck_rle_scan", "ck_pack_encoded",
 ]
 
 # typedef int (*ck_result_sink)(void *user, const ck_result *records, size_t count)
@@ -112,6 +130,8 @@ def load() -> C.CDLL:
         "ck_planes_num_sites": ([vp, C.POINTER(u32)], i32), "ck_planes_device_bytes": ([vp, C.POINTER(u64)], i32),
         "ck_pack_triples": ([vp, vp, vp, vp, C.c_size_t, i32], i32),
         "ck_pack_triples_narrow": ([vp, vp, vp, vp, C.c_size_t, i32], i32),
+        "ck_rle_scan": ([vp, C.c_size_t, u32, u32, u32, u32, vp, u32, C.POINTER(u32)], i32),
+        "ck_pack_encoded": ([vp, C.POINTER(EncodedColumn), u32], i32),
         "ck_host_alloc": ([C.c_size_t, C.POINTER(vp)], i32), "ck_host_free": ([vp], i32),
         "ck_planes_import_bitset": ([vp, vp, i32], i32), "ck_planes_export_bitset": ([vp, vp, i32], i32),
         "ck_planes_synthesize": ([vp, C.POINTER(SynthParams)], i32),

@@ -255,7 +255,7 @@ int ck_ctx_create(int device, ck_ctx **out) {
       (e = cudaEventCreate(&ctx->ev[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev[1])) != cudaSuccess ||
       (e = cudaMalloc(&ctx->d_counter, kCounterBytes)) != cudaSuccess ||
       (e = cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_holes), kCounterBytes, cudaHostAllocDefault)) != cudaSuccess ||
-      (e = cudaMalloc(&ctx->d_pack_err, 2 * sizeof(unsigned long long))) != cudaSuccess) {
+      (e = cudaMalloc(&ctx->d_pack_err, 4 * sizeof(unsigned long long))) != cudaSuccess) {
     ck_ctx_destroy(ctx);
     return fail_cuda(e, "ck_ctx_create", __FILE__, __LINE__);
   }
@@ -304,6 +304,7 @@ int ck_ctx_destroy(ck_ctx *ctx) {
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->h_holes) cudaFreeHost(ctx->h_holes);
   if (ctx->d_pack_err) cudaFree(ctx->d_pack_err);
+  if (ctx->decode_staging) cudaFree(ctx->decode_staging);
   if (ctx->dense_table) cudaFree(ctx->dense_table);
   for (void *p : ctx->out_pinned)
     if (p) cudaFreeHost(p);

@@ -58,7 +58,10 @@ struct ck_ctx {
   static constexpr uint32_t kHoleSlots = 1024;  // dense output: one below-threshold counter per output region
   unsigned long long *d_counter = nullptr;      // [0] emitted-pair counter, [1] spare, [2 ..] hole counters
   unsigned long long *h_holes = nullptr;        // pinned host mirror of the hole counters
-  unsigned long long *d_pack_err = nullptr;     // [0] invalid-genotype index+1 (min), [1] out-of-range index+1 (min)
+  unsigned long long *d_pack_err = nullptr;     // [0] invalid-genotype index+1 (min), [1] out-of-range index+1 (min),
+                                                // [2] dictionary index out of range (ck_pack_encoded), [3] spare
+  void *decode_staging = nullptr;               // grow-only device copy of one window's payloads, run tables and dictionaries
+  size_t decode_staging_bytes = 0;
   void *pinned[2] = {nullptr, nullptr};   // host staging for ck_pack_triples(on_device = 0)
   void *staging[2] = {nullptr, nullptr};  // device side of the same double buffer
   size_t pinned_bytes = 0;
@@ -172,6 +175,15 @@ cudaError_t launch_pack(const ck_planes &pl, const int64_t *row, const int64_t *
                         size_t index_base, unsigned long long *d_err, cudaStream_t s);
 cudaError_t launch_pack_narrow(const ck_planes &pl, const uint32_t *row, const uint32_t *col, const uint8_t *alt, size_t n,
                                size_t index_base, unsigned long long *d_err, cudaStream_t s);
+// device view of one ck_encoded_column (page_decode.cu): payload words (8-byte aligned, padded by 8 bytes), runs + sentinel
+struct EncodedColumnDev {
+  const uint32_t *words;
+  const ck_run *runs;
+  const void *dict;
+  uint32_t num_runs, dict_len, width, skip;
+};
+cudaError_t launch_decode_pack(const ck_planes &pl, const EncodedColumnDev (&cols)[3], uint32_t num_rows, unsigned long long *d_err,
+                               cudaStream_t s);
 cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s);
 cudaError_t launch_finalize_codes(const ck_planes &pl, int kind, cudaStream_t s);
 // the same for the 64-sample blocks [block0, block0 + num_blocks) only (pipelined host-buffer path)

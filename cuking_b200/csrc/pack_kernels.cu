@@ -80,6 +80,72 @@ __global__ void __launch_bounds__(256) pack_kernel(uint32_t *raw, SlotMap map, u
     pack_one(raw, map, words, num_sites, int64_t(__ldcs(row + i)), int64_t(__ldcs(col + i)), int32_t(__ldcs(alt + i)), index_base + i, err);
 }
 
+// ---- decode + pack: Parquet page payloads -> raw planes (ck_pack_encoded, page_decode.cu) ---------------------------
+// One thread decodes kDecodeRows consecutive rows of the window: per column one binary search over the run table for its
+// first value, then a walk.  RLE runs cost nothing, bit-packed dictionary indices one funnel shift over two aligned words
+// of the payload buffer, PLAIN values one load.  The decoded triples go through pack_one like every other triple.
+constexpr int kDecodeRows = 8;
+
+__device__ __forceinline__ uint32_t decode_rows(const EncodedColumnDev &c, uint32_t row0, uint32_t n, int64_t (&out)[kDecodeRows]) {
+  const uint32_t v0 = c.skip + row0;
+  uint32_t lo = 0, hi = c.num_runs;  // runs[lo].first_value <= v0 < runs[hi].first_value (runs[num_runs] is the sentinel)
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&c.runs[mid].first_value) <= v0) lo = mid; else hi = mid;
+  }
+  uint4 run = __ldg(reinterpret_cast<const uint4 *>(c.runs + lo));  // first_value, kind, bit_width, payload
+  uint32_t next = __ldg(&c.runs[lo + 1].first_value);
+  uint32_t bad = 0xffffffffu;  // first row of this thread whose dictionary index is out of range
+#pragma unroll
+  for (int k = 0; k < kDecodeRows; ++k) {
+    out[k] = 0;
+    if (uint32_t(k) < n) {
+      const uint32_t v = v0 + k;
+      while (v >= next) {
+        ++lo;
+        run = __ldg(reinterpret_cast<const uint4 *>(c.runs + lo));
+        next = __ldg(&c.runs[lo + 1].first_value);
+      }
+      const uint32_t rel = v - run.x;
+      if (run.y == CK_RUN_PLAIN) {
+        const uint8_t *p = reinterpret_cast<const uint8_t *>(c.words) + run.w;
+        out[k] = c.width == 8 ? __ldg(reinterpret_cast<const long long *>(p) + rel) : (long long)__ldg(reinterpret_cast<const int *>(p) + rel);
+      } else {
+        uint32_t idx = run.w;
+        if (run.y == CK_RUN_BITPACKED) {
+          const unsigned long long bit = (unsigned long long)run.w * 8ull + (unsigned long long)rel * run.z;
+          const size_t w = size_t(bit >> 5);
+          idx = __funnelshift_r(__ldg(c.words + w), __ldg(c.words + w + 1), uint32_t(bit) & 31u);  // the buffer is padded by 8 bytes
+          if (run.z < 32u) idx &= (1u << run.z) - 1u;
+        }
+        if (idx >= c.dict_len) {
+          if (bad == 0xffffffffu) bad = uint32_t(k);
+        } else {
+          out[k] = c.width == 8 ? __ldg(reinterpret_cast<const long long *>(c.dict) + idx) : (long long)__ldg(reinterpret_cast<const int *>(c.dict) + idx);
+        }
+      }
+    }
+  }
+  return bad;
+}
+
+__global__ void __launch_bounds__(256) decode_pack_kernel(uint32_t *raw, SlotMap map, uint32_t words, uint32_t num_sites,
+                                                          EncodedColumnDev c_row, EncodedColumnDev c_col, EncodedColumnDev c_alt,
+                                                          uint32_t num_rows, unsigned long long *err) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  const size_t groups = (size_t(num_rows) + kDecodeRows - 1) / kDecodeRows;
+  for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < groups; t += stride) {
+    const uint32_t row0 = uint32_t(t * kDecodeRows), n = min(uint32_t(kDecodeRows), num_rows - row0);
+    int64_t r[kDecodeRows], c[kDecodeRows], a[kDecodeRows];
+    const uint32_t bad = min(min(decode_rows(c_row, row0, n, r), decode_rows(c_col, row0, n, c)), decode_rows(c_alt, row0, n, a));
+    if (bad != 0xffffffffu) atomicMin(&err[2], (unsigned long long)(row0 + bad) + 1ull);
+#pragma unroll
+    for (int k = 0; k < kDecodeRows; ++k)
+      if (uint32_t(k) < n && uint32_t(k) < bad)  // nothing is packed from a corrupt row on (the call fails anyway)
+        pack_one(raw, map, words, num_sites, r[k], c[k], int32_t(a[k]), size_t(row0) + k, err);
+  }
+}
+
 // ---- finalize: raw (het, alt) -> compute (H, D, A) --------------------------------------------------------------
 // One thread per 4 lanes (16 bytes) of one (block, word) row; pure streaming, 8 B read + 12 B written per sample-word.
 __global__ void __launch_bounds__(256) finalize_kernel(const uint4 *__restrict__ raw4, uint4 *__restrict__ out4,
@@ -291,6 +357,14 @@ cudaError_t launch_pack_narrow(const ck_planes &pl, const uint32_t *row, const u
   if (n == 0) return cudaSuccess;
   pack_kernel<<<grid_for(n / 8 + 1, 256, 148 * 8), 256, 0, s>>>(pl.raw, pl.map, pl.words, pl.num_sites, row, col, alt, n,
                                                               index_base, d_err);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decode_pack(const ck_planes &pl, const EncodedColumnDev (&cols)[3], uint32_t num_rows, unsigned long long *d_err,
+                               cudaStream_t s) {
+  if (num_rows == 0) return cudaSuccess;
+  decode_pack_kernel<<<grid_for((size_t(num_rows) + kDecodeRows - 1) / kDecodeRows, 256), 256, 0, s>>>(
+      pl.raw, pl.map, pl.words, pl.num_sites, cols[0], cols[1], cols[2], num_rows, d_err);
   return cudaGetLastError();
 }
 

@@ -61,6 +61,17 @@ def synth_genotypes_host(seed: int, missing_rate: float, sample_begin: int, samp
     return out
 
 
+def rle_scan(data, bit_width: int, num_values: int, first_value: int = 0, payload_base: int = 0) -> np.ndarray:
+    """ck_rle_scan: the run table (capi.RUN_DTYPE, no sentinel) of one Parquet RLE / bit-packed hybrid stream.  Host code of
+    the library; needs no GPU."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+    runs = np.zeros(buf.size + 1, dtype=capi.RUN_DTYPE)
+    n = C.c_uint32(0)
+    check(capi.load().ck_rle_scan(buf.ctypes.data if buf.size else None, buf.size, bit_width, num_values, first_value, payload_base,
+                                  runs.ctypes.data, len(runs), C.byref(n)))
+    return runs[: n.value].copy()
+
+
 def _ptr(x) -> tuple[int, bool]:
     """(address, on_device) of a numpy array or a torch tensor."""
     if isinstance(x, np.ndarray):
@@ -215,6 +226,29 @@ class Planes:
         n = int(row_idx.shape[0])
         assert int(col_idx.shape[0]) == n and int(n_alt_alleles.shape[0]) == n
         check(self._lib.ck_pack_triples_narrow(self._h, r, c, a, n, int(dev_r)))
+
+    def pack_encoded(self, columns, num_rows: int) -> None:
+        """ck_pack_encoded: Parquet page payloads decoded and packed in one kernel.  `columns` = three dicts (row_idx,
+        col_idx, n_alt_alleles) with `bytes` (uint8 array), `runs` (RUN_DTYPE array, sentinel included), `dict` (int64 /
+        int32 array or None) and `skip`."""
+        from .capi import RUN_DTYPE, EncodedColumn
+
+        cols = (EncodedColumn * 3)()
+        keep = []
+        for c, col in zip(cols, columns):
+            data = np.ascontiguousarray(col["bytes"], dtype=np.uint8)
+            runs = np.ascontiguousarray(col["runs"], dtype=RUN_DTYPE)
+            d = col.get("dict")
+            width = int(col.get("value_width", d.dtype.itemsize if d is not None else 8))
+            if d is not None:
+                d = np.ascontiguousarray(d)
+                assert d.dtype.itemsize == width
+            keep += [data, runs, d]
+            c.bytes, c.num_bytes = data.ctypes.data, data.size
+            c.runs, c.num_runs = runs.ctypes.data, len(runs) - 1
+            c.dict, c.dict_len = (d.ctypes.data, len(d)) if d is not None and len(d) else (None, 0)
+            c.value_width, c.skip = width, int(col.get("skip", 0))
+        check(self._lib.ck_pack_encoded(self._h, cols, int(num_rows)))
 
     def pack_device_ptrs(self, row_ptr: int, col_ptr: int, alt_ptr: int, n: int) -> None:
         check(self._lib.ck_pack_triples(self._h, row_ptr, col_ptr, alt_ptr, n, 1))

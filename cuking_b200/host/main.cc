@@ -250,8 +250,15 @@ Status Run(const Flags &flags) {
     // CUKING_WIDE_TRIPLES=1: hand the pack kernel the columns at their physical widths (20 bytes per triple over PCIe, no
     // narrowing pass on the host) instead of the narrowed 9 bytes
     const bool narrow_triples = getenv("CUKING_WIDE_TRIPLES") == nullptr;
+    // Default: the pages go to the GPU still encoded (host: page codec + run headers only; ck_pack_encoded decodes and
+    // packs).  CUKING_HOST_DECODE=1 keeps libparquet's value decoding on the host (the path every unsupported file takes).
+    const bool device_decode = getenv("CUKING_HOST_DECODE") == nullptr;
+    size_t window_rows = size_t(2) << 20;
+    if (const char *v = getenv("CUKING_DECODE_WINDOW_ROWS")) window_rows = std::max<size_t>(1, strtoull(v, nullptr, 10));
+    std::atomic<size_t> host_decoded_files(0);
     auto worker = [&]() {
       cuking::Triples t(narrow_triples);
+      cuking::EncodedWindow win;
       for (;;) {
         const size_t f = next.fetch_add(1);
         if (f >= files.size()) return;
@@ -287,9 +294,37 @@ Status Run(const Flags &flags) {
           }
           return "";
         };
+        auto pack_encoded_on = [&](Gpu &g, size_t first_row) -> bool {
+          std::lock_guard<std::mutex> l(g.mu);
+          const int rc = ck_pack_encoded(g.planes, win.cols, win.num_rows);
+          if (rc == CK_OK) return true;
+          st = FromCk(rc);
+          st.message += " (chunk starting at row " + std::to_string(first_row) + ") in " + files[f];
+          return false;
+        };
+        auto consume_encoded = [&](size_t first_row) -> std::string {
+          if (exchange) {
+            if (!pack_encoded_on(gpus[next_chunk.fetch_add(1) % num_gpus], first_row)) return st.message;
+          } else {
+            for (Gpu &g : gpus)
+              if (!pack_encoded_on(g, first_row)) return st.message;
+          }
+          return "";
+        };
         size_t rows = 0;
-        if (std::string e = cuking::ReadTriples(files[f], kChunkRows, &t, consume, &rows); !e.empty() && st.ok())
-          st = (e.rfind("Error reading", 0) == 0) ? Unknown(e) : FailedPrecondition(e);
+        bool host_decode = !device_decode;
+        if (device_decode) {
+          bool unsupported = false;
+          if (std::string e = cuking::ReadEncoded(files[f], window_rows, &win, consume_encoded, &rows, &unsupported); !e.empty() && st.ok())
+            st = (e.rfind("Error reading", 0) == 0) ? Unknown(e) : FailedPrecondition(e);
+          host_decode = unsupported && st.ok();  // the windows already packed are packed again: harmless, the pack is an AND
+        }
+        if (host_decode) {
+          ++host_decoded_files;
+          rows = 0;
+          if (std::string e = cuking::ReadTriples(files[f], kChunkRows, &t, consume, &rows); !e.empty() && st.ok())
+            st = (e.rfind("Error reading", 0) == 0) ? Unknown(e) : FailedPrecondition(e);
+        }
         total_triples += rows;
         if (!st.ok()) {
           std::lock_guard<std::mutex> l(err_mu);
@@ -307,7 +342,9 @@ Status Run(const Flags &flags) {
     for (size_t i = 0; i < num_threads; ++i) threads.emplace_back(worker);
     for (auto &th : threads) th.join();
     if (!first_error.ok()) return first_error;
-    std::cout << " " << total_triples.load() << " entries (" << stop_watch.ElapsedAndReset() << ")" << std::endl;
+    std::cout << " " << total_triples.load() << " entries";
+    if (device_decode && host_decoded_files.load() > 0) std::cout << " [" << host_decoded_files.load() << " file(s) decoded on the host]";
+    std::cout << " (" << stop_watch.ElapsedAndReset() << ")" << std::endl;
   }
   if (exchange) {
     std::cout << "Exchanging bit sets between " << num_gpus << " GPUs...";

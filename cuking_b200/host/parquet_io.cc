@@ -3,9 +3,11 @@
 #include <arrow/io/file.h>
 #include <parquet/api/reader.h>
 #include <parquet/api/writer.h>
+#include <parquet/column_page.h>
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <filesystem>
 
 namespace cuking {
@@ -133,6 +135,277 @@ std::string ReadTriples(const std::string &path, size_t chunk_rows, Triples *buf
         if (!(err = consume(delivered)).empty()) return err;
         delivered += want;
         remaining -= want;
+      }
+    }
+    if (delivered != size_t(md->num_rows())) return "Column lengths differ from the row count in " + path;
+  } catch (const std::exception &e) {  // parquet::ParquetException, cuking.cu:580-583
+    return "Error reading " + path + ": " + e.what();
+  }
+  if (rows_out) *rows_out = delivered;
+  return "";
+}
+
+// ---- pages for the device decoder ---------------------------------------------------------------------------------
+
+namespace {
+std::string GrowPinned(uint8_t **ptr, size_t *cap, size_t used, size_t want) {
+  if (want <= *cap) return "";
+  const size_t ncap = std::max(want + want / 2, size_t(1) << 20);
+  void *fresh = nullptr;
+  if (ck_host_alloc(ncap, &fresh) != CK_OK) return std::string("Cannot allocate pinned host memory: ") + ck_last_error();
+  if (used) memcpy(fresh, *ptr, used);
+  ck_host_free(*ptr);
+  *ptr = static_cast<uint8_t *>(fresh);
+  *cap = ncap;
+  return "";
+}
+}  // namespace
+
+EncodedWindow::~EncodedWindow() {
+  for (Column &c : col) {
+    ck_host_free(c.bytes);
+    ck_host_free(c.runs);
+    ck_host_free(c.dict);
+  }
+}
+
+std::string EncodedWindow::Column::GrowBytes(size_t want) { return GrowPinned(&bytes, &bytes_cap, bytes_size, want); }
+std::string EncodedWindow::Column::GrowDict(size_t want) { return GrowPinned(&dict, &dict_cap, 0, want); }
+std::string EncodedWindow::Column::GrowRuns(size_t want) {
+  uint8_t *p = reinterpret_cast<uint8_t *>(runs);
+  size_t cap = runs_cap * sizeof(ck_run);
+  std::string e = GrowPinned(&p, &cap, runs_size * sizeof(ck_run), want * sizeof(ck_run));
+  runs = reinterpret_cast<ck_run *>(p);
+  runs_cap = cap / sizeof(ck_run);
+  return e;
+}
+
+void EncodedWindow::Column::Reset(uint32_t width) {
+  bytes_size = runs_size = 0;
+  dict_len = 0;
+  value_width = width;
+  first_row = 0;
+  num_values = 0;
+  pages.clear();
+}
+
+void EncodedWindow::Column::DropBefore(uint64_t row) {
+  size_t keep = 0;
+  while (keep < pages.size() && first_row + pages[keep].first_value + pages[keep].num_values <= row) ++keep;
+  if (keep == 0) return;
+  if (keep == pages.size()) {
+    first_row += num_values;
+    bytes_size = runs_size = 0;
+    num_values = 0;
+    pages.clear();
+    return;
+  }
+  // a page straddles the window's end: it becomes the head of the next window's table
+  const Page head = pages[keep];
+  const uint32_t dv = head.first_value, db = head.byte_begin, dr = head.run_begin;
+  memmove(bytes, bytes + db, bytes_size - db);
+  bytes_size -= db;
+  memmove(runs, runs + dr, (runs_size - dr) * sizeof(ck_run));
+  runs_size -= dr;
+  for (size_t r = 0; r < runs_size; ++r) {
+    runs[r].first_value -= dv;
+    if (runs[r].kind != CK_RUN_RLE) runs[r].payload -= db;
+  }
+  pages.erase(pages.begin(), pages.begin() + keep);
+  for (Page &p : pages) {
+    p.first_value -= dv;
+    p.byte_begin -= db;
+    p.byte_end -= db;
+    p.run_begin -= dr;
+    p.run_end -= dr;
+  }
+  first_row += dv;
+  num_values -= dv;
+}
+
+namespace {
+
+// All definition levels of an OPTIONAL column's page must be 1 (no nulls, cuking.cu:617-623): walks the hybrid stream.
+// Returns 1 = no nulls, 0 = nulls, -1 = malformed.
+int LevelsAllOne(const uint8_t *data, size_t n, uint32_t num_values, std::vector<ck_run> *scratch) {
+  scratch->resize(n + 2);
+  uint32_t runs = 0;
+  if (ck_rle_scan(data, n, 1, num_values, 0, 0, scratch->data(), uint32_t(scratch->size()), &runs) != CK_OK) return -1;
+  for (uint32_t r = 0; r < runs; ++r) {
+    const ck_run &run = (*scratch)[r];
+    const uint32_t count = (r + 1 < runs ? (*scratch)[r + 1].first_value : num_values) - run.first_value;
+    if (run.kind == CK_RUN_RLE) {
+      if (run.payload != 1) return 0;
+    } else {
+      const uint8_t *p = data + run.payload;
+      uint32_t full = count / 8, rest = count % 8;
+      for (uint32_t i = 0; i < full; ++i)
+        if (p[i] != 0xff) return 0;
+      if (rest && (p[full] & ((1u << rest) - 1u)) != ((1u << rest) - 1u)) return 0;
+    }
+  }
+  return 1;
+}
+
+bool DictionaryEncoding(parquet::Encoding::type e) {
+  return e == parquet::Encoding::RLE_DICTIONARY || e == parquet::Encoding::PLAIN_DICTIONARY;
+}
+
+// Appends one data page to a column of the window.  Returns "" / error; *unsupported as in ReadEncoded.
+std::string AppendPage(EncodedWindow::Column *c, const parquet::Page &page, bool optional, const std::string &path,
+                       std::vector<ck_run> *scratch, bool *unsupported) {
+  const uint8_t *data = nullptr;
+  size_t size = 0;
+  uint32_t num_values = 0;
+  parquet::Encoding::type enc;
+  if (page.type() == parquet::PageType::DATA_PAGE) {
+    const auto &p = static_cast<const parquet::DataPageV1 &>(page);
+    data = p.data();
+    size = size_t(p.size());
+    num_values = uint32_t(p.num_values());
+    enc = p.encoding();
+    if (optional) {  // [u32 length][hybrid definition levels]
+      if (p.definition_level_encoding() != parquet::Encoding::RLE) {
+        *unsupported = true;
+        return "";
+      }
+      if (size < 4) return "Error reading " + path + ": truncated data page";
+      uint32_t len;
+      memcpy(&len, data, 4);
+      if (size_t(len) + 4 > size) return "Error reading " + path + ": truncated definition levels";
+      const int ok = LevelsAllOne(data + 4, len, num_values, scratch);
+      if (ok < 0) return "Error reading " + path + ": malformed definition levels";
+      if (ok == 0) return "Null values in " + path;
+      data += 4 + len;
+      size -= 4 + len;
+    }
+  } else {
+    const auto &p = static_cast<const parquet::DataPageV2 &>(page);
+    data = p.data();
+    size = size_t(p.size());
+    num_values = uint32_t(p.num_values());
+    enc = p.encoding();
+    const size_t rl = size_t(p.repetition_levels_byte_length()), dl = size_t(p.definition_levels_byte_length());
+    if (rl + dl > size) return "Error reading " + path + ": truncated data page";
+    if (optional) {
+      if (p.num_nulls() != 0) return "Null values in " + path;
+      const int ok = LevelsAllOne(data + rl, dl, num_values, scratch);
+      if (ok < 0) return "Error reading " + path + ": malformed definition levels";
+      if (ok == 0) return "Null values in " + path;
+    }
+    data += rl + dl;
+    size -= rl + dl;
+  }
+  if (num_values == 0) return "";
+  if (size >= (size_t(1) << 31) || uint64_t(c->num_values) + num_values > 0x7fffffffull) {
+    *unsupported = true;
+    return "";
+  }
+  EncodedWindow::Page rec{};
+  rec.first_value = c->num_values;
+  rec.num_values = num_values;
+  rec.byte_begin = uint32_t((c->bytes_size + 7) & ~size_t(7));  // pages start 8-byte aligned (PLAIN values are read as words)
+  rec.run_begin = uint32_t(c->runs_size);
+  if (std::string e = c->GrowBytes(rec.byte_begin + size + 16); !e.empty()) return e;
+  memset(c->bytes + c->bytes_size, 0, rec.byte_begin - c->bytes_size);
+  if (DictionaryEncoding(enc)) {
+    if (size < 1) return "Error reading " + path + ": truncated dictionary-encoded page";
+    const uint32_t bit_width = data[0];
+    memcpy(c->bytes + rec.byte_begin, data + 1, size - 1);
+    c->bytes_size = rec.byte_begin + size - 1;
+    if (std::string e = c->GrowRuns(c->runs_size + size + 2); !e.empty()) return e;
+    uint32_t n = uint32_t(c->runs_size);
+    if (ck_rle_scan(c->bytes + rec.byte_begin, size - 1, bit_width, num_values, rec.first_value, rec.byte_begin, c->runs,
+                    uint32_t(c->runs_cap - 1), &n) != CK_OK)
+      return "Error reading " + path + ": " + ck_last_error();
+    c->runs_size = n;
+  } else if (enc == parquet::Encoding::PLAIN) {
+    if (size < size_t(num_values) * c->value_width) return "Error reading " + path + ": truncated PLAIN page";
+    memcpy(c->bytes + rec.byte_begin, data, size_t(num_values) * c->value_width);
+    c->bytes_size = rec.byte_begin + size_t(num_values) * c->value_width;
+    if (std::string e = c->GrowRuns(c->runs_size + 2); !e.empty()) return e;
+    c->runs[c->runs_size++] = ck_run{rec.first_value, CK_RUN_PLAIN, 0, rec.byte_begin};
+  } else {
+    *unsupported = true;
+    return "";
+  }
+  rec.byte_end = uint32_t(c->bytes_size);
+  rec.run_end = uint32_t(c->runs_size);
+  c->num_values += num_values;
+  c->pages.push_back(rec);
+  return "";
+}
+
+}  // namespace
+
+std::string ReadEncoded(const std::string &path, size_t window_rows, EncodedWindow *win,
+                        const std::function<std::string(size_t)> &consume, size_t *rows_out, bool *unsupported) {
+  size_t delivered = 0;
+  *unsupported = false;
+  try {
+    std::unique_ptr<parquet::ParquetFileReader> reader = parquet::ParquetFileReader::OpenFile(path, /*memory_map=*/false);
+    const auto md = reader->metadata();
+    constexpr int kNumColumns = 3;
+    if (md->num_columns() != kNumColumns)  // cuking.cu:585-590
+      return "Expected 3 columns, found " + std::to_string(md->num_columns()) + " in " + path;
+    const parquet::Type::type want_type[3] = {parquet::Type::INT64, parquet::Type::INT64, parquet::Type::INT32};
+    bool optional[3];
+    for (int c = 0; c < kNumColumns; ++c) {
+      const parquet::ColumnDescriptor *d = md->schema()->Column(c);
+      if (d->physical_type() != want_type[c])  // cuking.cu:608-612, :630-634, :652-656
+        return "Expected " + parquet::TypeToString(want_type[c]) + " type, found " + parquet::TypeToString(d->physical_type()) + " in " + path;
+      if (d->max_repetition_level() > 0) return "Repeated column in " + path;
+      if (d->max_definition_level() > 1) {
+        *unsupported = true;
+        return "";
+      }
+      optional[c] = d->max_definition_level() > 0;
+    }
+    std::vector<ck_run> scratch;
+    for (int rg = 0; rg < md->num_row_groups(); ++rg) {
+      auto group = reader->RowGroup(rg);
+      std::unique_ptr<parquet::PageReader> pages[3];
+      for (int c = 0; c < kNumColumns; ++c) {
+        pages[c] = group->GetColumnPageReader(c);
+        win->col[c].Reset(c == 2 ? 4 : 8);
+      }
+      const uint64_t rg_rows = uint64_t(md->RowGroup(rg)->num_rows());
+      uint64_t done = 0;
+      while (done < rg_rows) {
+        const uint64_t end = std::min<uint64_t>(done + window_rows, rg_rows);
+        for (int c = 0; c < kNumColumns; ++c) {
+          EncodedWindow::Column &col = win->col[c];
+          while (col.first_row + col.num_values < end) {
+            std::shared_ptr<parquet::Page> page = pages[c]->NextPage();
+            if (!page) return "Column lengths differ from the row count in " + path;
+            if (page->type() == parquet::PageType::DICTIONARY_PAGE) {
+              const auto &dp = static_cast<const parquet::DictionaryPage &>(*page);
+              if (dp.encoding() != parquet::Encoding::PLAIN && dp.encoding() != parquet::Encoding::PLAIN_DICTIONARY) {
+                *unsupported = true;
+                return "";
+              }
+              const size_t bytes = size_t(dp.num_values()) * col.value_width;
+              if (size_t(dp.size()) < bytes) return "Error reading " + path + ": truncated dictionary page";
+              if (std::string e = col.GrowDict(bytes); !e.empty()) return e;
+              memcpy(col.dict, dp.data(), bytes);
+              col.dict_len = uint32_t(dp.num_values());
+            } else if (page->type() == parquet::PageType::DATA_PAGE || page->type() == parquet::PageType::DATA_PAGE_V2) {
+              if (std::string e = AppendPage(&col, *page, optional[c], path, &scratch, unsupported); !e.empty() || *unsupported) return e;
+            }  // index pages carry no values
+          }
+        }
+        win->num_rows = uint32_t(end - done);
+        for (int c = 0; c < kNumColumns; ++c) {
+          EncodedWindow::Column &col = win->col[c];
+          if (std::string e = col.GrowRuns(col.runs_size + 1); !e.empty()) return e;
+          col.runs[col.runs_size] = ck_run{col.num_values, 0, 0, 0};  // sentinel
+          win->cols[c] = ck_encoded_column{col.bytes, col.bytes_size, col.runs, uint32_t(col.runs_size), col.dict, col.dict_len,
+                                           col.value_width, uint32_t(done - col.first_row)};
+        }
+        if (std::string e = consume(delivered); !e.empty()) return e;
+        delivered += size_t(end - done);
+        done = end;
+        for (int c = 0; c < kNumColumns; ++c) win->col[c].DropBefore(done);
       }
     }
     if (delivered != size_t(md->num_rows())) return "Column lengths differ from the row count in " + path;

@@ -57,6 +57,50 @@ std::string ListParquetFiles(const std::string &dir, std::vector<std::string> *f
 std::string ReadTriples(const std::string &path, size_t chunk_rows, Triples *buf,
                         const std::function<std::string(size_t)> &consume, size_t *rows_out);
 
+// ---- pages for the device decoder (ck_pack_encoded) -----------------------------------------------------------------
+// One window of rows of the three columns as page payloads + run tables + dictionaries, in page-locked memory that grows
+// geometrically and is reused by the owning reader thread.  The host only runs the page codec (parquet::PageReader) and
+// walks the run headers (ck_rle_scan); bit unpacking, dictionary lookup and the narrowing happen in the pack kernel.
+class EncodedWindow {
+ public:
+  EncodedWindow() = default;
+  EncodedWindow(const EncodedWindow &) = delete;
+  EncodedWindow &operator=(const EncodedWindow &) = delete;
+  ~EncodedWindow();
+  ck_encoded_column cols[3] = {};  // valid inside `consume`
+  uint32_t num_rows = 0;           // rows of the window
+
+  struct Page {  // one data page inside a column's buffers
+    uint32_t first_value, num_values, byte_begin, byte_end, run_begin, run_end;
+  };
+  struct Column {
+    uint8_t *bytes = nullptr;
+    size_t bytes_cap = 0, bytes_size = 0;
+    ck_run *runs = nullptr;
+    size_t runs_cap = 0, runs_size = 0;
+    uint8_t *dict = nullptr;
+    size_t dict_cap = 0;
+    uint32_t dict_len = 0, value_width = 0;
+    uint64_t first_row = 0;    // row (inside the row group) of table value 0
+    uint32_t num_values = 0;   // values described by the table
+    std::vector<Page> pages;
+    std::string GrowBytes(size_t want);
+    std::string GrowRuns(size_t want);
+    std::string GrowDict(size_t want);
+    void Reset(uint32_t width);
+    void DropBefore(uint64_t row);  // forgets the pages that end at or before `row` (a straddling page stays)
+  };
+  Column col[3];
+};
+
+// Streams one file through `win` in windows of at most `window_rows` rows: after each window `consume(first_row)` is called
+// with win->cols / win->num_rows describing it.  Same checks and error messages as ReadTriples.  *unsupported is set (and
+// "" returned, nothing more delivered) when the file uses something the device decoder does not take - an encoding other
+// than PLAIN / dictionary, legacy BIT_PACKED levels, a page of more than 2^31 bytes: the caller then reads the file with
+// ReadTriples instead (packing a triple twice is harmless, the pack is an AND).
+std::string ReadEncoded(const std::string &path, size_t window_rows, EncodedWindow *win,
+                        const std::function<std::string(size_t)> &consume, size_t *rows_out, bool *unsupported);
+
 // Writer of <dir>/part-<%05d shard>.snappy.parquet with the reference schema (all REQUIRED): i, j BYTE_ARRAY/String,
 // kin FLOAT, ibs0, ibs1, ibs2 INT32; Snappy (cuking.cu:770-798, :868-870).  Records are appended in sorted order chunk by
 // chunk, so a shard's output never has to sit in host memory as a whole (the reference sorts and writes from one

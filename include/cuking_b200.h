@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CK_ABI_VERSION 2
+#define CK_ABI_VERSION 3
 
 enum ck_status {
   CK_OK = 0,
@@ -180,6 +180,56 @@ int ck_pack_triples(ck_planes *planes, const int64_t *row_idx, const int64_t *co
  * columns once and use this entry point (host/parquet_io.cc does). */
 int ck_pack_triples_narrow(ck_planes *planes, const uint32_t *row_idx, const uint32_t *col_idx, const uint8_t *n_alt_alleles,
                            size_t num_triples, int on_device);
+
+/* ---- Parquet pages decoded on the device (replaces the ReadBatch loops of cuking.cu:603-672) ----
+ * The host only decompresses the pages of the three columns (parquet::PageReader, any codec) and walks the run headers of
+ * their RLE / bit-packed hybrid streams; bit unpacking, dictionary lookup, the int32 truncations and the pack itself run in
+ * one kernel.  About 2 bytes per triple cross PCIe instead of 9 (narrowed) or 20 (as decoded), and the host skips
+ * libparquet's value decoding altogether.
+ *
+ * A column of one window of rows is described by a table of runs over a byte buffer of page payloads:
+ *   CK_RUN_RLE        `count` copies of the dictionary index `payload`
+ *   CK_RUN_BITPACKED  dictionary indices of `bit_width` bits each, LSB first, starting at byte `payload` of the buffer
+ *                     (Parquet Encodings.md, "RLE/Bit-Packing Hybrid", the encoding of RLE_DICTIONARY / PLAIN_DICTIONARY
+ *                     data pages behind their bit-width byte)
+ *   CK_RUN_PLAIN      little-endian values of the column's physical width starting at byte `payload` (PLAIN data pages:
+ *                     the writer's fallback when a dictionary grows too large); `payload` is a multiple of that width
+ * Run r covers the values [first_value, runs[r + 1].first_value); first_value is strictly increasing and the table ends
+ * with a sentinel entry (kind ignored) whose first_value is the column's value count. */
+enum ck_run_kind { CK_RUN_RLE = 0, CK_RUN_BITPACKED = 1, CK_RUN_PLAIN = 2 };
+typedef struct ck_run {
+  uint32_t first_value; /* index of the run's first value in this column's window table */
+  uint32_t kind;        /* enum ck_run_kind */
+  uint32_t bit_width;   /* CK_RUN_BITPACKED: 0 .. 32 */
+  uint32_t payload;     /* see above */
+} ck_run;
+
+typedef struct ck_encoded_column {
+  const uint8_t *bytes; /* page payloads of the window (host memory; page-locked memory is copied faster) */
+  uint64_t num_bytes;
+  const ck_run *runs;   /* num_runs entries + the sentinel (host memory) */
+  uint32_t num_runs;
+  const void *dict;     /* PLAIN dictionary page: dict_len values of value_width bytes (NULL if no run needs it) */
+  uint32_t dict_len;
+  uint32_t value_width; /* 8 = INT64 (row_idx, col_idx), 4 = INT32 (n_alt_alleles) */
+  uint32_t skip;        /* leading values of the table that precede the window's first row (pages rarely end together
+                           in the three columns: a page that straddles two windows is simply described in both) */
+} ck_encoded_column;
+
+/* Walks one RLE / bit-packed hybrid stream of `num_values` values and appends its runs to runs[*num_runs ...] (capacity
+ * max_runs entries, sentinel not included and not written).  first_value = table index of the stream's first value,
+ * payload_base = byte offset of `data` inside the column's payload buffer.  Empty runs are dropped; the values of a
+ * last bit-packed group beyond num_values (padding) are not counted.  Pure host code.  CK_ERR_INVALID_ARGUMENT: the stream is malformed or ends early; CK_ERR_OUT_OF_RANGE: the
+ * table is full (num_bytes + 1 free entries always suffice). */
+int ck_rle_scan(const uint8_t *data, size_t num_bytes, uint32_t bit_width, uint32_t num_values, uint32_t first_value,
+                uint32_t payload_base, ck_run *runs, uint32_t max_runs, uint32_t *num_runs);
+
+/* Decodes rows [0, num_rows) of a window - row r is value skip + r of each column; cols[0] = row_idx, cols[1] = col_idx,
+ * cols[2] = n_alt_alleles - and packs them exactly like ck_pack_triples (same filter, truncations and errors; the
+ * "triple" index of an error message is the row inside the window).  A table that is inconsistent with its buffers
+ * (run outside the payload bytes, dictionary index >= dict_len, unsorted runs) fails with CK_ERR_INVALID_ARGUMENT
+ * before or instead of touching the planes' neighbours.  Synchronous like ck_pack_triples. */
+int ck_pack_encoded(ck_planes *planes, const ck_encoded_column cols[3], uint32_t num_rows);
 
 /* Page-locked host memory for triple buffers.  ck_pack_triples recognises it (and any other cudaHostAlloc /
  * cudaHostRegister memory) and lets the pack kernel stream the triples straight over PCIe, skipping the staging copy;

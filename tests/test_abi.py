@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/cuking_b200.h but not exported"
     assert sorted(capi.EXPORTED_SYMBOLS) == declared
-    assert capi.load().ck_abi_version() == 2
+    assert capi.load().ck_abi_version() == 3
 
 
 def test_struct_layouts():

@@ -32,7 +32,9 @@ ap.add_argument("--threshold", type=float, default=0.0884)
 ap.add_argument("--num-gpus", default="1", help="comma list: the binary is run once per entry on the same input")
 ap.add_argument("--split-factor", type=int, default=1, help="> 1: --all_shards with this split factor")
 ap.add_argument("--repeat", type=int, default=1, help="runs per configuration (page cache warm after the first)")
-ap.add_argument("--modes", default="narrow", help="comma list of narrow,wide (CUKING_WIDE_TRIPLES)")
+ap.add_argument("--modes", default="device", help="comma list of device (pages decoded on the GPU, the default of the binary), "
+                "narrow (CUKING_HOST_DECODE=1: libparquet decode + 9-byte triples), wide (that + CUKING_WIDE_TRIPLES=1)")
+ap.add_argument("--window-rows", type=int, default=0, help="CUKING_DECODE_WINDOW_ROWS for the device mode")
 args = ap.parse_args()
 
 with tempfile.TemporaryDirectory() as tmp:
@@ -56,8 +58,12 @@ with tempfile.TemporaryDirectory() as tmp:
             cmd += [f"--split_factor={args.split_factor}", "--all_shards", "--write_success_file"]
         t0 = time.perf_counter()
         env = dict(os.environ)
+        if mode in ("narrow", "wide"):
+            env["CUKING_HOST_DECODE"] = "1"
         if mode == "wide":
             env["CUKING_WIDE_TRIPLES"] = "1"
+        if mode == "device" and args.window_rows:
+            env["CUKING_DECODE_WINDOW_ROWS"] = str(args.window_rows)
         p = subprocess.run(cmd, capture_output=True, text=True, env=env)
         wall = time.perf_counter() - t0
         if p.returncode != 0:
