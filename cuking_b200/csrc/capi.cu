@@ -304,7 +304,16 @@ int ck_ctx_destroy(ck_ctx *ctx) {
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->h_holes) cudaFreeHost(ctx->h_holes);
   if (ctx->d_pack_err) cudaFree(ctx->d_pack_err);
-  if (ctx->decode_staging) cudaFree(ctx->decode_staging);
+  for (ck_ctx::IngestLane *lane : ctx->lanes_all) {
+    if (lane->stream) cudaStreamDestroy(lane->stream);
+    if (lane->dep) cudaEventDestroy(lane->dep);
+    for (cudaEvent_t ev : lane->ev)
+      if (ev) cudaEventDestroy(ev);
+    if (lane->staging) cudaFree(lane->staging);
+    if (lane->d_err) cudaFree(lane->d_err);
+    if (lane->h_err) cudaFreeHost(lane->h_err);
+    delete lane;
+  }
   if (ctx->dense_table) cudaFree(ctx->dense_table);
   for (void *p : ctx->out_pinned)
     if (p) cudaFreeHost(p);

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -60,8 +61,19 @@ struct ck_ctx {
   unsigned long long *h_holes = nullptr;        // pinned host mirror of the hole counters
   unsigned long long *d_pack_err = nullptr;     // [0] invalid-genotype index+1 (min), [1] out-of-range index+1 (min),
                                                 // [2] dictionary index out of range (ck_pack_encoded), [3] spare
-  void *decode_staging = nullptr;               // grow-only device copy of one window's payloads, run tables and dictionaries
-  size_t decode_staging_bytes = 0;
+  // ck_pack_encoded may be called by several host threads at once (the decode threads of bin/cuking): every call takes a
+  // free lane - its own stream, device staging buffer and error slots - so the calls overlap on the GPU instead of queueing
+  // behind one host lock; lanes are created on demand and live as long as the ctx
+  struct IngestLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t dep = nullptr, ev[2] = {nullptr, nullptr};
+    void *staging = nullptr;  // grow-only device copy of one window's payloads, run tables and dictionaries
+    size_t staging_bytes = 0;
+    unsigned long long *d_err = nullptr;  // 4 slots like d_pack_err
+    unsigned long long *h_err = nullptr;  // page-locked mirror
+  };
+  std::mutex lane_mu;
+  std::vector<IngestLane *> lanes_free, lanes_all;
   void *pinned[2] = {nullptr, nullptr};   // host staging for ck_pack_triples(on_device = 0)
   void *staging[2] = {nullptr, nullptr};  // device side of the same double buffer
   size_t pinned_bytes = 0;

@@ -106,6 +106,45 @@ int check_column(const ck_encoded_column &c, uint32_t num_rows, int which) {
 
 size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
+// A free ingest lane of the ctx for the duration of one call (created on first need).
+struct LaneLease {
+  ck_ctx *ctx;
+  ck_ctx::IngestLane *lane = nullptr;
+  explicit LaneLease(ck_ctx *c) : ctx(c) {}
+  LaneLease(const LaneLease &) = delete;
+  LaneLease &operator=(const LaneLease &) = delete;
+  int acquire() {
+    {
+      std::lock_guard<std::mutex> l(ctx->lane_mu);
+      if (!ctx->lanes_free.empty()) {
+        lane = ctx->lanes_free.back();
+        ctx->lanes_free.pop_back();
+        return CK_OK;
+      }
+    }
+    auto *fresh = new (std::nothrow) ck_ctx::IngestLane();
+    if (!fresh) return fail(CK_ERR_OUT_OF_MEMORY, "host allocation failed");
+    {
+      std::lock_guard<std::mutex> l(ctx->lane_mu);
+      ctx->lanes_all.push_back(fresh);  // owned by the ctx from here on, whatever happens below
+    }
+    CK_CUDA(cudaStreamCreateWithFlags(&fresh->stream, cudaStreamNonBlocking));
+    CK_CUDA(cudaEventCreateWithFlags(&fresh->dep, cudaEventDisableTiming));
+    CK_CUDA(cudaEventCreate(&fresh->ev[0]));
+    CK_CUDA(cudaEventCreate(&fresh->ev[1]));
+    CK_CUDA(cudaMalloc(&fresh->d_err, 4 * sizeof(unsigned long long)));
+    CK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&fresh->h_err), 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    lane = fresh;
+    return CK_OK;
+  }
+  ~LaneLease() {
+    if (!lane) return;
+    cudaStreamSynchronize(lane->stream);  // error exits: nothing of this call may still be in flight when the lane is reused
+    std::lock_guard<std::mutex> l(ctx->lane_mu);
+    ctx->lanes_free.push_back(lane);
+  }
+};
+
 }  // namespace
 
 extern "C" {
@@ -168,55 +207,100 @@ int ck_pack_encoded(ck_planes *pl, const ck_encoded_column cols[3], uint32_t num
     if (int rc = check_column(cols[c], num_rows, c); rc != CK_OK) return rc;
   ck_ctx *ctx = pl->ctx;
   DeviceGuard guard(ctx->device);
-  cudaStream_t s = ctx->stream;
+  LaneLease lease(ctx);
+  if (int rc = lease.acquire(); rc != CK_OK) return rc;
+  ck_ctx::IngestLane *lane = lease.lane;
+  cudaStream_t s = lane->stream;
+  // the lane's stream starts behind whatever the ctx's stream has been given so far (plane allocation, reset, an earlier pack)
+  CK_CUDA(cudaEventRecord(lane->dep, ctx->stream));
+  CK_CUDA(cudaStreamWaitEvent(s, lane->dep, 0));
 
-  // one device buffer: per column [payload words + 16 bytes of zero padding | runs + sentinel | dictionary]
-  size_t off[3][3], total = 0;
+  // Device copy of the window.  When the nine pieces (payload, runs + sentinel, dictionary per column) sit close together
+  // in host memory - host/parquet_io.cc stages every window in one page-locked arena - the whole span goes up with ONE
+  // copy and the device pointers keep the host offsets; otherwise piece by piece into
+  // [payload + 16 zero bytes | runs | dictionary] x 3.  (The funnel shift of decode_rows reads one word past a payload:
+  // whatever it finds there is masked off.)
+  struct Piece { const void *host; size_t bytes, align; };
+  Piece pieces[3][3];
+  uintptr_t lo = ~uintptr_t(0), hi = 0;
+  size_t sum = 0;
+  bool aligned = true;
   for (int c = 0; c < 3; ++c) {
-    off[c][0] = total;
-    total += align16(size_t(cols[c].num_bytes) + 16);
-    off[c][1] = total;
-    total += align16((size_t(cols[c].num_runs) + 1) * sizeof(ck_run));
-    off[c][2] = total;
-    total += align16(size_t(cols[c].dict_len) * cols[c].value_width);
+    pieces[c][0] = Piece{cols[c].bytes, size_t(cols[c].num_bytes), 8};
+    pieces[c][1] = Piece{cols[c].runs, (size_t(cols[c].num_runs) + 1) * sizeof(ck_run), 16};
+    pieces[c][2] = Piece{cols[c].dict, size_t(cols[c].dict_len) * cols[c].value_width, 8};
+    for (const Piece &p : pieces[c]) {
+      if (p.bytes == 0) continue;
+      const uintptr_t a = reinterpret_cast<uintptr_t>(p.host);
+      lo = std::min(lo, a);
+      hi = std::max(hi, a + p.bytes);
+      sum += p.bytes;
+      aligned = aligned && a % p.align == 0;
+    }
   }
-  if (total > ctx->decode_staging_bytes) {
-    if (ctx->decode_staging) {
-      CK_CUDA(cudaStreamSynchronize(s));
-      CK_CUDA(cudaFree(ctx->decode_staging));
-      ctx->decode_staging = nullptr;
-      ctx->decode_staging_bytes = 0;
+  lo &= ~uintptr_t(15);
+  const bool one_copy = aligned && hi - lo <= sum + 4096;
+  size_t off[3][3], total = 0;
+  if (one_copy) {
+    total = align16(hi - lo) + 16;
+    for (int c = 0; c < 3; ++c)
+      for (int k = 0; k < 3; ++k) off[c][k] = pieces[c][k].bytes ? reinterpret_cast<uintptr_t>(pieces[c][k].host) - lo : 0;
+  } else {
+    for (int c = 0; c < 3; ++c) {
+      off[c][0] = total;
+      total += align16(pieces[c][0].bytes + 16);
+      off[c][1] = total;
+      total += align16(pieces[c][1].bytes);
+      off[c][2] = total;
+      total += align16(pieces[c][2].bytes);
+    }
+  }
+  if (total > lane->staging_bytes) {
+    if (lane->staging) {
+      CK_CUDA(cudaFree(lane->staging));  // the lane is idle: every call ends with a synchronisation of its stream
+      lane->staging = nullptr;
+      lane->staging_bytes = 0;
     }
     const size_t want = std::max(total + total / 2, size_t(8) << 20);
-    CK_CUDA(dev_alloc(ctx, &ctx->decode_staging, want));
-    ctx->decode_staging_bytes = want;
+    {
+      std::lock_guard<std::mutex> l(ctx->lane_mu);  // dev_alloc may drop the ctx's buffer cache
+      CK_CUDA(dev_alloc(ctx, &lane->staging, want));
+    }
+    lane->staging_bytes = want;
   }
-  char *d = static_cast<char *>(ctx->decode_staging);
-  CK_CUDA(cudaMemsetAsync(ctx->d_pack_err, 0xff, 4 * sizeof(unsigned long long), s));
-  pl->mark_stale();
-  CK_CUDA(cudaEventRecord(ctx->ev[0], s));
+  char *d = static_cast<char *>(lane->staging);
+  CK_CUDA(cudaMemsetAsync(lane->d_err, 0xff, 4 * sizeof(unsigned long long), s));
+  CK_CUDA(cudaEventRecord(lane->ev[0], s));
+  if (one_copy) {
+    CK_CUDA(cudaMemcpyAsync(d, reinterpret_cast<const void *>(lo), hi - lo, cudaMemcpyHostToDevice, s));
+  } else {
+    for (int c = 0; c < 3; ++c) {
+      const size_t nb = pieces[c][0].bytes;
+      CK_CUDA(cudaMemsetAsync(d + off[c][0] + (nb & ~size_t(15)), 0, align16(nb + 16) - (nb & ~size_t(15)), s));
+      for (int k = 0; k < 3; ++k)
+        if (pieces[c][k].bytes) CK_CUDA(cudaMemcpyAsync(d + off[c][k], pieces[c][k].host, pieces[c][k].bytes, cudaMemcpyHostToDevice, s));
+    }
+  }
   EncodedColumnDev dev[3];
   for (int c = 0; c < 3; ++c) {
-    const ck_encoded_column &col = cols[c];
-    const size_t nb = size_t(col.num_bytes);
-    CK_CUDA(cudaMemsetAsync(d + off[c][0] + (nb & ~size_t(15)), 0, align16(nb + 16) - (nb & ~size_t(15)), s));  // the funnel shift reads one word ahead
-    if (nb) CK_CUDA(cudaMemcpyAsync(d + off[c][0], col.bytes, nb, cudaMemcpyHostToDevice, s));
-    CK_CUDA(cudaMemcpyAsync(d + off[c][1], col.runs, (size_t(col.num_runs) + 1) * sizeof(ck_run), cudaMemcpyHostToDevice, s));
-    if (col.dict_len) CK_CUDA(cudaMemcpyAsync(d + off[c][2], col.dict, size_t(col.dict_len) * col.value_width, cudaMemcpyHostToDevice, s));
     dev[c].words = reinterpret_cast<const uint32_t *>(d + off[c][0]);
     dev[c].runs = reinterpret_cast<const ck_run *>(d + off[c][1]);
     dev[c].dict = d + off[c][2];
-    dev[c].num_runs = col.num_runs;
-    dev[c].dict_len = col.dict_len;
-    dev[c].width = col.value_width;
-    dev[c].skip = col.skip;
+    dev[c].num_runs = cols[c].num_runs;
+    dev[c].dict_len = cols[c].dict_len;
+    dev[c].width = cols[c].value_width;
+    dev[c].skip = cols[c].skip;
   }
-  CK_CUDA(launch_decode_pack(*pl, dev, num_rows, ctx->d_pack_err, s));
-  CK_CUDA(cudaEventRecord(ctx->ev[1], s));
-  unsigned long long err[4];
-  CK_CUDA(cudaMemcpyAsync(err, ctx->d_pack_err, sizeof(err), cudaMemcpyDeviceToHost, s));
+  CK_CUDA(launch_decode_pack(*pl, dev, num_rows, lane->d_err, s));
+  CK_CUDA(cudaEventRecord(lane->ev[1], s));
+  CK_CUDA(cudaMemcpyAsync(lane->h_err, lane->d_err, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CK_CUDA(cudaStreamSynchronize(s));
-  ctx->timings.pack_ms = elapsed_ms(ctx->ev[0], ctx->ev[1]);
+  const unsigned long long *err = lane->h_err;
+  {
+    std::lock_guard<std::mutex> l(ctx->lane_mu);
+    pl->mark_stale();
+    ctx->timings.pack_ms = elapsed_ms(lane->ev[0], lane->ev[1]);
+  }
   if (err[2] != ~0ull)
     return fail(CK_ERR_INVALID_ARGUMENT, "dictionary index outside the dictionary at row " + std::to_string(size_t(err[2]) - 1) + " of the window (corrupt page)");
   if (err[0] != ~0ull) {

@@ -21,11 +21,15 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <filesystem>
 #include <fstream>
+#include <functional>
+#include <future>
 #include <iostream>
 #include <memory>
 #include <mutex>
@@ -246,29 +250,139 @@ Status Run(const Flags &flags) {
     std::atomic<size_t> next(0), processed(0), total_triples(0), next_chunk(0);
     std::mutex err_mu;
     Status first_error;  // first error wins, like ParallelFor (cuking.cu:415-433)
+    std::atomic<bool> failed(false);
+    std::mutex q_mu;  // guards the window queue and the slice pool below
+    std::condition_variable q_jobs, q_slices;
+    auto fail_with = [&](const Status &st) {
+      {
+        std::lock_guard<std::mutex> l(err_mu);
+        if (first_error.ok()) first_error = st;
+      }
+      {
+        std::lock_guard<std::mutex> l(q_mu);  // readers test `failed` under q_mu before they sleep on q_slices
+        failed = true;
+      }
+      q_slices.notify_all();
+    };
     constexpr size_t kChunkRows = size_t(1) << 20;  // 20 MiB of page-locked memory per reader thread
     // CUKING_WIDE_TRIPLES=1: hand the pack kernel the columns at their physical widths (20 bytes per triple over PCIe, no
     // narrowing pass on the host) instead of the narrowed 9 bytes
     const bool narrow_triples = getenv("CUKING_WIDE_TRIPLES") == nullptr;
-    // Default: the pages go to the GPU still encoded (host: page codec + run headers only; ck_pack_encoded decodes and
-    // packs).  CUKING_HOST_DECODE=1 keeps libparquet's value decoding on the host (the path every unsupported file takes).
+    // Default: the pages go to the GPU still encoded.  The reader threads only run the page codec and walk the run headers;
+    // a finished window is laid out in a page-locked slice and queued, and two submitter threads per GPU hand the windows to
+    // ck_pack_encoded (bit unpacking, dictionary lookup, narrowing and the pack in one kernel).  The readers never wait for
+    // the GPU unless every slice is in flight.  CUKING_HOST_DECODE=1 keeps libparquet's value decoding on the host (the
+    // path every unsupported file takes by itself).
     const bool device_decode = getenv("CUKING_HOST_DECODE") == nullptr;
-    size_t window_rows = size_t(2) << 20;
+    size_t window_rows = size_t(1) << 20;
     if (const char *v = getenv("CUKING_DECODE_WINDOW_ROWS")) window_rows = std::max<size_t>(1, strtoull(v, nullptr, 10));
     std::atomic<size_t> host_decoded_files(0);
+    const size_t num_threads = std::min(flags.num_reader_threads, files.size());
+
+    // ---- page-locked slices and the window queue ----
+    constexpr size_t kSliceBytes = size_t(4) << 20;
+    const bool queued = device_decode && (exchange || num_gpus == 1);  // every window goes to exactly one GPU
+    const size_t num_submitters = queued ? 2 * num_gpus : 0;
+    const size_t num_slices = queued ? std::min<size_t>(32, std::max<size_t>(8, 4 * num_submitters)) : 0;
+    struct Job {
+      ck_encoded_column cols[3];
+      uint32_t num_rows = 0;
+      uint8_t *slice = nullptr;
+      size_t file = 0, first_row = 0;
+    };
+    std::deque<Job> jobs;
+    std::vector<uint8_t *> free_slices, all_slices;
+    bool q_closed = false;
+    size_t slices_made = 0;
+    // page-locking memory is slow and holds up the other CUDA calls of the process: a helper makes the slices one by one
+    // while the readers are already decompressing their first pages
+    std::thread slice_maker;
+    if (queued)
+      slice_maker = std::thread([&] {
+        for (size_t i = 0; i < num_slices && !failed; ++i) {
+          void *p = nullptr;
+          const bool ok = ck_host_alloc(kSliceBytes, &p) == CK_OK;
+          std::lock_guard<std::mutex> l(q_mu);
+          ++slices_made;
+          if (ok) {
+            all_slices.push_back(static_cast<uint8_t *>(p));
+            free_slices.push_back(static_cast<uint8_t *>(p));
+          }
+          q_slices.notify_all();
+        }
+      });
+    auto acquire_slice = [&]() -> uint8_t * {
+      std::unique_lock<std::mutex> l(q_mu);
+      q_slices.wait(l, [&] { return failed || !free_slices.empty() || (slices_made == num_slices && all_slices.empty()); });
+      if (failed || free_slices.empty()) return nullptr;
+      uint8_t *p = free_slices.back();
+      free_slices.pop_back();
+      return p;
+    };
+    std::mutex stats_mu;
+    double s_pages = 0, s_scan = 0, s_stage = 0, s_wait = 0, s_pack = 0, s_pack_gpu = 0;  // CUKING_INGEST_STATS=1
+    size_t windows = 0;
+    auto pack_window = [&](Gpu &g, const ck_encoded_column *cols, uint32_t num_rows, size_t file, size_t first_row, double *wall, double *gpu) {
+      const auto t0 = std::chrono::steady_clock::now();
+      const int rc = ck_pack_encoded(g.planes, cols, num_rows);  // thread-safe: every call runs on its own lane of the ctx
+      *wall += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      ck_timings tm{};
+      ck_ctx_get_timings(g.ctx, &tm);
+      *gpu += tm.pack_ms * 1e-3;
+      if (rc == CK_OK) return true;
+      Status st = FromCk(rc);
+      st.message += " (chunk starting at row " + std::to_string(first_row) + ") in " + files[file];
+      fail_with(st);
+      return false;
+    };
+    auto submitter = [&](size_t index) {
+      Gpu &g = gpus[index % num_gpus];
+      double wall = 0, gpu = 0;
+      size_t count = 0;
+      for (;;) {
+        Job job;
+        {
+          std::unique_lock<std::mutex> l(q_mu);
+          q_jobs.wait(l, [&] { return q_closed || !jobs.empty(); });
+          if (jobs.empty()) break;
+          job = jobs.front();
+          jobs.pop_front();
+        }
+        if (!failed) {
+          pack_window(g, job.cols, job.num_rows, job.file, job.first_row, &wall, &gpu);
+          ++count;
+        }
+        {
+          std::lock_guard<std::mutex> l(q_mu);
+          free_slices.push_back(job.slice);
+        }
+        q_slices.notify_one();
+      }
+      std::lock_guard<std::mutex> l(stats_mu);
+      s_pack += wall, s_pack_gpu += gpu, windows += count;
+    };
+    std::vector<std::thread> submitters;
+    for (size_t i = 0; i < num_submitters; ++i) submitters.emplace_back(submitter, i);
+
     auto worker = [&]() {
       cuking::Triples t(narrow_triples);
       cuking::EncodedWindow win;
+      double my_pack = 0, my_pack_gpu = 0;
+      size_t my_windows = 0;
+      struct Report {
+        std::function<void()> fn;
+        ~Report() { fn(); }
+      } report{[&] {
+        std::lock_guard<std::mutex> l(stats_mu);
+        s_pages += win.s_pages, s_scan += win.s_scan, s_stage += win.s_stage, s_wait += win.s_wait, s_pack += my_pack, s_pack_gpu += my_pack_gpu;
+        windows += my_windows;
+      }};
       for (;;) {
         const size_t f = next.fetch_add(1);
-        if (f >= files.size()) return;
-        {
-          std::lock_guard<std::mutex> l(err_mu);
-          if (!first_error.ok()) return;
-        }
+        if (f >= files.size() || failed) return;
         Status st;
-        // Stream the file through this thread's chunk buffers: decode a chunk, narrow it to 9 bytes per triple in page-locked
-        // memory, let ONE GPU pack it (the kernel reads the pinned chunk in place over PCIe), decode the next chunk.
+        // Host decode: stream the file through this thread's chunk buffers - decode a chunk, narrow it to 9 bytes per triple
+        // in page-locked memory, let ONE GPU pack it (the kernel reads the pinned chunk in place over PCIe), decode the next.
         auto pack_on = [&](Gpu &g, size_t first_row) -> bool {
           std::lock_guard<std::mutex> l(g.mu);
           const int rc = t.narrow() ? ck_pack_triples_narrow(g.planes, t.row32, t.col32, t.alt8, t.size, /*on_device=*/0)
@@ -294,29 +408,35 @@ Status Run(const Flags &flags) {
           }
           return "";
         };
-        auto pack_encoded_on = [&](Gpu &g, size_t first_row) -> bool {
-          std::lock_guard<std::mutex> l(g.mu);
-          const int rc = ck_pack_encoded(g.planes, win.cols, win.num_rows);
-          if (rc == CK_OK) return true;
-          st = FromCk(rc);
-          st.message += " (chunk starting at row " + std::to_string(first_row) + ") in " + files[f];
-          return false;
-        };
-        auto consume_encoded = [&](size_t first_row) -> std::string {
-          if (exchange) {
-            if (!pack_encoded_on(gpus[next_chunk.fetch_add(1) % num_gpus], first_row)) return st.message;
-          } else {
-            for (Gpu &g : gpus)
-              if (!pack_encoded_on(g, first_row)) return st.message;
+        // Device decode: queue the window (its slice goes with it), or - no queue, or a window too large for a slice - pack it
+        // from the window's own arena before going on.
+        auto consume_encoded = [&](size_t first_row, uint8_t *slice) -> std::string {
+          if (slice) {
+            Job job;
+            for (int c = 0; c < 3; ++c) job.cols[c] = win.cols[c];
+            job.num_rows = win.num_rows, job.slice = slice, job.file = f, job.first_row = first_row;
+            {
+              std::lock_guard<std::mutex> l(q_mu);
+              jobs.push_back(job);
+            }
+            q_jobs.notify_one();
+            return failed ? "Aborted" : "";
           }
+          ++my_windows;
+          if (exchange || num_gpus == 1)
+            return pack_window(gpus[next_chunk.fetch_add(1) % num_gpus], win.cols, win.num_rows, f, first_row, &my_pack, &my_pack_gpu) ? "" : "Aborted";
+          for (Gpu &g : gpus)
+            if (!pack_window(g, win.cols, win.num_rows, f, first_row, &my_pack, &my_pack_gpu)) return "Aborted";
           return "";
         };
         size_t rows = 0;
         bool host_decode = !device_decode;
         if (device_decode) {
           bool unsupported = false;
-          if (std::string e = cuking::ReadEncoded(files[f], window_rows, &win, consume_encoded, &rows, &unsupported); !e.empty() && st.ok())
-            st = (e.rfind("Error reading", 0) == 0) ? Unknown(e) : FailedPrecondition(e);
+          const std::string e = cuking::ReadEncoded(files[f], window_rows, kSliceBytes, &win, queued ? std::function<uint8_t *()>(acquire_slice) : nullptr,
+                                                    consume_encoded, &rows, &unsupported);
+          if (e == "Aborted") return;  // another thread (or the GPU side of this one) has already recorded the error
+          if (!e.empty()) st = (e.rfind("Error reading", 0) == 0) ? Unknown(e) : FailedPrecondition(e);
           host_decode = unsupported && st.ok();  // the windows already packed are packed again: harmless, the pack is an AND
         }
         if (host_decode) {
@@ -327,8 +447,7 @@ Status Run(const Flags &flags) {
         }
         total_triples += rows;
         if (!st.ok()) {
-          std::lock_guard<std::mutex> l(err_mu);
-          if (first_error.ok()) first_error = st;
+          fail_with(st);
           return;
         }
         if ((++processed & ((size_t(1) << 10) - 1)) == 0) {  // progress indicator, cuking.cu:705-708
@@ -337,14 +456,25 @@ Status Run(const Flags &flags) {
         }
       }
     };
-    const size_t num_threads = std::min(flags.num_reader_threads, files.size());
     std::vector<std::thread> threads;
     for (size_t i = 0; i < num_threads; ++i) threads.emplace_back(worker);
     for (auto &th : threads) th.join();
+    {
+      std::lock_guard<std::mutex> l(q_mu);
+      q_closed = true;
+    }
+    q_jobs.notify_all();
+    for (auto &th : submitters) th.join();
+    if (slice_maker.joinable()) slice_maker.join();
+    for (uint8_t *p : all_slices) ck_host_free(p);
     if (!first_error.ok()) return first_error;
     std::cout << " " << total_triples.load() << " entries";
     if (device_decode && host_decoded_files.load() > 0) std::cout << " [" << host_decoded_files.load() << " file(s) decoded on the host]";
     std::cout << " (" << stop_watch.ElapsedAndReset() << ")" << std::endl;
+    if (getenv("CUKING_INGEST_STATS"))
+      std::cout << "Ingest thread-seconds over " << num_threads << " readers + " << num_submitters << " submitters: page read + codec " << s_pages
+                << ", run scan + copy " << s_scan << ", staging " << s_stage << ", waiting for a free slice " << s_wait << ", ck_pack_encoded "
+                << s_pack << " (GPU " << s_pack_gpu << ") in " << windows << " windows" << std::endl;
   }
   if (exchange) {
     std::cout << "Exchanging bit sets between " << num_gpus << " GPUs...";

@@ -6,7 +6,9 @@
 #include <parquet/column_page.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <filesystem>
 
@@ -148,36 +150,102 @@ std::string ReadTriples(const std::string &path, size_t chunk_rows, Triples *buf
 // ---- pages for the device decoder ---------------------------------------------------------------------------------
 
 namespace {
-std::string GrowPinned(uint8_t **ptr, size_t *cap, size_t used, size_t want) {
+// pageable, geometric growth (the page-locked memory is the window's one arena, below)
+std::string GrowHeap(uint8_t **ptr, size_t *cap, size_t used, size_t want) {
   if (want <= *cap) return "";
-  const size_t ncap = std::max(want + want / 2, size_t(1) << 20);
-  void *fresh = nullptr;
-  if (ck_host_alloc(ncap, &fresh) != CK_OK) return std::string("Cannot allocate pinned host memory: ") + ck_last_error();
+  const size_t ncap = std::max(want + want / 2, size_t(1) << 16);
+  void *fresh = aligned_alloc(64, (ncap + 63) & ~size_t(63));
+  if (!fresh) return "Out of host memory";
   if (used) memcpy(fresh, *ptr, used);
-  ck_host_free(*ptr);
+  free(*ptr);
   *ptr = static_cast<uint8_t *>(fresh);
   *cap = ncap;
   return "";
 }
+size_t Align64(size_t x) { return (x + 63) & ~size_t(63); }
 }  // namespace
 
 EncodedWindow::~EncodedWindow() {
   for (Column &c : col) {
-    ck_host_free(c.bytes);
-    ck_host_free(c.runs);
-    ck_host_free(c.dict);
+    free(c.bytes);
+    free(c.runs);
+    free(c.dict);
   }
+  ck_host_free(arena_);
 }
 
-std::string EncodedWindow::Column::GrowBytes(size_t want) { return GrowPinned(&bytes, &bytes_cap, bytes_size, want); }
-std::string EncodedWindow::Column::GrowDict(size_t want) { return GrowPinned(&dict, &dict_cap, 0, want); }
+std::string EncodedWindow::Column::GrowBytes(size_t want) { return GrowHeap(&bytes, &bytes_cap, bytes_size, want); }
+std::string EncodedWindow::Column::GrowDict(size_t want) { return GrowHeap(&dict, &dict_cap, 0, want); }
 std::string EncodedWindow::Column::GrowRuns(size_t want) {
   uint8_t *p = reinterpret_cast<uint8_t *>(runs);
   size_t cap = runs_cap * sizeof(ck_run);
-  std::string e = GrowPinned(&p, &cap, runs_size * sizeof(ck_run), want * sizeof(ck_run));
+  std::string e = GrowHeap(&p, &cap, runs_size * sizeof(ck_run), want * sizeof(ck_run));
   runs = reinterpret_cast<ck_run *>(p);
   runs_cap = cap / sizeof(ck_run);
   return e;
+}
+
+namespace {
+struct Cut {  // the part of a column's buffers that describes the rows before `end_row`
+  size_t bytes, runs;
+  uint32_t values;
+};
+Cut CutAt(const EncodedWindow::Column &c, uint64_t end_row) {
+  for (const EncodedWindow::Page &p : c.pages)
+    if (c.first_row + p.first_value >= end_row) return Cut{p.byte_begin, p.run_begin, p.first_value};
+  return Cut{c.bytes_size, c.runs_size, c.num_values};
+}
+}  // namespace
+
+size_t EncodedWindow::StagedBytes(uint64_t end_row) const {
+  size_t total = 0;
+  for (const Column &c : col) {
+    const Cut cut = CutAt(c, end_row);
+    total += Align64(cut.bytes + 16) + Align64((cut.runs + 1) * sizeof(ck_run)) + Align64(size_t(c.dict_len) * c.value_width);
+  }
+  return total;
+}
+
+std::string EncodedWindow::Stage(uint64_t first_row, uint64_t end_row, uint8_t *dst) {
+  if (!dst) {  // the window's own arena: page-locking is slow (and stalls other CUDA calls), so it only ever grows
+    const size_t total = StagedBytes(end_row);
+    if (total > arena_cap_) {
+      ck_host_free(arena_);
+      arena_ = nullptr;
+      arena_cap_ = 0;
+      const size_t want = std::max(total + total / 2, size_t(4) << 20);
+      void *fresh = nullptr;
+      if (ck_host_alloc(want, &fresh) != CK_OK) return std::string("Cannot allocate pinned host memory: ") + ck_last_error();
+      arena_ = static_cast<uint8_t *>(fresh);
+      arena_cap_ = want;
+    }
+    dst = arena_;
+  }
+  uint8_t *p = dst;
+  for (int i = 0; i < 3; ++i) {
+    const Column &c = col[i];
+    const Cut cut = CutAt(c, end_row);
+    ck_encoded_column &out = cols[i];
+    out.bytes = p;
+    out.num_bytes = cut.bytes;
+    if (cut.bytes) memcpy(p, c.bytes, cut.bytes);
+    memset(p + cut.bytes, 0, Align64(cut.bytes + 16) - cut.bytes);
+    p += Align64(cut.bytes + 16);
+    ck_run *runs = reinterpret_cast<ck_run *>(p);
+    if (cut.runs) memcpy(runs, c.runs, cut.runs * sizeof(ck_run));
+    runs[cut.runs] = ck_run{cut.values, 0, 0, 0};  // sentinel
+    out.runs = runs;
+    out.num_runs = uint32_t(cut.runs);
+    p += Align64((cut.runs + 1) * sizeof(ck_run));
+    out.dict = c.dict_len ? p : nullptr;
+    out.dict_len = c.dict_len;
+    if (c.dict_len) memcpy(p, c.dict, size_t(c.dict_len) * c.value_width);
+    p += Align64(size_t(c.dict_len) * c.value_width);
+    out.value_width = c.value_width;
+    out.skip = uint32_t(first_row - c.first_row);
+  }
+  num_rows = uint32_t(end_row - first_row);
+  return "";
 }
 
 void EncodedWindow::Column::Reset(uint32_t width) {
@@ -338,8 +406,10 @@ std::string AppendPage(EncodedWindow::Column *c, const parquet::Page &page, bool
 
 }  // namespace
 
-std::string ReadEncoded(const std::string &path, size_t window_rows, EncodedWindow *win,
-                        const std::function<std::string(size_t)> &consume, size_t *rows_out, bool *unsupported) {
+std::string ReadEncoded(const std::string &path, size_t window_rows, size_t slice_bytes, EncodedWindow *win,
+                        const std::function<uint8_t *()> &acquire,
+                        const std::function<std::string(size_t first_row, uint8_t *slice)> &consume, size_t *rows_out,
+                        bool *unsupported) {
   size_t delivered = 0;
   *unsupported = false;
   try {
@@ -372,37 +442,55 @@ std::string ReadEncoded(const std::string &path, size_t window_rows, EncodedWind
       const uint64_t rg_rows = uint64_t(md->RowGroup(rg)->num_rows());
       uint64_t done = 0;
       while (done < rg_rows) {
-        const uint64_t end = std::min<uint64_t>(done + window_rows, rg_rows);
-        for (int c = 0; c < kNumColumns; ++c) {
-          EncodedWindow::Column &col = win->col[c];
-          while (col.first_row + col.num_values < end) {
-            std::shared_ptr<parquet::Page> page = pages[c]->NextPage();
-            if (!page) return "Column lengths differ from the row count in " + path;
-            if (page->type() == parquet::PageType::DICTIONARY_PAGE) {
-              const auto &dp = static_cast<const parquet::DictionaryPage &>(*page);
-              if (dp.encoding() != parquet::Encoding::PLAIN && dp.encoding() != parquet::Encoding::PLAIN_DICTIONARY) {
-                *unsupported = true;
-                return "";
-              }
-              const size_t bytes = size_t(dp.num_values()) * col.value_width;
-              if (size_t(dp.size()) < bytes) return "Error reading " + path + ": truncated dictionary page";
-              if (std::string e = col.GrowDict(bytes); !e.empty()) return e;
-              memcpy(col.dict, dp.data(), bytes);
-              col.dict_len = uint32_t(dp.num_values());
-            } else if (page->type() == parquet::PageType::DATA_PAGE || page->type() == parquet::PageType::DATA_PAGE_V2) {
-              if (std::string e = AppendPage(&col, *page, optional[c], path, &scratch, unsupported); !e.empty() || *unsupported) return e;
-            }  // index pages carry no values
+        constexpr uint64_t kMinWindowRows = 4096;
+        uint64_t rows = std::min<uint64_t>(window_rows, rg_rows - done), end = 0;
+        for (;;) {
+          end = done + rows;
+          for (int c = 0; c < kNumColumns; ++c) {
+            EncodedWindow::Column &col = win->col[c];
+            while (col.first_row + col.num_values < end) {
+              const auto t0 = std::chrono::steady_clock::now();
+              std::shared_ptr<parquet::Page> page = pages[c]->NextPage();  // file read + page codec
+              const auto t1 = std::chrono::steady_clock::now();
+              win->s_pages += std::chrono::duration<double>(t1 - t0).count();
+              struct ScanTimer {
+                EncodedWindow *w;
+                std::chrono::steady_clock::time_point from;
+                ~ScanTimer() { w->s_scan += std::chrono::duration<double>(std::chrono::steady_clock::now() - from).count(); }
+              } scan_timer{win, t1};
+              if (!page) return "Column lengths differ from the row count in " + path;
+              if (page->type() == parquet::PageType::DICTIONARY_PAGE) {
+                const auto &dp = static_cast<const parquet::DictionaryPage &>(*page);
+                if (dp.encoding() != parquet::Encoding::PLAIN && dp.encoding() != parquet::Encoding::PLAIN_DICTIONARY) {
+                  *unsupported = true;
+                  return "";
+                }
+                const size_t bytes = size_t(dp.num_values()) * col.value_width;
+                if (size_t(dp.size()) < bytes) return "Error reading " + path + ": truncated dictionary page";
+                if (std::string e = col.GrowDict(bytes); !e.empty()) return e;
+                memcpy(col.dict, dp.data(), bytes);
+                col.dict_len = uint32_t(dp.num_values());
+              } else if (page->type() == parquet::PageType::DATA_PAGE || page->type() == parquet::PageType::DATA_PAGE_V2) {
+                if (std::string e = AppendPage(&col, *page, optional[c], path, &scratch, unsupported); !e.empty() || *unsupported) return e;
+              }  // index pages carry no values
+            }
           }
+          if (!acquire || win->StagedBytes(end) <= slice_bytes || rows <= kMinWindowRows) break;
+          rows = std::max<uint64_t>(kMinWindowRows, rows / 2);  // the pages gathered beyond the new end wait for the next window
         }
-        win->num_rows = uint32_t(end - done);
-        for (int c = 0; c < kNumColumns; ++c) {
-          EncodedWindow::Column &col = win->col[c];
-          if (std::string e = col.GrowRuns(col.runs_size + 1); !e.empty()) return e;
-          col.runs[col.runs_size] = ck_run{col.num_values, 0, 0, 0};  // sentinel
-          win->cols[c] = ck_encoded_column{col.bytes, col.bytes_size, col.runs, uint32_t(col.runs_size), col.dict, col.dict_len,
-                                           col.value_width, uint32_t(done - col.first_row)};
+        uint8_t *slice = nullptr;
+        if (acquire && win->StagedBytes(end) <= slice_bytes) {
+          const auto t0 = std::chrono::steady_clock::now();
+          slice = acquire();
+          win->s_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+          if (!slice) return "Aborted";
         }
-        if (std::string e = consume(delivered); !e.empty()) return e;
+        {
+          const auto t0 = std::chrono::steady_clock::now();
+          if (std::string e = win->Stage(done, end, slice); !e.empty()) return e;
+          win->s_stage += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        }
+        if (std::string e = consume(delivered, slice); !e.empty()) return e;
         delivered += size_t(end - done);
         done = end;
         for (int c = 0; c < kNumColumns; ++c) win->col[c].DropBefore(done);

@@ -58,9 +58,11 @@ std::string ReadTriples(const std::string &path, size_t chunk_rows, Triples *buf
                         const std::function<std::string(size_t)> &consume, size_t *rows_out);
 
 // ---- pages for the device decoder (ck_pack_encoded) -----------------------------------------------------------------
-// One window of rows of the three columns as page payloads + run tables + dictionaries, in page-locked memory that grows
-// geometrically and is reused by the owning reader thread.  The host only runs the page codec (parquet::PageReader) and
-// walks the run headers (ck_rle_scan); bit unpacking, dictionary lookup and the narrowing happen in the pack kernel.
+// One window of rows of the three columns as page payloads + run tables + dictionaries.  The host only runs the page codec
+// (parquet::PageReader) and walks the run headers (ck_rle_scan); bit unpacking, dictionary lookup and the narrowing happen
+// in the pack kernel.  Pages are gathered in pageable buffers; a finished window is laid out as ONE block
+// [payload | runs + sentinel | dictionary] x 3 in page-locked memory - a slice the caller lends (so that the window can be
+// queued for the GPU while the reader goes on), else the window's own arena - which ck_pack_encoded uploads with one copy.
 class EncodedWindow {
  public:
   EncodedWindow() = default;
@@ -91,15 +93,31 @@ class EncodedWindow {
     void DropBefore(uint64_t row);  // forgets the pages that end at or before `row` (a straddling page stays)
   };
   Column col[3];
+  // Bytes the block of the window that ends at row `end_row` takes (the pages gathered beyond it are left out).
+  size_t StagedBytes(uint64_t end_row) const;
+  // Lays that block out at `dst` (NULL: in the window's own page-locked arena, grown as needed) and points cols[] at it.
+  std::string Stage(uint64_t first_row, uint64_t end_row, uint8_t *dst);
+  // where this reader's time went, in seconds (CUKING_INGEST_STATS=1 prints the sums over the threads)
+  double s_pages = 0, s_scan = 0, s_stage = 0, s_wait = 0;
+
+ private:
+  uint8_t *arena_ = nullptr;
+  size_t arena_cap_ = 0;
 };
 
-// Streams one file through `win` in windows of at most `window_rows` rows: after each window `consume(first_row)` is called
-// with win->cols / win->num_rows describing it.  Same checks and error messages as ReadTriples.  *unsupported is set (and
-// "" returned, nothing more delivered) when the file uses something the device decoder does not take - an encoding other
-// than PLAIN / dictionary, legacy BIT_PACKED levels, a page of more than 2^31 bytes: the caller then reads the file with
-// ReadTriples instead (packing a triple twice is harmless, the pack is an AND).
-std::string ReadEncoded(const std::string &path, size_t window_rows, EncodedWindow *win,
-                        const std::function<std::string(size_t)> &consume, size_t *rows_out, bool *unsupported);
+// Streams one file through `win` in windows of at most `window_rows` rows: after each window `consume(first_row, slice)` is
+// called with win->cols / win->num_rows describing it.  `acquire` (may be empty) lends a page-locked slice of `slice_bytes`
+// bytes per window - it may block, and NULL aborts the read with "Aborted"; the slice is the consumer's from `consume` on,
+// so the window can be queued.  A window that would not fit a slice is halved (down to a few thousand rows); if it still
+// does not fit, or without `acquire`, it is staged in the window's own arena and `consume` gets slice == NULL: that memory
+// is reused by the next window, so the consumer must be done with it when it returns.  Same checks and error messages as
+// ReadTriples.  *unsupported is set (and "" returned, nothing more delivered) when the file uses something the device
+// decoder does not take - an encoding other than PLAIN / dictionary, legacy BIT_PACKED levels, a page of more than 2^31
+// bytes: the caller then reads the file with ReadTriples instead (packing a triple twice is harmless, the pack is an AND).
+std::string ReadEncoded(const std::string &path, size_t window_rows, size_t slice_bytes, EncodedWindow *win,
+                        const std::function<uint8_t *()> &acquire,
+                        const std::function<std::string(size_t first_row, uint8_t *slice)> &consume, size_t *rows_out,
+                        bool *unsupported);
 
 // Writer of <dir>/part-<%05d shard>.snappy.parquet with the reference schema (all REQUIRED): i, j BYTE_ARRAY/String,
 // kin FLOAT, ibs0, ibs1, ibs2 INT32; Snappy (cuking.cu:770-798, :868-870).  Records are appended in sorted order chunk by

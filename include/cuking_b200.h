@@ -228,7 +228,11 @@ int ck_rle_scan(const uint8_t *data, size_t num_bytes, uint32_t bit_width, uint3
  * cols[2] = n_alt_alleles - and packs them exactly like ck_pack_triples (same filter, truncations and errors; the
  * "triple" index of an error message is the row inside the window).  A table that is inconsistent with its buffers
  * (run outside the payload bytes, dictionary index >= dict_len, unsorted runs) fails with CK_ERR_INVALID_ARGUMENT
- * before or instead of touching the planes' neighbours.  Synchronous like ck_pack_triples. */
+ * before or instead of touching the planes' neighbours.  Synchronous like ck_pack_triples.  Unlike the other calls of a
+ * ctx this one may be issued by several host threads at once on the same planes (the decode threads of a host): every call
+ * runs on its own stream, staging buffer and error slots of the ctx, so the windows overlap on the GPU - the pack is a pure
+ * AND-accumulation - instead of queueing behind a host lock.  Pieces that lie close together in host memory (a window laid
+ * out in one arena) are uploaded with a single copy. */
 int ck_pack_encoded(ck_planes *planes, const ck_encoded_column cols[3], uint32_t num_rows);
 
 /* Page-locked host memory for triple buffers.  ck_pack_triples recognises it (and any other cudaHostAlloc /

@@ -140,11 +140,15 @@ def test_host_reader_windows_equal_libparquet_decode(tmp_path):
     g = random_genotypes(rng, 60, 500)
     files = write_variants(tmp_path, g)
     rows = int((g >= 0).sum())
-    for window in (1 << 21, 4099, 257):  # whole row groups; windows that straddle pages; windows smaller than a page
-        out = subprocess.run([CHECK, str(window), *files.values()], capture_output=True, text=True, check=True).stdout.splitlines()
+    # whole row groups; windows that straddle pages; windows smaller than a page; windows staged in lent slices - large
+    # ones, and ones so small that the reader has to halve its windows (and, below a few thousand rows, use its own arena)
+    for window in ("2097152", "4099", "257", "2097152:4194304", "20000:30000", "4099:9000"):
+        out = subprocess.run([CHECK, window, *files.values()], capture_output=True, text=True, check=True).stdout.splitlines()
         assert len(out) == len(files)
         for line in out:
-            assert line.startswith(f"OK {rows} rows"), line
+            assert line.startswith(f"OK {rows} rows"), (window, line)
+        if window == "2097152:4194304":
+            assert all("(0 in slices)" not in line for line in out), out
     # nulls are refused with the host path's message (cuking.cu:617-623); an encoding the kernel does not take is reported
     t = triple_table(g).to_pydict()
     t["col_idx"][17] = None

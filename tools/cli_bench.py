@@ -49,7 +49,7 @@ with tempfile.TemporaryDirectory() as tmp:
     with ck.Context(0) as ctx, ctx.planes(ck.submatrix(args.samples), args.sites) as pl:
         pl.synthesize(42, 0.01)
         want = len(pl.king(args.threshold, 10 << 20))
-    runs = [(int(x), m, r) for x in args.num_gpus.split(",") for m in args.modes.split(",") for r in range(args.repeat)]
+    runs = [(int(x), m, r) for x in args.num_gpus.split(",") for r in range(args.repeat) for m in args.modes.split(",")]  # modes interleaved
     for gpus, mode, rep in runs:
         out = f"{tmp}/out{gpus}{mode}{rep}"
         cmd = [os.path.join(ROOT, "bin", "cuking"), f"--input_uri={tmp}/in", f"--output_uri={out}",
@@ -58,6 +58,7 @@ with tempfile.TemporaryDirectory() as tmp:
             cmd += [f"--split_factor={args.split_factor}", "--all_shards", "--write_success_file"]
         t0 = time.perf_counter()
         env = dict(os.environ)
+        env["CUKING_INGEST_STATS"] = "1"
         if mode in ("narrow", "wide"):
             env["CUKING_HOST_DECODE"] = "1"
         if mode == "wide":
@@ -83,4 +84,5 @@ with tempfile.TemporaryDirectory() as tmp:
                           "phases": phases, "kernels": [{"what": k[0], "wall": k[1], "kernel_ms": float(k[2]), "gpu": int(k[3])} for k in kernels],
                           "triples_per_s_end_to_end": info["num_triples"] / wall,
                           "triples_per_s_decode_and_pack": (info["num_triples"] / decode_s) if decode_s else None,
-                          "retained_pairs": rows}), flush=True)
+                          "retained_pairs": rows,
+                          "ingest_stats": (re.search(r"^Ingest thread-seconds.*$", p.stdout, re.M) or [None])[0]}), flush=True)

@@ -1,11 +1,13 @@
 // Test tool (no GPU): checks the host half of the device page decoder.  For every file given, the rows that
 // cuking::ReadEncoded describes window by window (page payloads + run tables + dictionaries, interpreted here by a plain
 // loop that shares no code with the kernel) must equal the rows cuking::ReadTriples decodes through libparquet.
-//   encoded_check <window_rows> <file>...      prints "OK <rows> rows, <windows> windows, <runs> runs" per file
+//   encoded_check <window_rows>[:<slice_bytes>] <file>...      prints "OK <rows> rows, <windows> windows, ..." per file
+// With <slice_bytes> the windows are staged in a lent slice of that size (windows that do not fit are halved by the reader).
 // ck_host_alloc / ck_host_free are replaced by malloc / free below so that the tool runs without a CUDA device.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -48,7 +50,12 @@ static bool Value(const ck_encoded_column &c, uint32_t v, int64_t *out, uint32_t
 
 int main(int argc, char **argv) {
   if (argc < 3) return 2;
-  const size_t window_rows = strtoull(argv[1], nullptr, 10);
+  char *colon = nullptr;
+  const size_t window_rows = strtoull(argv[1], &colon, 10);
+  const size_t slice_bytes = (colon && *colon == ':') ? strtoull(colon + 1, nullptr, 10) : 0;
+  std::vector<uint8_t> slice_mem(slice_bytes + 64);
+  uint8_t *slice_base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(slice_mem.data()) + 63) & ~uintptr_t(63));
+  size_t in_slices = 0;
   for (int a = 2; a < argc; ++a) {
     const std::string path = argv[a];
     std::vector<int64_t> row, col, alt;
@@ -65,7 +72,15 @@ int main(int argc, char **argv) {
     size_t seen = 0, windows = 0, runs = 0, rows2 = 0, col_runs[3] = {0, 0, 0}, bytes = 0;
     bool unsupported = false;
     std::string bad;
-    std::string e2 = cuking::ReadEncoded(path, window_rows, &win, [&](size_t first) {
+    std::function<uint8_t *()> acquire;
+    if (slice_bytes) acquire = [&]() { return slice_base; };
+    std::string e2 = cuking::ReadEncoded(path, window_rows, slice_bytes, &win, acquire, [&](size_t first, uint8_t *slice) {
+      if (slice) {
+        ++in_slices;
+        if (win.cols[0].bytes != slice) bad = "window not staged in the lent slice";
+        const uint8_t *last = static_cast<const uint8_t *>(win.cols[2].dict ? win.cols[2].dict : static_cast<const void *>(win.cols[2].runs + win.cols[2].num_runs + 1));
+        if (last + size_t(win.cols[2].dict_len) * 4 > slice + slice_bytes) bad = "window overflows the slice";
+      }
       if (first != seen) bad = "window starts at " + std::to_string(first) + ", expected " + std::to_string(seen);
       ++windows;
       for (int c = 0; c < 3; ++c) {
@@ -90,8 +105,9 @@ int main(int argc, char **argv) {
     if (!e2.empty()) { printf("%s %s\n", e.empty() ? "ERROR" : (e == e2 ? "SAME_ERROR" : "OTHER_ERROR"), e2.c_str()); continue; }
     if (!e.empty()) { printf("ERROR host path failed where the encoded path did not\n"); continue; }
     if (rows2 != rows || seen != rows) { printf("ERROR rows %zu vs %zu\n", rows2, rows); continue; }
-    printf("OK %zu rows, %zu windows, %zu runs (%zu + %zu + %zu), %.2f bytes per row to the device\n", rows, windows, runs, col_runs[0],
-           col_runs[1], col_runs[2], double(bytes) / double(rows ? rows : 1));
+    printf("OK %zu rows, %zu windows (%zu in slices), %zu runs (%zu + %zu + %zu), %.2f bytes per row to the device\n", rows, windows, in_slices,
+           runs, col_runs[0], col_runs[1], col_runs[2], double(bytes) / double(rows ? rows : 1));
+    in_slices = 0;
   }
   return 0;
 }
