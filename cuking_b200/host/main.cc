@@ -283,7 +283,7 @@ Status Run(const Flags &flags) {
     constexpr size_t kSliceBytes = size_t(4) << 20;
     const bool queued = device_decode && (exchange || num_gpus == 1);  // every window goes to exactly one GPU
     const size_t num_submitters = queued ? 2 * num_gpus : 0;
-    const size_t num_slices = queued ? std::min<size_t>(32, std::max<size_t>(8, 4 * num_submitters)) : 0;
+    const size_t num_slices = queued ? std::min<size_t>(48, std::max<size_t>(16, 6 * num_submitters)) : 0;
     struct Job {
       ck_encoded_column cols[3];
       uint32_t num_rows = 0;
