@@ -1,0 +1,106 @@
+#!/usr/bin/env python3
+"""Device-side rate of ck_pack_encoded: windows of dictionary-encoded triples in Hail's order, built here
+with a plain numpy writer (bit-packed runs of 63 groups for col_idx / n_alt_alleles, RLE runs for row_idx - what parquet-cpp
+and parquet-mr emit for such columns), decoded and packed by decode_pack_kernel.
+
+  python tools/decode_bench.py [--samples 100000] [--rows 1048576] [--windows 8] [--reps 5]
+
+Prints one JSON line: rows per second of the call as the library times it (upload of the window + kernel, CUDA events) and
+the bytes per row that crossed PCIe.  For an ncu capture of the kernel alone run it with --reps 1 --windows 1 under ncu.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import cuking_b200 as ck  # noqa: E402
+from cuking_b200 import capi  # noqa: E402
+
+
+def varint(v: int) -> bytes:
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def bitpacked_stream(codes: np.ndarray, bw: int) -> bytes:
+    """Bit-packed runs of at most 63 groups of 8 values (the last group zero-padded), LSB first."""
+    n = len(codes)
+    pad = (-n) % 8
+    v = np.concatenate([codes.astype(np.uint64), np.zeros(pad, dtype=np.uint64)])
+    bits = ((v[:, None] >> np.arange(bw, dtype=np.uint64)) & np.uint64(1)).astype(np.uint8)
+    packed = np.packbits(bits.reshape(-1), bitorder="little").tobytes()
+    out = bytearray()
+    groups = len(v) // 8
+    for g0 in range(0, groups, 63):
+        g = min(63, groups - g0)
+        out += varint((g << 1) | 1)
+        out += packed[g0 * bw:(g0 + g) * bw]
+    return bytes(out)
+
+
+def rle_stream(codes: np.ndarray, bw: int) -> bytes:
+    """One RLE run per stretch of equal values."""
+    out = bytearray()
+    edges = np.flatnonzero(np.diff(codes)) + 1
+    starts = np.concatenate([[0], edges])
+    ends = np.concatenate([edges, [len(codes)]])
+    vb = (bw + 7) // 8
+    for a, b in zip(starts, ends):
+        out += varint(int(b - a) << 1)
+        out += int(codes[a]).to_bytes(vb, "little")
+    return bytes(out)
+
+
+def column(values: np.ndarray, width: int, rle: bool) -> dict:
+    uniq, codes = np.unique(values, return_inverse=True)
+    bw = max(1, int(len(uniq) - 1).bit_length())
+    data = rle_stream(codes, bw) if rle else bitpacked_stream(codes, bw)
+    runs = np.concatenate([ck.rle_scan(data, bw, len(values)), np.array([(len(values), 0, 0, 0)], dtype=capi.RUN_DTYPE)])
+    return {"bytes": np.frombuffer(data, dtype=np.uint8), "runs": runs, "dict": uniq.astype(np.int64 if width == 8 else np.int32),
+            "value_width": width, "skip": 0}
+
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--samples", type=int, default=100_000)
+ap.add_argument("--rows", type=int, default=1 << 20)
+ap.add_argument("--windows", type=int, default=8)
+ap.add_argument("--reps", type=int, default=5)
+args = ap.parse_args()
+
+rng = np.random.default_rng(42)
+sites = args.windows * (args.rows // args.samples + 2)
+windows = []
+bytes_per_row = 0.0
+row0 = 0
+for w in range(args.windows):  # site-major, sample-minor rows (Hail order), 1 % of the genotypes missing
+    idx = np.arange(row0, row0 + int(args.rows * 1.0101))
+    idx = idx[rng.random(len(idx)) >= 0.01][: args.rows]
+    row0 = int(idx[-1]) + 1
+    site, sample = idx // args.samples, idx % args.samples
+    alt = rng.choice(np.array([0, 1, 2]), size=len(idx), p=[0.55, 0.35, 0.10])
+    cols = [column(site, 8, True), column(sample, 8, False), column(alt, 4, False)]
+    bytes_per_row += sum(c["bytes"].nbytes + c["runs"].nbytes + c["dict"].nbytes for c in cols) / len(idx) / args.windows
+    windows.append((cols, len(idx)))
+
+with ck.Context(0) as ctx, ctx.planes(ck.submatrix(args.samples), sites + 1) as pl:
+    best = None
+    for rep in range(args.reps):
+        total_ms = 0.0
+        for cols, n in windows:
+            pl.pack_encoded(cols, n)
+            total_ms += ctx.timings()["pack_ms"]
+        best = total_ms if best is None else min(best, total_ms)
+    rows = sum(n for _, n in windows)
+    print(json.dumps({"tool": "decode_bench", "kernel": "decode_pack_kernel", "samples": args.samples, "rows_per_window": args.rows,
+                      "windows": args.windows, "ms_per_window": best / args.windows, "rows_per_s": rows / (best * 1e-3),
+                      "bytes_per_row_over_pcie": bytes_per_row, "upload_gbs": rows * bytes_per_row / (best * 1e-3) / 1e9,
+                      "timed": "cudaEvents around [upload of the window (pageable numpy arrays here) + decode_pack_kernel], best of %d" % args.reps}))
