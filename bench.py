@@ -302,6 +302,38 @@ def run_pack_bench(ctx, n_samples: int, missing: float, hbm_peak_gbs):
             "sample": f"{n_samples} samples x {sites} sites of the workload cohort, Hail order"}
 
 
+def run_pack_encoded_bench(ctx, n_samples: int, missing: float):
+    """Times ck_pack_encoded (Parquet pages decoded on the device) on two 2^20-row windows of the workload's
+    shape in Hail's order: RLE-coded row_idx, bit-packed col_idx and n_alt_alleles, sorted dictionaries; the windows are built
+    here with numpy (cuking_b200/io.py) and handed over as pageable host arrays, so the timed call = upload + decode_pack_kernel."""
+    import cuking_b200 as ck
+    from cuking_b200.io import encoded_column
+
+    rows, rng = 1 << 20, np.random.default_rng(SEED)
+    windows, row0, bytes_per_row = [], 0, 0.0
+    for _ in range(2):
+        idx = np.arange(row0, row0 + int(rows * (1.0 + 2.0 * missing)))
+        idx = idx[rng.random(len(idx)) >= missing][:rows]
+        row0 = int(idx[-1]) + 1
+        alt = rng.choice(np.array([0, 1, 2]), size=len(idx), p=[0.55, 0.35, 0.10])
+        cols = [encoded_column(idx // n_samples, 8, True), encoded_column(idx % n_samples, 8, False), encoded_column(alt, 4, False)]
+        bytes_per_row += sum(c["bytes"].nbytes + c["runs"].nbytes + c["dict"].nbytes for c in cols) / len(idx) / 2
+        windows.append((cols, len(idx)))
+    sites = row0 // n_samples + 1
+    best = None
+    with ctx.planes(ck.submatrix(n_samples), sites) as pl:
+        for _ in range(4):
+            ms = 0.0
+            for cols, n in windows:
+                pl.pack_encoded(cols, n)
+                ms += ctx.timings()["pack_ms"]
+            best = ms if best is None else min(best, ms)
+    total = sum(n for _, n in windows)
+    return {"kernel": "decode_pack_kernel", "triples": int(total), "ms": best, "triples_per_s": total / (best * 1e-3),
+            "bytes_per_triple_over_pcie": bytes_per_row, "bound": "host upload + latency (the kernel alone: profiles/r02_decode_launches.csv)",
+            "sample": f"2 windows of 2^20 rows, {n_samples} samples, Hail order, dictionary-encoded (RLE row_idx, bit-packed col_idx / n_alt_alleles)"}
+
+
 # ---- our arm ------------------------------------------------------------------------------------------------------
 
 
@@ -719,7 +751,7 @@ def main():
             "checks": w["checks"], "clocks": w["clocks"], "input_synthesis_s": w["input_synthesis_s"],
         }
 
-    cpu_baseline, ref_gpu, pack = None, None, None
+    cpu_baseline, ref_gpu, pack, pack_encoded = None, None, None, None
     if rank == 0 and b.n_gpus == 1:
         _, n_sites, missing, thr, _ = WORKLOADS[name]
         hbm_peak = b.measured.get("hbm_gbs") if b.measured else None
@@ -727,6 +759,10 @@ def main():
             pack = run_pack_bench(b.ctx, head["n_samples"], missing, hbm_peak)
         except Exception as exc:
             pack = {"error": repr(exc)}
+        try:
+            pack_encoded = run_pack_encoded_bench(b.ctx, head["n_samples"], missing)
+        except Exception as exc:  # a side measurement must never take the bench down
+            pack_encoded = {"error": repr(exc)}
         if not args.skip_ref_gpu:
             try:
                 ref_gpu = run_reference_gpu_kernel(b.ctx, n_sites, missing, thr)
@@ -749,7 +785,7 @@ def main():
                     "warmup_note": head["warmup_note"]},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
             "clocks": head["clocks"], "checks": head["checks"], "fixed_configs": fixed_configs or None,
-            "reference_gpu_kernel": ref_gpu, "pack": pack, "plane_exchange": head["exchange"],
+            "reference_gpu_kernel": ref_gpu, "pack": pack, "pack_encoded": pack_encoded, "plane_exchange": head["exchange"],
         }
         print(json.dumps(line), flush=True)
     b.ctx.close()

@@ -198,8 +198,17 @@ Status Run(const Flags &flags) {
       for (Gpu &g : *v) ck_ctx_destroy(g.ctx);
     }
   } closer{&gpus};
-  for (uint32_t g = 0; g < num_gpus; ++g)
-    if (int rc = ck_ctx_create(flags.device + int(g), &gpus[g].ctx); rc != CK_OK) return FromCk(rc);
+  {  // one thread per GPU: creating a CUDA context takes about half a second, and eight in a row would be the longest phase
+    std::vector<Status> created(num_gpus);
+    std::vector<std::thread> init;
+    for (uint32_t g = 0; g < num_gpus; ++g)
+      init.emplace_back([&, g] {
+        if (int rc = ck_ctx_create(flags.device + int(g), &gpus[g].ctx); rc != CK_OK) created[g] = FromCk(rc);  // ck_last_error is per thread
+      });
+    for (auto &th : init) th.join();
+    for (const Status &st : created)
+      if (!st.ok()) return st;
+  }
   std::cout << " " << num_gpus << " GPU(s) (" << stop_watch.ElapsedAndReset() << ")" << std::endl;
 
   // ---- shard planning (cuking.cu:505) and plane allocation (:513-523) ----

@@ -76,3 +76,55 @@ def read_output_dir(path: str, allow_row_groups: bool = False) -> pa.Table:
                     raise ValueError(f"{name}: column {c} is not Snappy-compressed (cuking.cu:797-798)")
         tables.append(pf.read())
     return pa.concat_tables(tables)
+
+
+# ---- encoded columns for ck_pack_encoded (synthetic inputs of bench.py / tools/decode_bench.py) ---------------------
+def _varint(v: int) -> bytes:
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def bitpacked_stream(codes: np.ndarray, bit_width: int) -> bytes:
+    """Parquet RLE / bit-packed hybrid stream made of bit-packed runs only: at most 63 groups of 8 values per run, LSB
+    first, the last group zero-padded (what parquet-cpp / parquet-mr write for columns without long repeats)."""
+    n = len(codes)
+    v = np.concatenate([codes.astype(np.uint64), np.zeros((-n) % 8, dtype=np.uint64)])
+    bits = ((v[:, None] >> np.arange(bit_width, dtype=np.uint64)) & np.uint64(1)).astype(np.uint8)
+    packed = np.packbits(bits.reshape(-1), bitorder="little").tobytes()
+    out = bytearray()
+    groups = len(v) // 8
+    for g0 in range(0, groups, 63):
+        g = min(63, groups - g0)
+        out += _varint((g << 1) | 1)
+        out += packed[g0 * bit_width:(g0 + g) * bit_width]
+    return bytes(out)
+
+
+def rle_stream(codes: np.ndarray, bit_width: int) -> bytes:
+    """The same encoding with one RLE run per stretch of equal values (row_idx of a site-major table)."""
+    out = bytearray()
+    edges = np.flatnonzero(np.diff(codes)) + 1
+    starts = np.concatenate([[0], edges])
+    ends = np.concatenate([edges, [len(codes)]])
+    vb = (bit_width + 7) // 8
+    for a, b in zip(starts, ends):
+        out += _varint(int(b - a) << 1)
+        out += int(codes[a]).to_bytes(vb, "little")
+    return bytes(out)
+
+
+def encoded_column(values: np.ndarray, width: int, rle: bool) -> dict:
+    """One dictionary-encoded column of a window in the form Planes.pack_encoded takes (sorted dictionary, one stream)."""
+    from .capi import RUN_DTYPE
+    from .engine import rle_scan
+
+    uniq, codes = np.unique(values, return_inverse=True)
+    bw = max(1, int(len(uniq) - 1).bit_length())
+    data = rle_stream(codes, bw) if rle else bitpacked_stream(codes, bw)
+    runs = np.concatenate([rle_scan(data, bw, len(values)), np.array([(len(values), 0, 0, 0)], dtype=RUN_DTYPE)])
+    return {"bytes": np.frombuffer(data, dtype=np.uint8), "runs": runs, "dict": uniq.astype(np.int64 if width == 8 else np.int32),
+            "value_width": width, "skip": 0}

@@ -19,54 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import cuking_b200 as ck  # noqa: E402
-from cuking_b200 import capi  # noqa: E402
-
-
-def varint(v: int) -> bytes:
-    out = bytearray()
-    while v >= 0x80:
-        out.append((v & 0x7F) | 0x80)
-        v >>= 7
-    out.append(v)
-    return bytes(out)
-
-
-def bitpacked_stream(codes: np.ndarray, bw: int) -> bytes:
-    """Bit-packed runs of at most 63 groups of 8 values (the last group zero-padded), LSB first."""
-    n = len(codes)
-    pad = (-n) % 8
-    v = np.concatenate([codes.astype(np.uint64), np.zeros(pad, dtype=np.uint64)])
-    bits = ((v[:, None] >> np.arange(bw, dtype=np.uint64)) & np.uint64(1)).astype(np.uint8)
-    packed = np.packbits(bits.reshape(-1), bitorder="little").tobytes()
-    out = bytearray()
-    groups = len(v) // 8
-    for g0 in range(0, groups, 63):
-        g = min(63, groups - g0)
-        out += varint((g << 1) | 1)
-        out += packed[g0 * bw:(g0 + g) * bw]
-    return bytes(out)
-
-
-def rle_stream(codes: np.ndarray, bw: int) -> bytes:
-    """One RLE run per stretch of equal values."""
-    out = bytearray()
-    edges = np.flatnonzero(np.diff(codes)) + 1
-    starts = np.concatenate([[0], edges])
-    ends = np.concatenate([edges, [len(codes)]])
-    vb = (bw + 7) // 8
-    for a, b in zip(starts, ends):
-        out += varint(int(b - a) << 1)
-        out += int(codes[a]).to_bytes(vb, "little")
-    return bytes(out)
-
-
-def column(values: np.ndarray, width: int, rle: bool) -> dict:
-    uniq, codes = np.unique(values, return_inverse=True)
-    bw = max(1, int(len(uniq) - 1).bit_length())
-    data = rle_stream(codes, bw) if rle else bitpacked_stream(codes, bw)
-    runs = np.concatenate([ck.rle_scan(data, bw, len(values)), np.array([(len(values), 0, 0, 0)], dtype=capi.RUN_DTYPE)])
-    return {"bytes": np.frombuffer(data, dtype=np.uint8), "runs": runs, "dict": uniq.astype(np.int64 if width == 8 else np.int32),
-            "value_width": width, "skip": 0}
+from cuking_b200.io import encoded_column as column  # noqa: E402
 
 
 ap = argparse.ArgumentParser()
