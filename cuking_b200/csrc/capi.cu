@@ -148,7 +148,7 @@ namespace ck {
 // site count the probe verified (kFp4MaxSites) and only if this GPU passed the self-test; otherwise the int8 kernel.
 int planes_variant(const ck_planes *pl) {
   const int v = active_variant(pl->ctx);
-  if (v < 3) return v;  // 3 = mxf4 kernel, 4 = its CTA-pair form: both rest on the fp32 accumulation of kind::mxf4
+  if (v < 3) return v;  // 3 = mxf4 kernel, 4 = its CTA-pair form, 5 = screen + mxf4: all rest on the fp32 accumulation of kind::mxf4
   return (pl->num_sites > kFp4MaxSites || !fp4_usable(pl->ctx)) ? 2 : v;
 }
 }  // namespace ck
@@ -273,7 +273,7 @@ int ck_ctx_set_stream(ck_ctx *ctx, void *cuda_stream) {
 
 int ck_ctx_set_king_variant(ck_ctx *ctx, int variant) {
   if (!ctx) return fail(CK_ERR_INVALID_ARGUMENT, "ctx is NULL");
-  if (variant < -1 || variant > 4) return fail(CK_ERR_INVALID_ARGUMENT, "unknown pairwise kernel variant");
+  if (variant < -1 || variant > 5) return fail(CK_ERR_INVALID_ARGUMENT, "unknown pairwise kernel variant");
   ctx->king_variant = variant;
   return CK_OK;
 }
@@ -323,6 +323,7 @@ int ck_ctx_destroy(ck_ctx *ctx) {
   if (ctx->syn_alt) cudaFree(ctx->syn_alt);
   if (ctx->result_buf) cudaFree(ctx->result_buf);
   if (ctx->tile_table) cudaFree(ctx->tile_table);
+  if (ctx->tile_flags) cudaFree(ctx->tile_flags);
   if (ctx->sort_scratch) cudaFree(ctx->sort_scratch);
   for (int i = 0; i < ck_ctx::kCacheSlots; ++i)
     if (ctx->cache_ptr[i]) cudaFree(ctx->cache_ptr[i]);
@@ -408,7 +409,7 @@ int ensure_compute(ck_planes *pl) {
   const int kind = variant >= 3 ? 3 : variant;  // nibble encoding: 2 = int8 selectors, 3 = E2M1 (both mxf4 kernels)
   if (want_codes ? (!pl->codes_stale && pl->codes_kind == kind) : !pl->compute_stale) return CK_OK;
   if (want_codes && pl->codes == nullptr) {
-    pl->codes_bytes = std::max<size_t>(pl->codes_words(), 1) * 4;
+    pl->codes_bytes = std::max<size_t>(pl->codes_alloc_words(), 1) * 4;
     CK_CUDA(ctx_alloc(ctx, reinterpret_cast<void **>(&pl->codes), pl->codes_bytes));
   }
   if (!want_codes && pl->compute == nullptr) {

@@ -91,6 +91,8 @@ struct ck_ctx {
   // alive-tile table of the tcgen05 kernel (grow-only device scratch)
   void *tile_table = nullptr;
   size_t tile_table_bytes = 0;
+  uint8_t *tile_flags = nullptr;  // screen kernel: one byte per tile of a launch (grow-only)
+  size_t tile_flags_bytes = 0;
   uint64_t tile_table_key[3] = {~0ull, 0, 0};  // (variant, rows/cols, global origins) of the table now on the device
   // dense output: first output slot of every band (device copy + the host vector the async upload reads)
   unsigned long long *dense_table = nullptr;
@@ -176,6 +178,9 @@ struct ck_planes {
   size_t raw_words() const { return size_t(map.num_blocks) * words * ck::kRawPlanes * ck::kTileSamples; }
   size_t compute_words() const { return size_t(map.num_blocks) * words * ck::kComputePlanes * ck::kTileSamples; }
   size_t codes_words() const { return size_t(map.num_blocks) * words * ck::kTileSamples * 4; }
+  // the codes buffer is followed by one uint32 per plane slot: the sample's het count over all sites (screen kernel)
+  size_t codes_alloc_words() const { return codes_words() + size_t(map.num_blocks) * ck::kTileSamples; }
+  uint32_t *het_totals() const { return codes ? codes + codes_words() : nullptr; }
   void mark_stale() { compute_stale = codes_stale = true; }
 };
 
@@ -237,6 +242,11 @@ struct KingLaunch {
   // sort is needed; a pair at or below the threshold leaves a hole (sample_i = 0xffffffff) and bumps *holes.
   const unsigned long long *dense_band_base;
   unsigned long long *holes;
+  // Screen kernel (king_screen_kernel.cu, variant 5): het count of every plane slot over all sites, and one byte per tile
+  // of the launch - written by the screen kernel (1 = the tile holds a pair that may pass the threshold), read by the mxf4
+  // kernel launched behind it over the same tile range, whose CTAs leave at once where the byte is 0.
+  const uint32_t *het_total;
+  uint8_t *tile_flags;
 };
 // Where the records of one evaluation go (king_api.cu).  Sparse: appended through the atomic counter, sorted afterwards.
 // Dense: every pair has its slot in the sorted output; `regions` lists the output ranges in launch order with the event
@@ -304,6 +314,8 @@ uint64_t king_fp4_pair_num_tiles(const KingLaunch &k);
 constexpr uint32_t kPairTileCols = 64;  // 256 x 64 pair tiles
 // band table of this launch geometry for the mxf4 kernel's tile shape (band_prepare)
 cudaError_t king_fp4_prepare(const KingLaunch &k, ck_ctx *ctx, cudaStream_t s, std::vector<uint64_t> *band_prefix);
+// king_screen_kernel.cu (variant 5): three-product screen of every tile + the mxf4 kernel on the tiles it flags
+cudaError_t launch_king_screen(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches);
 constexpr uint32_t kFp4BandRows = kBandRowTiles * kBandTileRows;
 constexpr uint32_t kFp4MaxSites = 1u << 23;  // exactness of the tensor core's fp32 accumulation was measured up to this count
 

@@ -102,12 +102,15 @@ uint32_t variant_tile_cols(int variant) { return variant == 4 ? kPairTileCols : 
 
 uint64_t variant_num_tiles(int variant, const KingLaunch &k) {
   if (variant == 4) return king_fp4_pair_num_tiles(k);
-  if (variant == 3) return king_fp4_num_tiles(k);
+  if (variant == 3 || variant == 5) return king_fp4_num_tiles(k);
   if (variant == 2) return king_umma_num_tiles(k);
   return king_num_tiles(k.num_row_blocks, k.num_col_blocks, k.triangular != 0);
 }
 
 cudaError_t dispatch_king(int variant, const ck_planes *pl, const KingLaunch &k, cudaStream_t s, uint32_t *launches) {
+  // the screen needs nothing but sparse records out of the tile: dense output and the count dump take the mxf4 kernel
+  if (variant == 5) return (k.dense_band_base || k.dump_counts || !k.het_total) ? launch_king_fp4(k, pl->map.num_blocks, pl->ctx, s, launches)
+                                                                              : launch_king_screen(k, pl->map.num_blocks, pl->ctx, s, launches);
   if (variant == 4) return launch_king_fp4_pair(k, pl->map.num_blocks, pl->ctx, s, launches);
   if (variant == 3) return launch_king_fp4(k, pl->map.num_blocks, pl->ctx, s, launches);
   if (variant == 2) return launch_king_umma(k, pl->map.num_blocks, pl->ctx, s, launches);
@@ -122,6 +125,7 @@ int view_launch(const ck_planes *pl, const ck_submatrix *view, int variant, King
   KingLaunch k{};
   k.compute = pl->compute;
   k.codes = pl->codes;
+  k.het_total = pl->het_totals();
   k.words = pl->words;
   if (view == nullptr) {
     k.row_slot0 = 0;
@@ -527,7 +531,7 @@ int stream_begin_impl(ck_planes *pl, float kin_threshold, uint32_t max_results, 
   if (variant < 2) return fail(CK_ERR_INVALID_ARGUMENT, "streaming delivery needs a tensor-core kernel variant (2 or 3): their band-ordered tiles");
   if (pl->stream_state) return fail(CK_ERR_INVALID_ARGUMENT, "a stream session is already open on these planes");
   if (pl->codes == nullptr) {
-    pl->codes_bytes = std::max<size_t>(pl->codes_words(), 1) * 4;
+    pl->codes_bytes = std::max<size_t>(pl->codes_alloc_words(), 1) * 4;
     CK_CUDA(ctx_alloc(ctx, reinterpret_cast<void **>(&pl->codes), pl->codes_bytes));
   }
   KingStream *st = new (std::nothrow) KingStream();
@@ -574,6 +578,7 @@ int stream_rows_device(ck_planes *pl, const uint64_t *d_rows, uint32_t s0, uint3
   ctx->timings.king_launches += 2;
   const uint32_t band_lo = s0 / kFp4BandRows, band_hi = ceil_div(std::min(s1, n), kFp4BandRows);
   st->k.codes = pl->codes;
+  st->k.het_total = pl->het_totals();
   int rc = launch_bands(pl, st->k, st->variant, st->band_prefix, band_lo, band_hi, st->part_index, st->num_parts, 0xffffffffu, false, &st->plan);
   if (rc != CK_OK) return rc;
   st->next_end = s0;

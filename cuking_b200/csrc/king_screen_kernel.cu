@@ -1,34 +1,22 @@
-// Pairwise KING on the 5th-generation tensor cores at the FP4 rate: tcgen05.mma.kind::mxf4.block_scale over E2M1
-// indicator vectors with all block scales = 2^0 and fp32 accumulation (sm_100a only).  Variant 3, the default.
+// Three-product screen in front of the mxf4 pairwise kernel (variant 5; sm_100a only).
 //
-// Same algebra as king_umma_kernel.cu (the six counters of ComputeKingKernel, /root/reference/cuking.cu:214-240, as
-// five bilinear forms of per-sample indicator vectors):
-//     x = [hom-alt] - [hom-ref]   y = [hom]   h = [het] / 2          (all 0 where the genotype is missing)
-//     D_xx = x_i.x_j = conc - opp            D_y = y_i.[y_j ; h_j] = (conc + opp | (i hom, j het) / 2)
-//     D_h = h_i.[y_j ; h_j] = ((i het, j hom) / 2 | both_het / 4)
-// kind::mxf4 multiplies 64 sites per instruction — twice kind::i8 — and the operands are 4 bits wide, so operand
-// expansion, TMEM stores and shared-memory traffic per site all halve as well.  Exactness: every operand is 0, 0.5 or
-// +-1 in E2M1, every product a multiple of 1/4, every partial sum a multiple of 1/4 below 2^24 / 4: exactly representable
-// in the fp32 accumulator.  tools/umma_mxf4_probe.cu measured the tensor core's accumulation to be exact for counts up
-// to 2^23 on this pool's B200s (profiles/r01_mxf4_probe.txt); capi.cu routes cohorts with more than 2^23 sites to the
-// int8 kernel (exact to 2^31) instead.
-//
-// Operands are expanded on the fly from 4-bit genotype codes (layout.cuh) chosen so that the expansion is ONE logic
-// instruction per operand per 8 genotypes: code = 1 het, 2 hom-alt, 0xA hom-ref, 0 missing, i.e. E2M1(0.5), E2M1(+1),
-// E2M1(-1), 0, and   x = z & 0xAAAAAAAA   y = z & 0x22222222   h = z & 0x11111111.
-//   * warps 0-7   A operands: one thread per row sample; the two groups of four warps take alternate A stages (two 64-site
-//                 steps each) and write straight into a 4-slot TMEM ring with tcgen05.st (thread = TMEM lane = row);
-//                 a slot is announced as soon as it is stored, a stage is released by one commit per issuer;
-//   * warps 8-12  B operands: two threads per column sample (32 sites each per step) write K-major no-swizzle canonical
-//                 shared-memory tiles, several steps per stage so the proxy fence and barrier round trip are amortised;
-//   * one lane of each of warps 13-15 issues one of the three MMAs per step (A from TMEM, B from shared memory) and
-//                 releases the A slot / B stage with tcgen05.commit;
-//   * epilogue    all 16 warps read the fp32 accumulators with tcgen05.ld, convert to the exact integer counts, compute
-//                 kinship in the reference's fp32 order and append through the warp-aggregated atomic.
-// TMEM: 400 accumulator columns + 4 x 24 A columns + 16 scale-factor columns (all 0x7F = 2^0; every byte is the same,
-// so the scale-factor layout is immaterial) = 512.
-// Tiles are enumerated in bands of 8 row tiles (band_tiles.cu), column-major inside a band, so that the ~148 tiles in flight share
-// 8 row blocks and ~19 column blocks and the genotype codes are served from L2.
+// A pair passes the threshold only if   kin = 0.5 - D / (4 min(het_i, het_j)) > thr   (cuking.cu:289-297), where
+//     D = sum over the sites both samples are called at of (g_i - g_j)^2 = het_i + het_j - 2 both_het + 4 opp
+// is the squared genotype distance.  With the E2M1 indicator vectors of king_fp4_kernel.cu (x = +-1 hom-alt / hom-ref,
+// y = 1 hom, h = 0.5 het) and w = y + h (one LOP3: z & 0x33333333),
+//     D = 2 (y_i.w_j + h_i.y_j - x_i.x_j)
+// THREE exact products of N = 80 instead of the five (N = 80 + 160 + 160) the counters need: 127 instead of 212 tensor
+// clocks per 64 sites, 240 instead of 400 accumulator columns - so the A ring in TMEM is 8 slots deep instead of 4 and the
+// refill latency that holds the five-product kernel at 88 % tensor activity is off the critical path.  min(het_i, het_j)
+// over the jointly called sites is at most the minimum of the two samples' het counts over ALL sites (het_totals_kernel),
+// so   D < 4 (0.5 - thr) min(Het_i, Het_j)   is a necessary condition, exact in fp32 up to a margin.  For unrelated
+// pairs kin is near 0 and the bound is off by about missing_rate / 2: at the thresholds cuKING is run with the screen
+// rejects everything but the related pairs and their immediate neighbourhood.
+// The kernel computes nothing else: a tile that holds at least one candidate pair sets its byte in p.tile_flags, and
+// launch_king_screen runs king_fp4_kernel over the same tile range behind it - its CTAs leave at once where the byte is
+// 0 - which produces the records of the flagged tiles exactly as variant 3 does.  Every record therefore comes out of the
+// five-product kernel and its reference-order epilogue: same pairs, same bits.
+// Dense output (negative thresholds keep every pair) and the count dump bypass the screen (dispatch_king).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -44,12 +32,11 @@ namespace ck {
 
 namespace {
 
-#ifndef CK_FP4_TILE_N  // tile shape experiments: -DCK_FP4_TILE_N=64 -DCK_FP4_SLOTS=6 (profiles/r01_fp4_tuning.md)
-#define CK_FP4_TILE_N 80
-#define CK_FP4_SLOTS 4
+#ifndef CK_SCREEN_SLOTS
+#define CK_SCREEN_SLOTS 8
 #endif
-constexpr uint32_t kFM = 128, kFN = CK_FP4_TILE_N;  // tile rows (A operand, TMEM lanes) x tile columns (B operand)
-constexpr uint32_t kFSlots = CK_FP4_SLOTS;  // A ring in TMEM: one 64-site step per slot; AS slots form one A stage (barrier pair)
+constexpr uint32_t kFM = 128, kFN = 80;     // tile rows (A operand, TMEM lanes) x tile columns (B operand): the mxf4 kernel's tiles
+constexpr uint32_t kFSlots = CK_SCREEN_SLOTS;  // A ring in TMEM: one 64-site step per slot; AS slots form one A stage (barrier pair)
 constexpr uint32_t kFGroups = 2;            // groups of four A warps; group g fills the A stages with stage % 2 == g
 constexpr uint32_t kFSub = 4;               // B expanders work in sub-stages of 4 steps (register prefetch unit)
 constexpr uint32_t kFLBO = 128;             // bytes between K-adjacent 8x16-byte core matrices
@@ -58,13 +45,13 @@ constexpr uint32_t kFAWarps = 8, kFBWarps = (2 * kFN) / 32, kFExpWarps = kFAWarp
 constexpr uint32_t kFIssuers = 3;           // warps 13, 14, 15: x, y and h MMAs
 constexpr uint32_t kFAPrefetchSteps = 4;    // A register prefetch depth in steps of the group (= 8 steps ahead)
 constexpr uint32_t kFBPrefetch = 2;         // B register prefetch depth in sub-stages (= 8 steps ahead)
-constexpr uint32_t kFColXX = 0, kFColY = kFN, kFColH = 3 * kFN;  // accumulators: xx | (yy|yh) | (hy|hh)
-constexpr uint32_t kFColA = 5 * kFN;        // A ring: slot s at kFColA + 24 s: x, y, h (8 columns = 64 E2M1 each)
+constexpr uint32_t kFColXX = 0, kFColYW = kFN, kFColHY = 2 * kFN;  // accumulators: x.x | y.w | h.y
+constexpr uint32_t kFColA = 3 * kFN;        // A ring: slot s at kFColA + 24 s: x, y, h (8 columns = 64 E2M1 each)
 constexpr uint32_t kFColSF = kFColA + 24 * kFSlots;  // 16 columns of scale factors
 constexpr uint32_t kFTmemCols = 512;
 static_assert(kFBWarps * 32 == 2 * kFN, "two threads per column sample must fill whole warps");
 static_assert(kFColSF + 16 <= kFTmemCols, "TMEM budget");
-static_assert(kFM == kBandTileRows && (kFN == kBandTileCols || CK_FP4_TILE_N != 80), "band enumeration tile shape");
+static_assert(kFM == kBandTileRows && kFN == kBandTileCols, "band enumeration tile shape");
 static_assert(kChunkWords % (2 * kFGroups * kFAPrefetchSteps) == 0 && kChunkWords % (2 * kFSub * kFBPrefetch) == 0, "loop unrolling");
 
 template <uint32_t AS, uint32_t BS, uint32_t NS>
@@ -96,9 +83,9 @@ __device__ __forceinline__ void umma_mxf4_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 
 #ifdef CK_UMMA_PROFILE
-__device__ unsigned long long g_fp4_prof[16];
+__device__ unsigned long long g_screen_prof[16];
 #define FPROF_T() clock64()
-#define FPROF_ADD(slot, dt) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_fp4_prof[slot], (unsigned long long)(dt)); } while (0)
+#define FPROF_ADD(slot, dt) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_screen_prof[slot], (unsigned long long)(dt)); } while (0)
 #else
 #define FPROF_T() 0ull
 #define FPROF_ADD(slot, dt) do { (void)(dt); } while (0)
@@ -109,14 +96,19 @@ __device__ unsigned long long g_fp4_prof[16];
 __device__ __forceinline__ void pin8(const uint32_t (&v)[8]) {
   asm volatile("" ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
 }
-__device__ __forceinline__ void expand_fp4(uint32_t z, uint32_t &x, uint32_t &y, uint32_t &h) {
+__device__ __forceinline__ void expand_fp4(uint32_t z, uint32_t &x, uint32_t &y, uint32_t &h) {  // A operands
   x = z & 0xAAAAAAAAu;  // +1 hom-alt (0x2), -1 hom-ref (0xA)
   y = z & 0x22222222u;  // 1 hom
   h = z & 0x11111111u;  // 0.5 het
 }
+__device__ __forceinline__ void expand_b(uint32_t z, uint32_t &x, uint32_t &y, uint32_t &w) {  // B operands
+  x = z & 0xAAAAAAAAu;
+  y = z & 0x22222222u;
+  w = z & 0x33333333u;  // 1 hom, 0.5 het: y + h
+}
 
 template <uint32_t AS, uint32_t BS, uint32_t NS>
-__global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch p, const BandTiles tiles) {
+__global__ void __launch_bounds__(kFThreads, 1) king_screen_kernel(const KingLaunch p, const BandTiles tiles) {
   using G = Fp4Geo<AS, BS, NS>;
   constexpr uint32_t kAStages = G::kAStages;
   extern __shared__ uint8_t smem_raw[];
@@ -124,7 +116,6 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (p.tile_flags != nullptr && p.tile_flags[blockIdx.x] == 0) return;  // behind the screen kernel: only the tiles it flagged
 
   // ---- which tile: band order (band_tiles.cu) ----
   uint32_t ti, tj;
@@ -262,14 +253,14 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
         const uint32_t m = m0 + u;
         const uint32_t st = m / kSubsPerStage, sub = m % kSubsPerStage;  // stage counter, sub-stage inside it
         const uint32_t s = st % NS, fill = st / NS;
-        uint32_t x[kFSub][4], y[kFSub][4], h[kFSub][4];
+        uint32_t x[kFSub][4], y[kFSub][4], h[kFSub][4];  // h holds w = y + h on the B side
         const unsigned long long p0 = FPROF_T();
 #pragma unroll
         for (uint32_t q = 0; q < kFSub; ++q) {
-          expand_fp4(z[u][q].x, x[q][0], y[q][0], h[q][0]);
-          expand_fp4(z[u][q].y, x[q][1], y[q][1], h[q][1]);
-          expand_fp4(z[u][q].z, x[q][2], y[q][2], h[q][2]);
-          expand_fp4(z[u][q].w, x[q][3], y[q][3], h[q][3]);
+          expand_b(z[u][q].x, x[q][0], y[q][0], h[q][0]);
+          expand_b(z[u][q].y, x[q][1], y[q][1], h[q][1]);
+          expand_b(z[u][q].z, x[q][2], y[q][2], h[q][2]);
+          expand_b(z[u][q].w, x[q][3], y[q][3], h[q][3]);
         }
         load_sub(m + kFBPrefetch, z[u]);
         const unsigned long long p1 = FPROF_T();
@@ -295,15 +286,16 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
       }
     }
   } else {
-    // ===== MMA issuers: warps 13 (x.x), 14 (y.[y;h]), 15 (h.[y;h]).  The whole warp runs the loop (warp-uniform control
-    // flow keeps the descriptor arithmetic in the uniform datapath); one elected lane issues the MMA and the commits.
+    // ===== MMA issuers: warps 13 (x.x), 14 (y.w), 15 (h.y), N = 80 each.  The whole warp runs the loop (warp-uniform
+    // control flow keeps the descriptor arithmetic in the uniform datapath); one elected lane issues the MMA and the commits.
     const uint32_t which = warp - kFExpWarps;
     if (which < kFIssuers) {
-    const uint32_t idesc = which == 0 ? make_idesc_mxf4(kFM, kFN) : make_idesc_mxf4(kFM, 2 * kFN);
-    const uint32_t d_addr = tmem_base + (which == 0 ? kFColXX : which == 1 ? kFColY : kFColH);
+    const uint32_t idesc = make_idesc_mxf4(kFM, kFN);
+    const uint32_t d_addr = tmem_base + (which == 0 ? kFColXX : which == 1 ? kFColYW : kFColHY);
     const uint32_t a_addr = tmem_base + kFColA + which * 8;
     const uint32_t sf_addr = tmem_base + kFColSF;
-    const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem) + (which == 0 ? 0u : G::kTile), kFLBO, G::kSBO);  // x, or stacked [y ; h]
+    // B planes of a stage: x | y | w.  x.x reads x, y.w reads w, h.y reads y.
+    const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem) + (which == 0 ? 0u : which == 1 ? 2u * G::kTile : G::kTile), kFLBO, G::kSBO);
     const uint32_t elected = elect_one();
     for (uint32_t step = 0; step < num_steps; step += AS) {
       const uint32_t stage_no = step / AS, astage = stage_no % kAStages, mb = step / BS, sb = mb % NS, q = step % BS;
@@ -336,6 +328,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
   }
 
   // ===== epilogue: all 16 warps; thread = row (TMEM lane quadrant warp % 4), 20 columns per warp group (16 + 4) =====
+  bool any = false;
   {
     __syncwarp();
     mbar_wait_suspend(&acc_bar, 0);
@@ -346,137 +339,97 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     const uint32_t r = quad * 32 + lane;
     const uint32_t gi = i0 + r;
     const uint32_t lane_base = tmem_base + ((quad * 32u) << 16);
-    // Cheap conservative screen before the exact kinship, in fp32 on the raw accumulators (no conversions).  With
-    // every count at most 2^23 the accumulators are exact and the two expressions below are exact or off by one ulp
-    // (relative 2^-23, far inside the margin whenever they matter: |num| >= 2^23 implies den >= 2^23 / |thr - 0.5|):
-    //     num = 2 both_het - 4 opp - het_i - het_j = 2 (D_xx - D_yy - D_hy - D_yh)          (cuking.cu:289-292)
-    //     den = 4 min(het_i, het_j)                = 8 (2 D_hh + min(D_hy, D_yh))           (cuking.cu:293)
-    // and kin = fl(0.5 + fl(num / den)) differs from the real value by < 2^-22 relative, so a pair with
-    // num <= (thr - 0.5 - margin) den cannot pass the strict threshold test and skips the conversions and the IEEE
-    // division.  den == 0 implies num <= 0 (both_het <= min_hets), i.e. -inf / NaN, which the reference never emits.
-    const float screen4 = 4.f * (p.kin_threshold - 0.5f - (1e-3f + 1e-5f * fabsf(p.kin_threshold)));
-    const bool dump = p.dump_counts != nullptr, dense = p.dense_band_base != nullptr;
-    auto finish = [&](uint32_t c, uint32_t xx, uint32_t yy, uint32_t yh, uint32_t hy, uint32_t hh) {
+    // kin > thr needs D < 4 (0.5 - thr) min(het_i, het_j) <= 4 (0.5 - thr) min(Het_i, Het_j) with the het counts over all
+    // sites on the right.  The accumulators are exact multiples of 1/4 (header of king_fp4_kernel.cu), so half_d below is
+    // exact or off by an ulp; the reference's fp32 kin differs from the real value by a few ulps: a relative margin of
+    // 1e-4 plus one site on the bound covers both.  thr >= 0.5 (bound <= 0) leaves no candidate, like the reference.
+    const float bound2 = 2.f * (0.5f - p.kin_threshold) * 1.0001f;  // on D / 2
+    const uint32_t row_slot = p.row_slot0 + row0 + (r < rows_here ? r : 0u);
+    const float het_i = __uint2float_rn(__ldg(p.het_total + row_slot));
+    auto screen = [&](uint32_t c, uint32_t xx, uint32_t yw, uint32_t hy) {
       const uint32_t gj = j0 + c;
-      const float fxx = __uint_as_float(xx), fyy = __uint_as_float(yy), fyh = __uint_as_float(yh), fhy = __uint_as_float(hy),
-                  fhh = __uint_as_float(hh);
-      const float half_num = (fxx - fyy) - (fhy + fyh);
-      const float eighth_den = fmaf(2.f, fhh, fminf(fhy, fyh));
-      const bool in_tile = r < rows_here && c < cols_here;
-      const bool pair = in_tile && gi < gj;
-      const bool cand = pair && half_num > screen4 * eighth_den;
-      if (__ballot_sync(0xffffffffu, cand || dump || (dense && pair)) == 0) return;  // dense output: every pair owns a slot
-      // the accumulators hold exact multiples of 1/4 (see the header): scale back to integer counts
-      const int32_t n_xx = __float2int_rn(fxx);                    // conc - opp (signed)
-      const uint32_t n_yy = uint32_t(__float2int_rn(fyy));         // conc + opp
-      const uint32_t n_yh = uint32_t(__float2int_rn(2.f * fyh));   // i hom, j het
-      const uint32_t n_hy = uint32_t(__float2int_rn(2.f * fhy));   // i het, j hom
-      const uint32_t both_het = uint32_t(__float2int_rn(4.f * fhh));
-      const uint32_t het_i = both_het + n_hy;  // i het where j is defined
-      const uint32_t het_j = both_het + n_yh;  // j het where i is defined
-      const uint32_t opp = uint32_t(int32_t(n_yy) - n_xx) >> 1;
-      const uint32_t shared = n_yy + n_yh + n_hy + both_het;
-      const uint32_t conc = uint32_t(int32_t(n_yy) + n_xx) >> 1;
-      const float kin = kinship(het_i, het_j, both_het, opp);
-      if (dump && in_tile) {
-        const size_t idx = size_t(row0 + r) * p.num_cols + (col0 + c);
-        ck_counts out;
-        out.het_i = het_i; out.het_j = het_j; out.both_het = both_het;
-        out.opposing_hom = opp; out.concordant_hom = conc; out.shared_sites = shared;
-        p.dump_counts[idx] = out;
-        p.dump_kin[idx] = kin;
-      }
-      emit_pair(p, pair, cand, gi, gj, kin, opp, conc, both_het, shared);
+      const bool pair = r < rows_here && c < cols_here && gi < gj;
+      const float het_j = __uint2float_rn(__ldg(p.het_total + p.col_slot0 + col0 + (c < cols_here ? c : 0u)));  // warp-uniform address
+      const float half_d = (__uint_as_float(yw) + __uint_as_float(hy)) - __uint_as_float(xx);
+      any = any || (pair && half_d < fmaf(bound2, fminf(het_i, het_j), 1.f));
     };
     constexpr uint32_t kColsPerGroup = kFN / 4;  // 20
-    static_assert(kColsPerGroup == 20 || kColsPerGroup == 16, "epilogue column split");
     const uint32_t c0 = group * kColsPerGroup;
     {
-      uint32_t xx[16], yy[16], yh[16], hy[16], hh[16];
+      uint32_t xx[16], yw[16], hy[16];
       tmem_load16(lane_base + kFColXX + c0, xx);
-      tmem_load16(lane_base + kFColY + c0, yy);
-      tmem_load16(lane_base + kFColY + kFN + c0, yh);
-      tmem_load16(lane_base + kFColH + c0, hy);
-      tmem_load16(lane_base + kFColH + kFN + c0, hh);
+      tmem_load16(lane_base + kFColYW + c0, yw);
+      tmem_load16(lane_base + kFColHY + c0, hy);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (uint32_t q = 0; q < 16; ++q) finish(c0 + q, xx[q], yy[q], yh[q], hy[q], hh[q]);
+      for (uint32_t q = 0; q < 16; ++q) screen(c0 + q, xx[q], yw[q], hy[q]);
     }
-    if constexpr (kColsPerGroup > 16) {
-      uint32_t xx[4], yy[4], yh[4], hy[4], hh[4];
+    {
+      uint32_t xx[4], yw[4], hy[4];
       tmem_load4(lane_base + kFColXX + c0 + 16, xx);
-      tmem_load4(lane_base + kFColY + c0 + 16, yy);
-      tmem_load4(lane_base + kFColY + kFN + c0 + 16, yh);
-      tmem_load4(lane_base + kFColH + c0 + 16, hy);
-      tmem_load4(lane_base + kFColH + kFN + c0 + 16, hh);
+      tmem_load4(lane_base + kFColYW + c0 + 16, yw);
+      tmem_load4(lane_base + kFColHY + c0 + 16, hy);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (uint32_t q = 0; q < 4; ++q) finish(c0 + 16 + q, xx[q], yy[q], yh[q], hy[q], hh[q]);
+      for (uint32_t q = 0; q < 4; ++q) screen(c0 + 16 + q, xx[q], yw[q], hy[q]);
     }
     if (tid == 0) FPROF_ADD(14, FPROF_T() - t_main);
   }
   tcgen05_before_sync();
-  __syncthreads();
+  if (__syncthreads_or(any ? 1 : 0) && tid == 0) p.tile_flags[blockIdx.x] = 1;
   __syncwarp();
   if (warp == kFExpWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kFTmemCols));
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
 
-struct Fp4Config { uint32_t as, bs, ns; };
-Fp4Config fp4_config() {  // stage geometry; CUKING_FP4_STAGE = "<steps per A stage>x<steps per B stage>x<B stages>" is a tuning knob
-  static Fp4Config cfg = [] {
-    Fp4Config c{2, 8, 3};
-    if (const char *v = getenv("CUKING_FP4_STAGE")) {
-      unsigned a = 0, b = 0, n = 0;
-      if (sscanf(v, "%ux%ux%u", &a, &b, &n) == 3 && (a == 1 || a == 2) && ((b == 4 && n == 4) || (b == 8 && n == 3))) c = Fp4Config{a, b, n};
-    }
-    return c;
-  }();
-  return cfg;
-}
-
 template <uint32_t AS, uint32_t BS, uint32_t NS>
 cudaError_t launch_cfg(const KingLaunch &part, const BandTiles &tiles, cudaStream_t s) {
   static std::atomic<uint64_t> configured{0};  // one bit per device
-  if (cudaError_t e = optin_dynamic_smem(king_fp4_kernel<AS, BS, NS>, Fp4Geo<AS, BS, NS>::kSmem, configured); e != cudaSuccess) return e;
-  king_fp4_kernel<AS, BS, NS><<<unsigned(part.tile_end - part.tile_begin), kFThreads, Fp4Geo<AS, BS, NS>::kSmem, s>>>(part, tiles);
+  if (cudaError_t e = optin_dynamic_smem(king_screen_kernel<AS, BS, NS>, Fp4Geo<AS, BS, NS>::kSmem, configured); e != cudaSuccess) return e;
+  king_screen_kernel<AS, BS, NS><<<unsigned(part.tile_end - part.tile_begin), kFThreads, Fp4Geo<AS, BS, NS>::kSmem, s>>>(part, tiles);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 #ifdef CK_UMMA_PROFILE
-extern "C" void ck_debug_fp4_prof(unsigned long long *out) {
-  cudaMemcpyFromSymbol(out, g_fp4_prof, sizeof(g_fp4_prof));
+extern "C" void ck_debug_screen_prof(unsigned long long *out) {
+  cudaMemcpyFromSymbol(out, g_screen_prof, sizeof(g_screen_prof));
   unsigned long long z[16] = {0};
-  cudaMemcpyToSymbol(g_fp4_prof, z, sizeof(z));
+  cudaMemcpyToSymbol(g_screen_prof, z, sizeof(z));
 }
 #endif
 
-uint64_t king_fp4_num_tiles(const KingLaunch &k) { return band_num_tiles(k, kFN); }
-
-cudaError_t king_fp4_prepare(const KingLaunch &k, ck_ctx *ctx, cudaStream_t s, std::vector<uint64_t> *band_prefix) {
-  return band_prepare(k, kFN, ctx, s, band_prefix, nullptr);
-}
-
-cudaError_t launch_king_fp4(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches) {
-  (void)total_blocks;  // every row / column a tile reads lies inside the shard's allocated blocks
+// Screen kernel over the tile range, then the mxf4 kernel over the same range restricted to the flagged tiles.  Ranges are
+// cut at 2^24 tiles so that the flag bytes stay a small grow-only scratch of the ctx.
+cudaError_t launch_king_screen(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches) {
   if (k.tile_end <= k.tile_begin) return cudaSuccess;
   BandTiles tiles{};
   cudaError_t e = band_prepare(k, kFN, ctx, s, nullptr, &tiles);
   if (e != cudaSuccess) return e;
-  const Fp4Config cfg = fp4_config();
-  constexpr uint64_t kMaxGrid = 1ull << 30;
+  constexpr uint64_t kMaxGrid = 1ull << 24;
+  const size_t need = size_t(std::min<uint64_t>(k.tile_end - k.tile_begin, kMaxGrid));
+  if (ctx->tile_flags_bytes < need) {
+    if (ctx->tile_flags) {
+      if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;  // an earlier launch may still read the old buffer
+      cudaFree(ctx->tile_flags);
+      ctx->tile_flags = nullptr;
+      ctx->tile_flags_bytes = 0;
+    }
+    const size_t want = std::max<size_t>(need + need / 2, size_t(1) << 20);
+    if ((e = dev_alloc(ctx, reinterpret_cast<void **>(&ctx->tile_flags), want)) != cudaSuccess) return e;
+    ctx->tile_flags_bytes = want;
+  }
   for (uint64_t t = k.tile_begin; e == cudaSuccess && t < k.tile_end; t += kMaxGrid) {
     KingLaunch part = k;
     part.tile_begin = t;
     part.tile_end = (t + kMaxGrid < k.tile_end) ? t + kMaxGrid : k.tile_end;
-    if (cfg.as == 1 && cfg.bs == 4) e = launch_cfg<1, 4, 4>(part, tiles, s);
-    else if (cfg.as == 1) e = launch_cfg<1, 8, 3>(part, tiles, s);
-    else if (cfg.bs == 4) e = launch_cfg<2, 4, 4>(part, tiles, s);
-    else e = launch_cfg<2, 8, 3>(part, tiles, s);
+    part.tile_flags = ctx->tile_flags;
+    if ((e = cudaMemsetAsync(ctx->tile_flags, 0, size_t(part.tile_end - part.tile_begin), s)) != cudaSuccess) return e;
+    e = launch_cfg<2, 8, 3>(part, tiles, s);
     if (launches) ++*launches;
+    if (e == cudaSuccess) e = launch_king_fp4(part, total_blocks, ctx, s, launches);  // reads part.tile_flags
   }
   return e;
 }

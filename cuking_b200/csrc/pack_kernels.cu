@@ -197,6 +197,22 @@ __global__ void __launch_bounds__(256) finalize_codes_kernel(const uint32_t *__r
   }
 }
 
+// Het count of every plane slot over all its sites, from the E2M1 nibble codes (het = 0x1): what the screen kernel
+// (king_screen_kernel.cu) bounds min(het_i, het_j) with.  One CTA per 64-sample block, four word-strided partial sums per lane.
+__global__ void __launch_bounds__(256) het_totals_kernel(const uint4 *__restrict__ codes, uint32_t *__restrict__ totals, uint32_t words) {
+  __shared__ uint32_t partial[4][kTileSamples];
+  const uint32_t lane = threadIdx.x % kTileSamples, part = threadIdx.x / kTileSamples;
+  const uint4 *src = codes + size_t(blockIdx.x) * words * kTileSamples + lane;
+  uint32_t n = 0;
+  for (uint32_t w = part; w < words; w += 4) {
+    const uint4 z = __ldg(src + size_t(w) * kTileSamples);
+    n += __popc(z.x & 0x11111111u) + __popc(z.y & 0x11111111u) + __popc(z.z & 0x11111111u) + __popc(z.w & 0x11111111u);
+  }
+  partial[part][lane] = n;
+  __syncthreads();
+  if (part == 0) totals[size_t(blockIdx.x) * kTileSamples + lane] = partial[0][lane] + partial[1][lane] + partial[2][lane] + partial[3][lane];
+}
+
 // ---- reference layout <-> raw planes ----------------------------------------------------------------------------
 // The reference bit set is sample-major (cuking.cu:204-212): slot o, plane p, 64-bit word q at
 // bit_set[o*W + p*W/2 + q]; as little-endian uint32 the 32-site word k sits at index 2*(o*W + p*W/2) + k.
@@ -383,8 +399,10 @@ cudaError_t launch_finalize_codes_range(const ck_planes &pl, int kind, uint32_t 
   const size_t rows = size_t(num_blocks) * pl.words, row0 = size_t(block0) * pl.words;
   const uint32_t *raw = pl.raw + row0 * kRawPlanes * kTileSamples;
   uint4 *codes = reinterpret_cast<uint4 *>(pl.codes) + row0 * kTileSamples;
-  if (kind == 3)
+  if (kind == 3) {
     finalize_codes_kernel<true><<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(raw, codes, rows);
+    het_totals_kernel<<<num_blocks, 256, 0, s>>>(codes, pl.het_totals() + size_t(block0) * kTileSamples, pl.words);
+  }
   else
     finalize_codes_kernel<false><<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(raw, codes, rows);
   return cudaGetLastError();

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Checks the CTA-pair mxf4 kernel (variant 4) against variant 3 and the oracle on shapes that stress its tile pairing:
+"""Checks a tensor-core kernel variant (argv[1]; default 4, the CTA-pair mxf4 kernel; 5 = screen + mxf4) against variant 3 and the oracle on shapes that stress its tile pairing:
 odd / even numbers of row tiles, ragged edges, off-diagonal shards, views, parts, dense output."""
 import os
 import sys
@@ -12,6 +12,7 @@ import cuking_b200 as ck  # noqa: E402
 from oracle import king_oracle as ko  # noqa: E402
 from tests.helpers import random_genotypes, triples_of, oracle_bitset, assert_results_equal  # noqa: E402
 
+V = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 ok = True
 with ck.Context(0) as ctx:
     rng = np.random.default_rng(5)
@@ -22,7 +23,7 @@ with ck.Context(0) as ctx:
             osm = ko.submatrix(n, k, shard)
             want, count, _ = ko.king(oracle_bitset(g, osm), s, osm, 0.03, 1 << 22)
             res = {}
-            for v in (3, 4):
+            for v in (3, V):
                 ctx.set_king_variant(v)
                 with ctx.planes(sm, s) as pl:
                     pl.pack(*triples_of(g))
@@ -38,14 +39,14 @@ with ck.Context(0) as ctx:
                             ok = False
                             print("DENSE MISMATCH", n, s, k, shard, exc)
             try:
-                assert_results_equal(res[4], want)
+                assert_results_equal(res[V], want)
                 print("ok", n, s, k, shard, count)
             except AssertionError as exc:
                 ok = False
-                print("MISMATCH", n, s, k, shard, len(res[4]), len(res[3]), count, exc)
+                print("MISMATCH", n, s, k, shard, len(res[V]), len(res[3]), count, exc)
     # views and parts of a cohort
     g = random_genotypes(rng, 2600, 260)
-    ctx.set_king_variant(4)
+    ctx.set_king_variant(V)
     with ctx.planes(ck.submatrix(2600), 260) as pl:
         pl.pack(*triples_of(g))
         for k in (2, 3):
