@@ -261,6 +261,7 @@ int ck_ctx_create(int device, ck_ctx **out) {
   }
   ctx->stream = ctx->own_stream;
   ctx->king_variant = king_variant_from_env();
+  if (const char *v = getenv("CUKING_SCREEN_LEVEL")) ctx->screen_level = (atoi(v) == 1) ? 1 : (atoi(v) == 3) ? 3 : 0;
   *out = ctx;
   return CK_OK;
 }
@@ -417,10 +418,23 @@ int ensure_compute(ck_planes *pl) {
     CK_CUDA(ctx_alloc(ctx, reinterpret_cast<void **>(&pl->compute), pl->compute_bytes));
   }
   CK_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (want_codes && kind == 3) CK_CUDA(cudaMemsetAsync(pl->totals_sums(), 0, 2 * sizeof(unsigned long long), ctx->stream));
   if (pl->raw_words()) CK_CUDA(want_codes ? launch_finalize_codes(*pl, kind, ctx->stream) : launch_finalize(*pl, ctx->stream));
   CK_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   CK_CUDA(cudaEventSynchronize(ctx->ev[1]));
   ctx->timings.finalize_ms = elapsed_ms(ctx->ev[0], ctx->ev[1]);
+  pl->screen1_floor = -1.f;
+  if (want_codes && kind == 3 && variant == 5 && pl->raw_words()) {
+    // cohort call rate r and mean het count -> the kinship an unrelated pair's one-product bound reaches: about
+    // r + r^2 S / (2 het) (king_screen1_kernel.cu: the bound loses the sites where one sample is missing and the other not hom)
+    unsigned long long sums[2] = {0, 0};
+    CK_CUDA(cudaMemcpy(sums, pl->totals_sums(), sizeof(sums), cudaMemcpyDeviceToHost));
+    const double n = double(sm_samples(pl->map.sm)), sites = double(pl->num_sites);
+    if (n > 0 && sites > 0 && sums[0] > 0) {
+      const double r = std::max(0.0, 1.0 - double(sums[0] + sums[1]) / (n * sites)), het = double(sums[0]) / n;
+      pl->screen1_floor = float(r + r * r * sites / (2.0 * het));
+    }
+  }
   (want_codes ? pl->codes_stale : pl->compute_stale) = false;
   if (want_codes) pl->codes_kind = kind;
   return CK_OK;

@@ -86,6 +86,7 @@ struct ck_ctx {
   ck_result *result_buf = nullptr;
   size_t result_cap = 0;
   int king_variant = -1;  // -1 = library default
+  int screen_level = 0;   // variant 5: 0 = chosen per evaluation from the cohort's call rate, 1 / 3 = forced (CUKING_SCREEN_LEVEL)
   // kind::mxf4 accumulation self-test (fp4_selftest.cu): 0 = not run yet, 1 = exact, -1 = inexact -> int8 kernel
   int fp4_state = 0;
   // alive-tile table of the tcgen05 kernel (grow-only device scratch)
@@ -178,9 +179,16 @@ struct ck_planes {
   size_t raw_words() const { return size_t(map.num_blocks) * words * ck::kRawPlanes * ck::kTileSamples; }
   size_t compute_words() const { return size_t(map.num_blocks) * words * ck::kComputePlanes * ck::kTileSamples; }
   size_t codes_words() const { return size_t(map.num_blocks) * words * ck::kTileSamples * 4; }
-  // the codes buffer is followed by one uint32 per plane slot: the sample's het count over all sites (screen kernel)
-  size_t codes_alloc_words() const { return codes_words() + size_t(map.num_blocks) * ck::kTileSamples; }
-  uint32_t *het_totals() const { return codes ? codes + codes_words() : nullptr; }
+  // the codes buffer is followed by (het, hom) site counts per plane slot (uint2; the screen kernels bound kinship with
+  // them) and by the two sums over all slots (2 x uint64; the host picks the screen level from the cohort's call rate)
+  size_t codes_alloc_words() const { return codes_words() + size_t(map.num_blocks) * ck::kTileSamples * 2 + 4; }
+  uint2 *sample_totals() const { return codes ? reinterpret_cast<uint2 *>(codes + codes_words()) : nullptr; }
+  unsigned long long *totals_sums() const {
+    return codes ? reinterpret_cast<unsigned long long *>(codes + codes_words() + size_t(map.num_blocks) * ck::kTileSamples * 2) : nullptr;
+  }
+  // kinship an unrelated pair's one-product bound (king_screen1_kernel.cu) is expected to reach, from the cohort's call rate
+  // and het rate; < 0: not known (planes filled piecewise by the streaming seam) -> the three-product screen
+  float screen1_floor = -1.f;
   void mark_stale() { compute_stale = codes_stale = true; }
 };
 
@@ -242,11 +250,13 @@ struct KingLaunch {
   // sort is needed; a pair at or below the threshold leaves a hole (sample_i = 0xffffffff) and bumps *holes.
   const unsigned long long *dense_band_base;
   unsigned long long *holes;
-  // Screen kernel (king_screen_kernel.cu, variant 5): het count of every plane slot over all sites, and one byte per tile
+  // Screen kernels (king_screen_kernel.cu, king_screen1_kernel.cu; variant 5): site counts of every plane slot, and one byte per tile
   // of the launch - written by the screen kernel (1 = the tile holds a pair that may pass the threshold), read by the mxf4
   // kernel launched behind it over the same tile range, whose CTAs leave at once where the byte is 0.
-  const uint32_t *het_total;
+  const uint2 *sample_totals;  // (het, hom) site counts per plane slot
   uint8_t *tile_flags;
+  uint32_t num_sites;          // real (unpadded) sites
+  int screen_level;            // 1: one-product screen first (king_screen1_kernel.cu), else the three-product screen
 };
 // Where the records of one evaluation go (king_api.cu).  Sparse: appended through the atomic counter, sorted afterwards.
 // Dense: every pair has its slot in the sorted output; `regions` lists the output ranges in launch order with the event
@@ -316,6 +326,7 @@ constexpr uint32_t kPairTileCols = 64;  // 256 x 64 pair tiles
 cudaError_t king_fp4_prepare(const KingLaunch &k, ck_ctx *ctx, cudaStream_t s, std::vector<uint64_t> *band_prefix);
 // king_screen_kernel.cu (variant 5): three-product screen of every tile + the mxf4 kernel on the tiles it flags
 cudaError_t launch_king_screen(const KingLaunch &k, uint32_t total_blocks, ck_ctx *ctx, cudaStream_t s, uint32_t *launches);
+cudaError_t launch_king_screen1(const KingLaunch &part, const BandTiles &tiles, cudaStream_t s);  // king_screen1_kernel.cu
 constexpr uint32_t kFp4BandRows = kBandRowTiles * kBandTileRows;
 constexpr uint32_t kFp4MaxSites = 1u << 23;  // exactness of the tensor core's fp32 accumulation was measured up to this count
 

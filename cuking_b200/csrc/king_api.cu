@@ -109,8 +109,16 @@ uint64_t variant_num_tiles(int variant, const KingLaunch &k) {
 
 cudaError_t dispatch_king(int variant, const ck_planes *pl, const KingLaunch &k, cudaStream_t s, uint32_t *launches) {
   // the screen needs nothing but sparse records out of the tile: dense output and the count dump take the mxf4 kernel
-  if (variant == 5) return (k.dense_band_base || k.dump_counts || !k.het_total) ? launch_king_fp4(k, pl->map.num_blocks, pl->ctx, s, launches)
-                                                                              : launch_king_screen(k, pl->map.num_blocks, pl->ctx, s, launches);
+  if (variant == 5) {
+    if (k.dense_band_base || k.dump_counts || !k.sample_totals) return launch_king_fp4(k, pl->map.num_blocks, pl->ctx, s, launches);
+    // Which screen: the one-product bound (king_screen1_kernel.cu) is looser by about the cohort's missing rate; it is used
+    // when unrelated pairs are expected to stay 0.02 of kinship below the threshold under it (mispredicting only costs
+    // time: more tiles go on to the exact kernel).  CUKING_SCREEN_LEVEL=1 / 3 (read when the ctx is created) overrides.
+    KingLaunch ks = k;
+    if (pl->ctx->screen_level != 0) ks.screen_level = pl->ctx->screen_level;
+    else ks.screen_level = (pl->screen1_floor >= 0.f && k.kin_threshold - pl->screen1_floor > 0.02f) ? 1 : 3;
+    return launch_king_screen(ks, pl->map.num_blocks, pl->ctx, s, launches);
+  }
   if (variant == 4) return launch_king_fp4_pair(k, pl->map.num_blocks, pl->ctx, s, launches);
   if (variant == 3) return launch_king_fp4(k, pl->map.num_blocks, pl->ctx, s, launches);
   if (variant == 2) return launch_king_umma(k, pl->map.num_blocks, pl->ctx, s, launches);
@@ -125,7 +133,8 @@ int view_launch(const ck_planes *pl, const ck_submatrix *view, int variant, King
   KingLaunch k{};
   k.compute = pl->compute;
   k.codes = pl->codes;
-  k.het_total = pl->het_totals();
+  k.sample_totals = pl->sample_totals();
+  k.num_sites = pl->num_sites;
   k.words = pl->words;
   if (view == nullptr) {
     k.row_slot0 = 0;
@@ -578,7 +587,7 @@ int stream_rows_device(ck_planes *pl, const uint64_t *d_rows, uint32_t s0, uint3
   ctx->timings.king_launches += 2;
   const uint32_t band_lo = s0 / kFp4BandRows, band_hi = ceil_div(std::min(s1, n), kFp4BandRows);
   st->k.codes = pl->codes;
-  st->k.het_total = pl->het_totals();
+  st->k.sample_totals = pl->sample_totals();
   int rc = launch_bands(pl, st->k, st->variant, st->band_prefix, band_lo, band_hi, st->part_index, st->num_parts, 0xffffffffu, false, &st->plan);
   if (rc != CK_OK) return rc;
   st->next_end = s0;

@@ -8,7 +8,7 @@
 // THREE exact products of N = 80 instead of the five (N = 80 + 160 + 160) the counters need: 127 instead of 212 tensor
 // clocks per 64 sites, 240 instead of 400 accumulator columns - so the A ring in TMEM is 8 slots deep instead of 4 and the
 // refill latency that holds the five-product kernel at 88 % tensor activity is off the critical path.  min(het_i, het_j)
-// over the jointly called sites is at most the minimum of the two samples' het counts over ALL sites (het_totals_kernel),
+// over the jointly called sites is at most the minimum of the two samples' het counts over ALL sites (sample_totals_kernel),
 // so   D < 4 (0.5 - thr) min(Het_i, Het_j)   is a necessary condition, exact in fp32 up to a margin.  For unrelated
 // pairs kin is near 0 and the bound is off by about missing_rate / 2: at the thresholds cuKING is run with the screen
 // rejects everything but the related pairs and their immediate neighbourhood.
@@ -345,11 +345,11 @@ __global__ void __launch_bounds__(kFThreads, 1) king_screen_kernel(const KingLau
     // 1e-4 plus one site on the bound covers both.  thr >= 0.5 (bound <= 0) leaves no candidate, like the reference.
     const float bound2 = 2.f * (0.5f - p.kin_threshold) * 1.0001f;  // on D / 2
     const uint32_t row_slot = p.row_slot0 + row0 + (r < rows_here ? r : 0u);
-    const float het_i = __uint2float_rn(__ldg(p.het_total + row_slot));
+    const float het_i = __uint2float_rn(__ldg(p.sample_totals + row_slot).x);
     auto screen = [&](uint32_t c, uint32_t xx, uint32_t yw, uint32_t hy) {
       const uint32_t gj = j0 + c;
       const bool pair = r < rows_here && c < cols_here && gi < gj;
-      const float het_j = __uint2float_rn(__ldg(p.het_total + p.col_slot0 + col0 + (c < cols_here ? c : 0u)));  // warp-uniform address
+      const float het_j = __uint2float_rn(__ldg(p.sample_totals + p.col_slot0 + col0 + (c < cols_here ? c : 0u)).x);  // warp-uniform address
       const float half_d = (__uint_as_float(yw) + __uint_as_float(hy)) - __uint_as_float(xx);
       any = any || (pair && half_d < fmaf(bound2, fminf(het_i, het_j), 1.f));
     };
@@ -427,7 +427,7 @@ cudaError_t launch_king_screen(const KingLaunch &k, uint32_t total_blocks, ck_ct
     part.tile_end = (t + kMaxGrid < k.tile_end) ? t + kMaxGrid : k.tile_end;
     part.tile_flags = ctx->tile_flags;
     if ((e = cudaMemsetAsync(ctx->tile_flags, 0, size_t(part.tile_end - part.tile_begin), s)) != cudaSuccess) return e;
-    e = launch_cfg<2, 8, 3>(part, tiles, s);
+    e = part.screen_level == 1 ? launch_king_screen1(part, tiles, s) : launch_cfg<2, 8, 3>(part, tiles, s);
     if (launches) ++*launches;
     if (e == cudaSuccess) e = launch_king_fp4(part, total_blocks, ctx, s, launches);  // reads part.tile_flags
   }

@@ -197,20 +197,32 @@ __global__ void __launch_bounds__(256) finalize_codes_kernel(const uint32_t *__r
   }
 }
 
-// Het count of every plane slot over all its sites, from the E2M1 nibble codes (het = 0x1): what the screen kernel
-// (king_screen_kernel.cu) bounds min(het_i, het_j) with.  One CTA per 64-sample block, four word-strided partial sums per lane.
-__global__ void __launch_bounds__(256) het_totals_kernel(const uint4 *__restrict__ codes, uint32_t *__restrict__ totals, uint32_t words) {
-  __shared__ uint32_t partial[4][kTileSamples];
+// (het, hom) site counts of every plane slot over all its sites, from the E2M1 nibble codes (het = 0x1, hom = 0x2 | sign):
+// what the screen kernels bound kinship with (king_screen_kernel.cu, king_screen1_kernel.cu).  One CTA per 64-sample block,
+// four word-strided partial sums per lane; the block's sums also go into the two cohort-wide counters.
+__global__ void __launch_bounds__(256) sample_totals_kernel(const uint4 *__restrict__ codes, uint2 *__restrict__ totals,
+                                                            unsigned long long *__restrict__ sums, uint32_t words) {
+  __shared__ uint32_t partial[2][4][kTileSamples];
   const uint32_t lane = threadIdx.x % kTileSamples, part = threadIdx.x / kTileSamples;
   const uint4 *src = codes + size_t(blockIdx.x) * words * kTileSamples + lane;
-  uint32_t n = 0;
+  uint32_t het = 0, hom = 0;
   for (uint32_t w = part; w < words; w += 4) {
     const uint4 z = __ldg(src + size_t(w) * kTileSamples);
-    n += __popc(z.x & 0x11111111u) + __popc(z.y & 0x11111111u) + __popc(z.z & 0x11111111u) + __popc(z.w & 0x11111111u);
+    het += __popc(z.x & 0x11111111u) + __popc(z.y & 0x11111111u) + __popc(z.z & 0x11111111u) + __popc(z.w & 0x11111111u);
+    hom += __popc(z.x & 0x22222222u) + __popc(z.y & 0x22222222u) + __popc(z.z & 0x22222222u) + __popc(z.w & 0x22222222u);
   }
-  partial[part][lane] = n;
+  partial[0][part][lane] = het;
+  partial[1][part][lane] = hom;
   __syncthreads();
-  if (part == 0) totals[size_t(blockIdx.x) * kTileSamples + lane] = partial[0][lane] + partial[1][lane] + partial[2][lane] + partial[3][lane];
+  if (part == 0) {
+    het = partial[0][0][lane] + partial[0][1][lane] + partial[0][2][lane] + partial[0][3][lane];
+    hom = partial[1][0][lane] + partial[1][1][lane] + partial[1][2][lane] + partial[1][3][lane];
+    totals[size_t(blockIdx.x) * kTileSamples + lane] = make_uint2(het, hom);
+    if (sums != nullptr) {
+      atomicAdd(&sums[0], (unsigned long long)het);
+      atomicAdd(&sums[1], (unsigned long long)hom);
+    }
+  }
 }
 
 // ---- reference layout <-> raw planes ----------------------------------------------------------------------------
@@ -401,7 +413,9 @@ cudaError_t launch_finalize_codes_range(const ck_planes &pl, int kind, uint32_t 
   uint4 *codes = reinterpret_cast<uint4 *>(pl.codes) + row0 * kTileSamples;
   if (kind == 3) {
     finalize_codes_kernel<true><<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(raw, codes, rows);
-    het_totals_kernel<<<num_blocks, 256, 0, s>>>(codes, pl.het_totals() + size_t(block0) * kTileSamples, pl.words);
+    // the cohort-wide sums only make sense when everything is derived in one go (ensure_compute zeroes them)
+    sample_totals_kernel<<<num_blocks, 256, 0, s>>>(codes, pl.sample_totals() + size_t(block0) * kTileSamples,
+                                                    (block0 == 0 && num_blocks == pl.map.num_blocks) ? pl.totals_sums() : nullptr, pl.words);
   }
   else
     finalize_codes_kernel<false><<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(raw, codes, rows);

@@ -148,7 +148,7 @@ def load_kats():
         return json.load(f)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 5])
 @pytest.mark.parametrize("kat", load_kats(), ids=lambda k: k["id"])
 def test_known_answer_vectors_on_gpu(ctx, kat, variant):
     ctx.set_king_variant(variant)
@@ -178,7 +178,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 5])
 @pytest.mark.parametrize("n,s,k,shard,thr", CASES)
 def test_king_matches_oracle(ctx, n, s, k, shard, thr, variant):
     ctx.set_king_variant(variant)

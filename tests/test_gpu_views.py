@@ -44,7 +44,7 @@ def device_count():
 # ---- views ---------------------------------------------------------------------------------------------------------
 
 
-@pytest.mark.parametrize("variant", [3, 2])
+@pytest.mark.parametrize("variant", [3, 2, 5])
 @pytest.mark.parametrize("n,s", [(700, 500), (1300, 333)])
 def test_every_shard_as_a_view_of_cohort_planes(ctx, variant, n, s):
     # one plane set for the whole cohort; each shard of --split_factor k is evaluated as a view (cuking.cu:129-152
@@ -139,7 +139,7 @@ def test_parts_are_disjoint_and_their_union_is_the_shard(ctx, variant):
 # ---- dense output --------------------------------------------------------------------------------------------------
 
 
-@pytest.mark.parametrize("variant", [3, 2])
+@pytest.mark.parametrize("variant", [3, 2, 5])
 @pytest.mark.parametrize("k,shard", [(1, 0), (2, 1)])
 def test_dense_output_with_and_without_holes(ctx, variant, k, shard):
     # thr = -1 keeps (nearly) every pair: records are written straight to their sorted slot; thr = -0.02 leaves

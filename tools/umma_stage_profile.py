@@ -11,7 +11,7 @@ n, s = 4096, 100000
 pl = ctx.planes(ck.submatrix(n), s); pl.synthesize(42, 0.01); pl.finalize()
 out = np.empty(1 << 20, dtype=ck.RESULT_DTYPE)
 L = capi.load()
-prof = L.ck_debug_fp4_pair_prof if variant == 4 else L.ck_debug_fp4_prof if variant == 3 else L.ck_debug_umma_prof
+prof = L.ck_debug_screen_prof if variant == 5 else L.ck_debug_fp4_pair_prof if variant == 4 else L.ck_debug_fp4_prof if variant == 3 else L.ck_debug_umma_prof
 buf = (ctypes.c_ulonglong * 32)()
 for it in range(2):
     prof(buf)
@@ -30,4 +30,4 @@ ka, kb = max(v[3], 1), max(v[7], 1)
 kk = max(v[13] if variant >= 3 else v[11], 1)
 print("per item per warp: A expand %.0f wait %.0f store %.0f | B expand %.0f wait %.0f store %.0f | issuers wait/step %.0f %.0f %.0f" % (v[0]/ka, v[1]/ka, v[2]/ka, v[4]/kb, v[5]/kb, v[6]/kb, v[8]/kk, v[9]/kk, v[10]/kk))
 if variant >= 3:
-    print("mainloop clk/step %.1f (tensor floor 212), issuer1 issue+commit clk/step %.1f, epilogue clk %d" % (v[12] / kk, v[11] / kk, v[14]))
+    print("mainloop clk/step %.1f (tensor floor 212; screen kernel 127), issuer1 issue+commit clk/step %.1f, epilogue clk %d" % (v[12] / kk, v[11] / kk, v[14]))
