@@ -447,6 +447,7 @@ class Bench:
         for _ in range(warmup):
             step(scale)
         self.barrier()
+        screen0 = ctx.screen_stats()  # variant 5 (outside the timed region: the call synchronises)
         sampler = ClockSampler(self.local_rank, args.clock_sample_ms / 1e3)
         sampler.start()
         king_ms, launches, d2h_tail_ms, last = [], 0, [], []
@@ -466,6 +467,12 @@ class Bench:
         self.ev1.record(self.stream)
         self.barrier()
         clocks = sampler.stop()
+        screen1 = ctx.screen_stats()
+        screened, flagged = (screen1["tiles_screened"] - screen0["tiles_screened"]) / steps, (screen1["tiles_flagged"] - screen0["tiles_flagged"]) / steps
+        screen = {"level": screen1["level"] if screened else 0, "tiles_screened_per_step": screened, "tiles_flagged_per_step": flagged,
+                  "flagged_frac": (flagged / screened) if screened else None,
+                  "what": "variant 5: a one- (level 1) or three-product (level 3) bound on the squared genotype distance is evaluated on "
+                          "every tile; only the flagged tiles go on to the five-product kernel, which produces every record"}
         elapsed_ms = self.max_over_ranks(self.ev0.elapsed_time(self.ev1))
         # checksum of the last timed pass's records (outside the timed region)
         retained, check_parts, block_parts = 0, [], []
@@ -509,7 +516,7 @@ class Bench:
                             "config takes over a minute at N = 1); allocations, tile tables and clocks are warm when the timed "
                             "passes start") if partial_warmup else None,
             "ms_per_step": ms_per_step, "value": value, "kernel_ms": kernel_ms, "sort_d2h_ms": float(np.mean(d2h_tail_ms)),
-            "retained_pairs": retained, "gpu_launches": launches, "kernel_variant": variant, "my_units": my_units,
+            "retained_pairs": retained, "gpu_launches": launches, "kernel_variant": variant, "my_units": my_units, "screen": screen,
             "total_units": total_units, "clocks": clocks, "e2e": e2e, "exchange": exchange, "checks": checks,
             "input_synthesis_s": round(synth_s, 3), "items_this_rank": len(items), "max_results": max_results,
             "config": workload_config(name, self.n_gpus),
@@ -642,7 +649,7 @@ class Bench:
             "peak_source": "POPC.32 issue rate measured live on this GPU by ck_measure_int_peaks (16 lanes/clk/SM)",
             "lop3_peak": peaks["lop3_lane_ops_per_s"] / 1e9,
         }
-        umma = variant in (2, 3, 4)
+        umma = variant in (2, 3, 4, 5)
         # operand streaming: each 128 x 80 tile reads the genotype codes of its 208 samples once - from L2 mostly; the
         # compulsory HBM traffic is every sample's codes once per pass
         pairs = my_units / n_sites
@@ -660,7 +667,7 @@ class Bench:
         if variant == 3 and w["name"] == "cfg2" and self.n_gpus == 1:
             traffic, traffic_from = 425.21e9, ("profiles/r01_king_fp4_cfg2_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum of one "
                                                "ncu --set full capture of this launch shape; not re-measured by this run)")
-        if variant in (3, 4):
+        if variant in (3, 4, 5):
             if self.fp4_sustained_ops is None:  # once per process, right after the headline passes (the board is warm)
                 sampler = ClockSampler(self.local_rank, 0.1)
                 sampler.start()
@@ -672,8 +679,23 @@ class Bench:
             # A pass that holds the board at its power cap (NVML says so during the timed region) is the latter.
             capped = "sw_power_cap" in (w["clocks"].get("reasons") or [])
             peak = sustained if capped else burst
+            screen = w.get("screen") or {}
+            level = screen.get("level") or 0
+            executed = None
+            kernel_name = "king_fp4_kernel"
+            if variant == 5 and level:
+                # What the tensor cores executed: the screen's products over every pair-site (1 MAC = 2 ops at level 1, 3 MACs at
+                # level 3) plus the five-product kernel on the flagged tiles.  `achieved` stays SURVEY 8(d)'s algorithmic figure
+                # (10 ops per pair-site of the reference formulation), which a screen can legitimately exceed the peak with.
+                per_unit = 2.0 * (1 if level == 1 else 3) + 10.0 * (screen.get("flagged_frac") or 0.0)
+                ex = my_units * per_unit / (kernel_ms * 1e-3) / 1e12
+                executed = {"ops_per_unit": per_unit, "achieved": ex, "frac": ex / peak,
+                            "note": "tensor ops actually issued per pair-site: the screen kernel is bound by operand delivery (L2 -> SM and the "
+                                    "shared-memory data path), not by the tensor pipe: see profiles/r02_screen1_ncu.txt"}
+                kernel_name = ("king_screen1_kernel" if level == 1 else "king_screen_kernel") + " + king_fp4_kernel on the flagged tiles"
             return {
-                "bound": "tensor", "kernel": "king_fp4_kernel", "achieved": tops, "peak": peak, "unit": "TOP/s (fp4 e2m1, dense)",
+                "bound": "tensor", "kernel": kernel_name, "achieved": tops, "peak": peak, "unit": "TOP/s (fp4 e2m1, dense)",
+                "executed": executed, "screen": screen or None,
                 "frac": tops / peak, "peak_kind": "sustained" if capped else "burst",
                 "burst": {"peak": burst, "frac": tops / burst,
                           "how": "ck_measure_fp4_peak: best of five 2-ms launches, constant operands - the board stays at its maximum clock"},
@@ -745,6 +767,7 @@ def main():
             "warmup_note": w["warmup_note"], "ms_per_step": w["ms_per_step"], "value": w["value"], "unit": UNIT,
             "kernel_ms": w["kernel_ms"], "sort_d2h_ms_exposed": w["sort_d2h_ms"], "ms_per_step_over_kernel_ms": w["ms_per_step"] / w["kernel_ms"],
             "retained_pairs": w["retained_pairs"], "gpu_launches": w["gpu_launches"], "items_on_rank0": w["items_this_rank"],
+            "kernel_variant": w["kernel_variant"], "screen": w["screen"],
             "roofline_frac": r["frac"], "roofline_peak_kind": r.get("peak_kind"), "roofline_frac_burst": (r.get("burst") or {}).get("frac"),
             "roofline_achieved": r["achieved"], "roofline_peak": r["peak"], "e2e": w["e2e"],
             "e2e_note": None if w["e2e"] else "resident inputs only: a pinned host copy of the 25 GB bit set per rank is not staged by the bench",
@@ -777,7 +800,8 @@ def main():
         line = {
             "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": b.n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong" if fixed else "weak", "vs_baseline": None,
-            "dtype": {3: "fp4 (e2m1 indicators, exact fp32 accumulation)", 2: "int8 (indicators, s32 accumulation)"}.get(variant, "u32 (bit planes, LOP3+POPC)"),
+            "dtype": {3: "fp4 (e2m1 indicators, exact fp32 accumulation)", 4: "fp4 (e2m1 indicators, exact fp32 accumulation)",
+                      5: "fp4 (e2m1 indicators, exact fp32 accumulation)", 2: "int8 (indicators, s32 accumulation)"}.get(variant, "u32 (bit planes, LOP3+POPC)"),
             "data": "synthetic",
             "config": head["config"],
             "run": {"retained_pairs": head["retained_pairs"], "kernel_variant": variant, "input_synthesis_s": head["input_synthesis_s"],

@@ -95,7 +95,7 @@ EXPORTED_SYMBOLS = [
     "ck_king_num_tiles", "ck_planes_king_variant", "ck_king_tiles", "ck_king_counts", "ck_king_host_bitset", "ck_king_host_bitset_part", "ck_king_stream_granularity", "ck_king_stream_begin",
     "ck_king_stream_rows", "ck_king_stream_end", "ck_synth_genotypes_host",
     "ck_synth_triples_device", "ck_ctx_fp4_selftest", "ck_planes_and_reduce", "ck_king_view", "ck_king_view_sink", "ck_plan_work", "ck_measure_fp4_peak", "ck_measure_fp4_peak_sustained", "ck_pack_triples_narrow",
-    "ck_rle_scan", "ck_pack_encoded",
+    "ck_rle_scan", "ck_pack_encoded", "ck_ctx_screen_stats",
 ]
 
 # typedef int (*ck_result_sink)(void *user, const ck_result *records, size_t count)
@@ -148,6 +148,7 @@ def load() -> C.CDLL:
         "ck_measure_fp4_peak_sustained": ([vp, C.c_double, C.POINTER(C.c_double)], i32),
         "ck_plan_work": ([u32, u32, u32, u32, u32, C.POINTER(WorkItem), u32, C.POINTER(u32)], i32),
         "ck_ctx_fp4_selftest": ([vp, C.POINTER(i32)], i32),
+        "ck_ctx_screen_stats": ([vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)], i32),
         "ck_planes_and_reduce": ([C.POINTER(vp), u32], i32),
         "ck_king_view": ([vp, SMp, u32, u32, f32, u32, vp, i32, C.POINTER(u32), i32], i32),
         "ck_king_view_sink": ([vp, SMp, u32, u32, f32, u32, C.c_size_t, RESULT_SINK, vp, C.POINTER(u64)], i32),

@@ -121,8 +121,9 @@ int king_variant_from_env() {
 using namespace ck;
 
 // default pairwise kernel variant: 0 = 5 POPC per pair-word, 1 = carry-save (2.5 POPC + 5 more LOP3),
-// 2 = tcgen05 int8 tensor-core formulation, 3 = tcgen05 mxf4 (E2M1, fp32 accumulation) formulation
-static int g_default_variant = 3;
+// 2 = tcgen05 int8 tensor-core formulation, 3 = tcgen05 mxf4 (E2M1, fp32 accumulation) formulation,
+// 5 = the mxf4 kernel behind the one- / three-product screens (king_screen1_kernel.cu, king_screen_kernel.cu)
+static int g_default_variant = 5;
 static int active_variant(const ck_ctx *ctx) { return ctx->king_variant >= 0 ? ctx->king_variant : g_default_variant; }
 
 // The mxf4 kernel relies on the tensor core adding E2M1 products into its fp32 accumulator without losing low bits - a
@@ -144,6 +145,11 @@ static bool fp4_usable(ck_ctx *ctx) {
 }
 
 namespace ck {
+float screen1_floor_from_sums(const unsigned long long sums[2], double samples, double sites) {
+  if (samples <= 0 || sites <= 0 || sums[0] == 0) return -1.f;
+  const double r = std::max(0.0, 1.0 - double(sums[0] + sums[1]) / (samples * sites)), het = double(sums[0]) / samples;
+  return float(r + r * r * sites / (2.0 * het));
+}
 // The variant that actually runs on these planes: the fp32 accumulators of the mxf4 kernel are exact only up to the
 // site count the probe verified (kFp4MaxSites) and only if this GPU passed the self-test; otherwise the int8 kernel.
 int planes_variant(const ck_planes *pl) {
@@ -255,7 +261,9 @@ int ck_ctx_create(int device, ck_ctx **out) {
       (e = cudaEventCreate(&ctx->ev[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev[1])) != cudaSuccess ||
       (e = cudaMalloc(&ctx->d_counter, kCounterBytes)) != cudaSuccess ||
       (e = cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_holes), kCounterBytes, cudaHostAllocDefault)) != cudaSuccess ||
-      (e = cudaMalloc(&ctx->d_pack_err, 4 * sizeof(unsigned long long))) != cudaSuccess) {
+      (e = cudaMalloc(&ctx->d_pack_err, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->d_screen_flagged, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(ctx->d_screen_flagged, 0, sizeof(unsigned long long))) != cudaSuccess) {
     ck_ctx_destroy(ctx);
     return fail_cuda(e, "ck_ctx_create", __FILE__, __LINE__);
   }
@@ -283,6 +291,18 @@ int ck_ctx_synchronize(ck_ctx *ctx) {
   if (!ctx) return fail(CK_ERR_INVALID_ARGUMENT, "ctx is NULL");
   DeviceGuard guard(ctx->device);
   CK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CK_OK;
+}
+
+int ck_ctx_screen_stats(ck_ctx *ctx, uint64_t *tiles_screened, uint64_t *tiles_flagged, int *level) {
+  if (!ctx) return fail(CK_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  DeviceGuard guard(ctx->device);
+  unsigned long long flagged = 0;
+  CK_CUDA(cudaStreamSynchronize(ctx->stream));
+  CK_CUDA(cudaMemcpy(&flagged, ctx->d_screen_flagged, sizeof(flagged), cudaMemcpyDeviceToHost));
+  if (tiles_screened) *tiles_screened = ctx->screen_tiles;
+  if (tiles_flagged) *tiles_flagged = flagged;
+  if (level) *level = ctx->screen_level_used;
   return CK_OK;
 }
 
@@ -325,6 +345,7 @@ int ck_ctx_destroy(ck_ctx *ctx) {
   if (ctx->result_buf) cudaFree(ctx->result_buf);
   if (ctx->tile_table) cudaFree(ctx->tile_table);
   if (ctx->tile_flags) cudaFree(ctx->tile_flags);
+  if (ctx->d_screen_flagged) cudaFree(ctx->d_screen_flagged);
   if (ctx->sort_scratch) cudaFree(ctx->sort_scratch);
   for (int i = 0; i < ck_ctx::kCacheSlots; ++i)
     if (ctx->cache_ptr[i]) cudaFree(ctx->cache_ptr[i]);
@@ -429,11 +450,7 @@ int ensure_compute(ck_planes *pl) {
     // r + r^2 S / (2 het) (king_screen1_kernel.cu: the bound loses the sites where one sample is missing and the other not hom)
     unsigned long long sums[2] = {0, 0};
     CK_CUDA(cudaMemcpy(sums, pl->totals_sums(), sizeof(sums), cudaMemcpyDeviceToHost));
-    const double n = double(sm_samples(pl->map.sm)), sites = double(pl->num_sites);
-    if (n > 0 && sites > 0 && sums[0] > 0) {
-      const double r = std::max(0.0, 1.0 - double(sums[0] + sums[1]) / (n * sites)), het = double(sums[0]) / n;
-      pl->screen1_floor = float(r + r * r * sites / (2.0 * het));
-    }
+    pl->screen1_floor = screen1_floor_from_sums(sums, double(sm_samples(pl->map.sm)), double(pl->num_sites));
   }
   (want_codes ? pl->codes_stale : pl->compute_stale) = false;
   if (want_codes) pl->codes_kind = kind;

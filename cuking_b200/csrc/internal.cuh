@@ -94,6 +94,9 @@ struct ck_ctx {
   size_t tile_table_bytes = 0;
   uint8_t *tile_flags = nullptr;  // screen kernel: one byte per tile of a launch (grow-only)
   size_t tile_flags_bytes = 0;
+  unsigned long long *d_screen_flagged = nullptr;  // tiles the screens have flagged on this ctx so far (ck_ctx_screen_stats)
+  unsigned long long screen_tiles = 0;             // tiles they have been launched over
+  int screen_level_used = 0;                       // screen of the last variant-5 launch: 1, 3, or 0 = none (mxf4 kernel alone)
   uint64_t tile_table_key[3] = {~0ull, 0, 0};  // (variant, rows/cols, global origins) of the table now on the device
   // dense output: first output slot of every band (device copy + the host vector the async upload reads)
   unsigned long long *dense_table = nullptr;
@@ -212,7 +215,10 @@ cudaError_t launch_decode_pack(const ck_planes &pl, const EncodedColumnDev (&col
 cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s);
 cudaError_t launch_finalize_codes(const ck_planes &pl, int kind, cudaStream_t s);
 // the same for the 64-sample blocks [block0, block0 + num_blocks) only (pipelined host-buffer path)
-cudaError_t launch_finalize_codes_range(const ck_planes &pl, int kind, uint32_t block0, uint32_t num_blocks, cudaStream_t s);
+cudaError_t launch_finalize_codes_range(const ck_planes &pl, int kind, uint32_t block0, uint32_t num_blocks, cudaStream_t s,
+                                        bool add_to_sums = false);
+// call rate and het rate of `samples` samples (their (het, hom) sums) -> ck_planes::screen1_floor
+float screen1_floor_from_sums(const unsigned long long sums[2], double samples, double sites);
 // d_rows points at the reference-layout row of slot ref_slot0 (a chunk of the bit set, or the whole of it with 0)
 cudaError_t launch_import_ref_range(const ck_planes &pl, const uint64_t *d_rows, uint32_t ref_slot0, uint32_t block0,
                                     uint32_t num_blocks, cudaStream_t s);
@@ -255,6 +261,7 @@ struct KingLaunch {
   // kernel launched behind it over the same tile range, whose CTAs leave at once where the byte is 0.
   const uint2 *sample_totals;  // (het, hom) site counts per plane slot
   uint8_t *tile_flags;
+  unsigned long long *flagged_counter;  // += 1 per flagged tile (statistics)
   uint32_t num_sites;          // real (unpadded) sites
   int screen_level;            // 1: one-product screen first (king_screen1_kernel.cu), else the three-product screen
 };

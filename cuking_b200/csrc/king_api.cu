@@ -110,13 +110,20 @@ uint64_t variant_num_tiles(int variant, const KingLaunch &k) {
 cudaError_t dispatch_king(int variant, const ck_planes *pl, const KingLaunch &k, cudaStream_t s, uint32_t *launches) {
   // the screen needs nothing but sparse records out of the tile: dense output and the count dump take the mxf4 kernel
   if (variant == 5) {
+    pl->ctx->screen_level_used = 0;
     if (k.dense_band_base || k.dump_counts || !k.sample_totals) return launch_king_fp4(k, pl->map.num_blocks, pl->ctx, s, launches);
-    // Which screen: the one-product bound (king_screen1_kernel.cu) is looser by about the cohort's missing rate; it is used
-    // when unrelated pairs are expected to stay 0.02 of kinship below the threshold under it (mispredicting only costs
-    // time: more tiles go on to the exact kernel).  CUKING_SCREEN_LEVEL=1 / 3 (read when the ctx is created) overrides.
+    // Which screen.  Under the three-product bound an unrelated pair reaches a kinship of about r / 2 (r = the cohort's
+    // missing rate), under the one-product bound (king_screen1_kernel.cu) about r + r^2 S / (2 het) (ck_planes::
+    // screen1_floor, from the cohort's totals).  A screen is used when that leaves unrelated pairs clear of the threshold
+    // (0.02 / 0.015 of kinship; without totals - planes filled piecewise - the three-product screen from 0.03 on); below,
+    // nearly every tile would go on to the exact kernel anyway, which then runs alone.  Mispredicting only costs time.
+    // CUKING_SCREEN_LEVEL = 1 / 3 (read when the ctx is created) forces a screen.
     KingLaunch ks = k;
+    const float floor1 = pl->screen1_floor, floor3 = floor1 >= 0.f ? 0.5f * floor1 : 0.015f;
     if (pl->ctx->screen_level != 0) ks.screen_level = pl->ctx->screen_level;
-    else ks.screen_level = (pl->screen1_floor >= 0.f && k.kin_threshold - pl->screen1_floor > 0.02f) ? 1 : 3;
+    else if (floor1 >= 0.f && k.kin_threshold - floor1 > 0.02f) ks.screen_level = 1;
+    else if (k.kin_threshold - floor3 > 0.015f) ks.screen_level = 3;
+    else return launch_king_fp4(k, pl->map.num_blocks, pl->ctx, s, launches);
     return launch_king_screen(ks, pl->map.num_blocks, pl->ctx, s, launches);
   }
   if (variant == 4) return launch_king_fp4_pair(k, pl->map.num_blocks, pl->ctx, s, launches);
@@ -583,7 +590,18 @@ int stream_rows_device(ck_planes *pl, const uint64_t *d_rows, uint32_t s0, uint3
                                          "ck_king_stream_granularity()");
   const uint32_t block0 = s0 / kTileSamples, num_blocks = ceil_div(s1, kTileSamples) - block0;
   CK_CUDA(launch_import_ref_range(*pl, d_rows, s0, block0, num_blocks, s));
-  CK_CUDA(launch_finalize_codes_range(*pl, st->variant >= 3 ? 3 : st->variant, block0, num_blocks, s));
+  // variant 5: the first piece delivered (the last rows) stands for the cohort when the screen level is chosen - one small
+  // synchronisation per session, behind which the uploads of the next pieces are already running
+  const bool sample_stats = st->variant == 5 && s1 == n && ctx->screen_level == 0;
+  if (sample_stats) CK_CUDA(cudaMemsetAsync(pl->totals_sums(), 0, 2 * sizeof(unsigned long long), s));
+  CK_CUDA(launch_finalize_codes_range(*pl, st->variant >= 3 ? 3 : st->variant, block0, num_blocks, s, sample_stats));
+  if (s1 == n) pl->screen1_floor = -1.f;
+  if (sample_stats) {
+    unsigned long long sums[2] = {0, 0};
+    CK_CUDA(cudaMemcpyAsync(sums, pl->totals_sums(), sizeof(sums), cudaMemcpyDeviceToHost, s));
+    CK_CUDA(cudaStreamSynchronize(s));
+    pl->screen1_floor = screen1_floor_from_sums(sums, double(s1 - s0), double(pl->num_sites));
+  }
   ctx->timings.king_launches += 2;
   const uint32_t band_lo = s0 / kFp4BandRows, band_hi = ceil_div(std::min(s1, n), kFp4BandRows);
   st->k.codes = pl->codes;

@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
   if (tid == 0) {
     if (f0) p.tile_flags[blockIdx.x] = 1;
     if (wide && f1) p.tile_flags[blockIdx.x + band_rows] = 1;
+    if (f0 || (wide && f1)) atomicAdd(p.flagged_counter, (unsigned long long)((f0 ? 1 : 0) + ((wide && f1) ? 1 : 0)));
   }
   __syncwarp();
   if (warp == kSExpWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kSTmemCols));

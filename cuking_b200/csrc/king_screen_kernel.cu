@@ -376,7 +376,10 @@ __global__ void __launch_bounds__(kFThreads, 1) king_screen_kernel(const KingLau
     if (tid == 0) FPROF_ADD(14, FPROF_T() - t_main);
   }
   tcgen05_before_sync();
-  if (__syncthreads_or(any ? 1 : 0) && tid == 0) p.tile_flags[blockIdx.x] = 1;
+  if (__syncthreads_or(any ? 1 : 0) && tid == 0) {
+    p.tile_flags[blockIdx.x] = 1;
+    atomicAdd(p.flagged_counter, 1ull);
+  }
   __syncwarp();
   if (warp == kFExpWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kFTmemCols));
 }
@@ -426,6 +429,9 @@ cudaError_t launch_king_screen(const KingLaunch &k, uint32_t total_blocks, ck_ct
     part.tile_begin = t;
     part.tile_end = (t + kMaxGrid < k.tile_end) ? t + kMaxGrid : k.tile_end;
     part.tile_flags = ctx->tile_flags;
+    part.flagged_counter = ctx->d_screen_flagged;
+    ctx->screen_tiles += part.tile_end - part.tile_begin;
+    ctx->screen_level_used = part.screen_level == 1 ? 1 : 3;
     if ((e = cudaMemsetAsync(ctx->tile_flags, 0, size_t(part.tile_end - part.tile_begin), s)) != cudaSuccess) return e;
     e = part.screen_level == 1 ? launch_king_screen1(part, tiles, s) : launch_cfg<2, 8, 3>(part, tiles, s);
     if (launches) ++*launches;

@@ -404,18 +404,18 @@ cudaError_t launch_finalize(const ck_planes &pl, cudaStream_t s) {
 }
 
 cudaError_t launch_finalize_codes(const ck_planes &pl, int kind, cudaStream_t s) {
-  return launch_finalize_codes_range(pl, kind, 0, pl.map.num_blocks, s);
+  return launch_finalize_codes_range(pl, kind, 0, pl.map.num_blocks, s, /*add_to_sums=*/true);
 }
-cudaError_t launch_finalize_codes_range(const ck_planes &pl, int kind, uint32_t block0, uint32_t num_blocks, cudaStream_t s) {
+cudaError_t launch_finalize_codes_range(const ck_planes &pl, int kind, uint32_t block0, uint32_t num_blocks, cudaStream_t s, bool add_to_sums) {
   if (num_blocks == 0) return cudaSuccess;
   const size_t rows = size_t(num_blocks) * pl.words, row0 = size_t(block0) * pl.words;
   const uint32_t *raw = pl.raw + row0 * kRawPlanes * kTileSamples;
   uint4 *codes = reinterpret_cast<uint4 *>(pl.codes) + row0 * kTileSamples;
   if (kind == 3) {
     finalize_codes_kernel<true><<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(raw, codes, rows);
-    // the cohort-wide sums only make sense when everything is derived in one go (ensure_compute zeroes them)
+    // the sums over the slots are only wanted where the caller has zeroed them and knows which samples they cover
     sample_totals_kernel<<<num_blocks, 256, 0, s>>>(codes, pl.sample_totals() + size_t(block0) * kTileSamples,
-                                                    (block0 == 0 && num_blocks == pl.map.num_blocks) ? pl.totals_sums() : nullptr, pl.words);
+                                                    add_to_sums ? pl.totals_sums() : nullptr, pl.words);
   }
   else
     finalize_codes_kernel<false><<<grid_for(rows * kTileSamples, 256), 256, 0, s>>>(raw, codes, rows);

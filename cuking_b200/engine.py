@@ -107,6 +107,12 @@ class Context:
         check(self._lib.ck_ctx_fp4_selftest(self._h, C.byref(exact)))
         return bool(exact.value), (self._lib.ck_last_error() or b"").decode()
 
+    def screen_stats(self) -> dict:
+        """ck_ctx_screen_stats: tiles the variant-5 screens ran over / flagged since the ctx was created, and the last level."""
+        t, f, lv = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        check(self._lib.ck_ctx_screen_stats(self._h, C.byref(t), C.byref(f), C.byref(lv)))
+        return {"tiles_screened": int(t.value), "tiles_flagged": int(f.value), "level": int(lv.value)}
+
     def set_king_variant(self, variant: int) -> None:
         check(self._lib.ck_ctx_set_king_variant(self._h, variant))
 

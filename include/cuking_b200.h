@@ -123,8 +123,12 @@ int ck_ctx_set_stream(ck_ctx *ctx, void *cuda_stream);
  * 2 = tcgen05 int8 tensor-core formulation (five exact s32 GEMMs of indicator vectors), 3 = the same five GEMMs on
  * the FP4 tensor path (kind::mxf4 E2M1 operands, unit block scales, fp32 accumulation - exact for counts <= 2^23; planes
  * with more than 2^23 sites are routed to variant 2), 4 = variant 3 on CTA pairs (tcgen05 cta_group::2, 256-row tiles
- * sharing the B operand; experimental, slower today: profiles/r02_pair_kernel.md), -1 = library default (= 3; also
- * settable with the CUKING_KING_VARIANT environment variable).  Results are bit-identical across variants. */
+ * sharing the B operand; experimental, slower today: profiles/r02_pair_kernel.md), 5 = variant 3 behind a screen: a
+ * pair can only pass the threshold if a bound on its squared genotype distance - one or three exact products instead of
+ * five, chosen from the cohort's call rate - lies under a multiple of the samples' het counts, and only tiles holding
+ * such a pair go on to the five-product kernel (dense output, the count dump and thresholds too low for a
+ * screen to reject anything take variant 3 directly), -1 = library default (= 5; also settable with the
+ * CUKING_KING_VARIANT environment variable).  Results are bit-identical across variants. */
 int ck_ctx_set_king_variant(ck_ctx *ctx, int variant);
 /* Variant 3 relies on the tensor core adding E2M1 products into its fp32 accumulator without losing low bits, which the
  * PTX ISA does not spell out.  The first use of variant 3 on a ctx therefore runs an on-device self-test (about a
@@ -133,6 +137,10 @@ int ck_ctx_set_king_variant(ck_ctx *ctx, int variant);
  * accumulators, exact by specification) wherever variant 3 was asked for, and says so on stderr.  This call runs the
  * self-test now: *exact = 1 / 0, and ck_last_error() holds a one-line report. */
 int ck_ctx_fp4_selftest(ck_ctx *ctx, int *exact);
+/* Variant 5 bookkeeping since the ctx was created: tiles its screens were launched over, tiles they flagged (the ones the
+ * five-product kernel then ran on), and the screen of the last evaluation (1 = one product, 3 = three products, 0 = none:
+ * dense output, count dump, or a threshold too low for a screen).  Synchronises the ctx's stream. */
+int ck_ctx_screen_stats(ck_ctx *ctx, uint64_t *tiles_screened, uint64_t *tiles_flagged, int *level);
 int ck_ctx_synchronize(ck_ctx *ctx);
 int ck_ctx_get_timings(ck_ctx *ctx, ck_timings *out);
 /* Measures, on this GPU and now, the sustained issue rate of POPC.32 and LOP3 (lane-ops per second, whole chip).
@@ -294,8 +302,8 @@ typedef int (*ck_result_sink)(void *user, const ck_result *records, size_t count
 int ck_king_view_sink(ck_planes *planes, const ck_submatrix *view, uint32_t part_index, uint32_t num_parts, float kin_threshold,
                       uint32_t max_results, size_t chunk_records, ck_result_sink sink, void *user, uint64_t *num_results);
 
-/* The pairwise kernel variant that ck_king* will run on these planes (the ctx's variant, except that variant 3 falls
- * back to 2 beyond 2^23 sites or when the ctx's GPU failed the kind::mxf4 self-test). */
+/* The pairwise kernel variant that ck_king* will run on these planes (the ctx's variant, except that variants 3, 4 and 5
+ * fall back to 2 beyond 2^23 sites or when the ctx's GPU failed the kind::mxf4 self-test). */
 int ck_planes_king_variant(const ck_planes *pl, int *variant);
 /* Same, restricted to the linear range [tile_begin, tile_end) of the sub-matrix's tile grid (row-major over the tiles
  * that can contain an i < j pair; the tile shape belongs to the active kernel variant, so tile counts are only
