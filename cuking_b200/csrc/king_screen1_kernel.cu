@@ -15,8 +15,8 @@
 // With one 80-column accumulator per column tile there is TMEM for a 128 x 160 tile (two column tiles of the mxf4 kernel's
 // enumeration side by side: 0.44 instead of 0.63 bytes of genotype codes per pair from L2, which is what bounds the wider
 // kernels) and a 16-slot A ring.  Roles as in king_fp4_kernel.cu: warps 0-7 expand the row samples' x into TMEM, warps
-// 8-12 the column samples' x into shared memory (each thread two columns), one lane of warp 13 issues one N = 160 MMA per
-// 64-site step; all 16 warps screen the accumulators.  The CTA of an even column tile of a band takes its right-hand
+// 8-12 the column samples' x into shared memory (each thread two columns), one lane of warp 13 issues the N = 160 MMAs of a
+// four-step A stage behind one barrier wait; all 16 warps screen the accumulators.  The CTA of an even column tile of a band takes its right-hand
 // neighbour along (when that one is inside the launch range); a tile whose left-hand neighbour lies outside the range
 // runs alone.  Output: one flag byte per tile of the launch, as in king_screen_kernel.cu.
 #include <cuda_runtime.h>
@@ -34,7 +34,8 @@ namespace {
 constexpr uint32_t kSM = 128, kSN = 80;       // tile rows x columns of ONE column tile (the mxf4 kernel's tile)
 constexpr uint32_t kSWide = 2 * kSN;           // columns a CTA screens
 constexpr uint32_t kSSlots = 16;               // A ring in TMEM: one 64-site step (8 columns of x) per slot
-constexpr uint32_t kSAS = 2;                   // steps per A stage (one barrier pair per stage)
+constexpr uint32_t kSAS = 4;                   // steps per A stage: ONE barrier pair, wait and commit per stage - the issuing
+                                               // lane's loop (wait ~75 clk, MMA ~55, commit ~100) is what bounds a step otherwise
 constexpr uint32_t kSAStages = kSSlots / kSAS;
 constexpr uint32_t kSGroups = 2;               // groups of four A warps; group g fills the A stages with stage % 2 == g
 constexpr uint32_t kSBS = 8, kSNS = 3;         // steps per B stage, B stages
@@ -45,14 +46,14 @@ constexpr uint32_t kSStageBytes = (kSWide / 8) * kSSBO;  // 40 KB
 constexpr size_t kSSmem = size_t(kSNS) * kSStageBytes + 1024;
 constexpr uint32_t kSThreads = 512;
 constexpr uint32_t kSAWarps = 8, kSBWarps = (2 * kSN) / 32, kSExpWarps = kSAWarps + kSBWarps;  // 8 + 5
-constexpr uint32_t kSAPrefetchItems = 2;       // A register prefetch depth in items (stages) of the group
+constexpr uint32_t kSAPrefetchItems = 1;       // A register prefetch depth in items (stages) of the group
 constexpr uint32_t kSBPrefetch = 2;            // B register prefetch depth in sub-stages
 constexpr uint32_t kSColAcc = 0, kSColA = kSWide, kSColSF = kSColA + 8 * kSSlots;
 constexpr uint32_t kSTmemCols = 512;
 static_assert(kSColSF + 16 <= kSTmemCols, "TMEM budget");
 static_assert(kSM == kBandTileRows && kSN == kBandTileCols, "band enumeration tile shape");
 static_assert(kChunkWords % (2 * kSAS * kSGroups * kSAPrefetchItems) == 0 && kChunkWords % (2 * kSSub * kSBPrefetch) == 0 &&
-                  kChunkWords % (2 * kSBS) == 0, "loop unrolling");
+                  kChunkWords % (2 * kSBS) == 0 && kSBS % kSAS == 0, "loop unrolling");
 
 __host__ __device__ constexpr uint32_t make_idesc_mxf4(uint32_t M, uint32_t N) {  // see king_fp4_kernel.cu
   return (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
@@ -75,7 +76,7 @@ constexpr uint32_t kXMask = 0xAAAAAAAAu;  // x = z & mask: +1 hom-alt (0x2), -1 
 
 __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLaunch p, const BandTiles tiles) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_a[kSSlots], empty_a[kSAStages], full_b[kSNS], empty_b[kSNS], acc_bar;
+  __shared__ __align__(8) uint64_t full_a[kSAStages], empty_a[kSAStages], full_b[kSNS], empty_b[kSNS], acc_bar;
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -108,8 +109,8 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (uint32_t s = 0; s < kSSlots; ++s) mbar_init(&full_a[s], kSAWarps / kSGroups);  // the four warps of the filling group
-    for (uint32_t s = 0; s < kSAStages; ++s) mbar_init(&empty_a[s], 1);                // one commit of the issuer
+    for (uint32_t s = 0; s < kSAStages; ++s) mbar_init(&full_a[s], kSAWarps / kSGroups);  // the four warps of the filling group
+    for (uint32_t s = 0; s < kSAStages; ++s) mbar_init(&empty_a[s], 1);                  // one commit of the issuer
     for (uint32_t s = 0; s < kSNS; ++s) {
       mbar_init(&full_b[s], kSBWarps);
       mbar_init(&empty_b[s], 1);
@@ -167,14 +168,11 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
         __syncwarp();  // tcgen05.st is warp-collective; the polling loop may leave the lanes diverged
         tcgen05_after_sync();
 #pragma unroll
-        for (uint32_t a = 0; a < kSAS; ++a) {
-          const uint32_t aslot = astage * kSAS + a;
-          tmem_store8(ta + aslot * 8, x[a]);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tcgen05_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full_a[aslot]);
-        }
+        for (uint32_t a = 0; a < kSAS; ++a) tmem_store8(ta + (astage * kSAS + a) * 8, x[a]);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tcgen05_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[astage]);
       }
     }
   } else if (warp < kSExpWarps) {
@@ -240,14 +238,13 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
     for (uint32_t step = 0; step < num_steps; step += kSAS) {
       const uint32_t stage_no = step / kSAS, astage = stage_no % kSAStages, mb = step / kSBS, sb = mb % kSNS, qb = step % kSBS;
       if (qb == 0) mbar_wait_suspend(&full_b[sb], (mb / kSNS) & 1u);
+      mbar_wait_suspend(&full_a[astage], (stage_no / kSAStages) & 1u);
+      tcgen05_after_sync();
+      if (elected) {
 #pragma unroll
-      for (uint32_t a = 0; a < kSAS; ++a) {
-        const uint32_t aslot = astage * kSAS + a;
-        mbar_wait_suspend(&full_a[aslot], (stage_no / kSAStages) & 1u);
-        tcgen05_after_sync();
-        if (elected) {
+        for (uint32_t a = 0; a < kSAS; ++a) {
           const uint32_t b_bytes = sb * kSStageBytes + (qb + a) * 2 * kSLBO;
-          umma_mxf4_ts(d_addr, a_addr + aslot * 8, b_desc0 + uint64_t(b_bytes >> 4), idesc, sf_addr, (step + a) > 0 ? 1u : 0u);
+          umma_mxf4_ts(d_addr, a_addr + (astage * kSAS + a) * 8, b_desc0 + uint64_t(b_bytes >> 4), idesc, sf_addr, (step + a) > 0 ? 1u : 0u);
         }
       }
       if (elected) {

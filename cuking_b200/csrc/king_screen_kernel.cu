@@ -56,7 +56,7 @@ static_assert(kChunkWords % (2 * kFGroups * kFAPrefetchSteps) == 0 && kChunkWord
 
 template <uint32_t AS, uint32_t BS, uint32_t NS>
 struct Fp4Geo {
-  static_assert(BS % kFSub == 0 && BS % AS == 0 && kFSlots % AS == 0 && (AS == 1 || AS == 2), "stage geometry");
+  static_assert(BS % kFSub == 0 && BS % AS == 0 && kFSlots % AS == 0 && (AS == 1 || AS == 2 || AS == 4), "stage geometry");
   static constexpr uint32_t kAStages = kFSlots / AS;        // A stages in the TMEM ring
   static constexpr uint32_t kSBO = BS * 2 * kFLBO;          // a stage holds 32 K-bytes (64 sites) per step
   static constexpr uint32_t kTile = (kFN / 8) * kSBO;       // one B operand plane of one stage
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_screen_kernel(const KingLau
   using G = Fp4Geo<AS, BS, NS>;
   constexpr uint32_t kAStages = G::kAStages;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_a[kFSlots], empty_a[kFSlots], full_b[NS], empty_b[NS], acc_bar;
+  __shared__ __align__(8) uint64_t full_a[kFSlots], empty_a[kFSlots], full_b[NS], empty_b[NS], acc_bar;  // full_a: one per STAGE is used
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -132,8 +132,10 @@ __global__ void __launch_bounds__(kFThreads, 1) king_screen_kernel(const KingLau
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (uint32_t s = 0; s < kFSlots; ++s) mbar_init(&full_a[s], kFAWarps / kFGroups);  // per slot: the four warps of the filling group
-    for (uint32_t s = 0; s < kAStages; ++s) mbar_init(&empty_a[s], kFIssuers);             // per stage: one commit per issuer
+    // super-stage = kFGroups consecutive A stages (one per group): ONE full / empty barrier pair, so that an issuer pays one
+    // wait and one commit per kFGroups * AS steps
+    for (uint32_t s = 0; s < kAStages / kFGroups; ++s) mbar_init(&full_a[s], kFAWarps);  // all eight A warps
+    for (uint32_t s = 0; s < kAStages / kFGroups; ++s) mbar_init(&empty_a[s], kFIssuers);  // one commit per issuer
     for (uint32_t s = 0; s < NS; ++s) {
       mbar_init(&full_b[s], kFBWarps);
       mbar_init(&empty_b[s], kFIssuers);
@@ -205,7 +207,9 @@ __global__ void __launch_bounds__(kFThreads, 1) king_screen_kernel(const KingLau
         }
         load_item(n0 + u + kPrefetch, z[u]);  // refill the registers just consumed
         const unsigned long long p1 = FPROF_T();
-        if (stage_no >= kAStages) mbar_wait_suspend(&empty_a[astage], ((stage_no / kAStages) - 1) & 1u);  // previous readers done
+        constexpr uint32_t kSuper = kAStages / kFGroups;  // super-stages in the ring
+        const uint32_t super_no = n0 + u, ss = super_no % kSuper;
+        if (super_no >= kSuper) mbar_wait_suspend(&empty_a[ss], ((super_no / kSuper) - 1) & 1u);  // previous readers done
         __syncwarp();  // tcgen05.st is warp-collective; the polling loop may leave the lanes diverged
         const unsigned long long p2 = FPROF_T();
         tcgen05_after_sync();
@@ -217,11 +221,13 @@ __global__ void __launch_bounds__(kFThreads, 1) king_screen_kernel(const KingLau
           tmem_store8(ta + aslot * 24, x[a]);
           tmem_store8(ta + aslot * 24 + 8, y[a]);
           tmem_store8(ta + aslot * 24 + 16, h[a]);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tcgen05_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full_a[aslot]);
         }
+        // one announcement per stage: with an 8-slot ring the issuers need not start on a half-written stage, and their loop -
+        // a barrier wait, the MMAs, a commit - is what bounds a step (profiles/r02_screen_kernels.md)
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tcgen05_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[ss]);
         const unsigned long long p3 = FPROF_T();
         FPROF_ADD(0, p1 - p0);
         FPROF_ADD(1, p2 - p1);
@@ -297,26 +303,23 @@ __global__ void __launch_bounds__(kFThreads, 1) king_screen_kernel(const KingLau
     // B planes of a stage: x | y | w.  x.x reads x, y.w reads w, h.y reads y.
     const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem) + (which == 0 ? 0u : which == 1 ? 2u * G::kTile : G::kTile), kFLBO, G::kSBO);
     const uint32_t elected = elect_one();
-    for (uint32_t step = 0; step < num_steps; step += AS) {
-      const uint32_t stage_no = step / AS, astage = stage_no % kAStages, mb = step / BS, sb = mb % NS, q = step % BS;
+    constexpr uint32_t kSuperSteps = AS * kFGroups, kSuper = kAStages / kFGroups;
+    static_assert(BS % kSuperSteps == 0, "a super-stage must not straddle B stages");
+    for (uint32_t step = 0; step < num_steps; step += kSuperSteps) {
+      const uint32_t super_no = step / kSuperSteps, ss = super_no % kSuper, mb = step / BS, sb = mb % NS, q = step % BS;
       const unsigned long long q0 = FPROF_T();
       if (q == 0) mbar_wait_suspend(&full_b[sb], (mb / NS) & 1u);
-      unsigned long long waited = FPROF_T() - q0;
-#pragma unroll
-      for (uint32_t a = 0; a < AS; ++a) {
-        const uint32_t aslot = astage * AS + a;
-        const unsigned long long w0 = FPROF_T();
-        mbar_wait_suspend(&full_a[aslot], (stage_no / kAStages) & 1u);
-        waited += FPROF_T() - w0;
-        tcgen05_after_sync();
-        if (elected) {
-          const uint32_t b_bytes = sb * G::kStageBytes + (q + a) * 2 * kFLBO;
-          umma_mxf4_ts(d_addr, a_addr + aslot * 24, b_desc0 + uint64_t(b_bytes >> 4), idesc, sf_addr, (step + a) > 0 ? 1u : 0u);
-        }
-      }
+      mbar_wait_suspend(&full_a[ss], (super_no / kSuper) & 1u);
+      const unsigned long long waited = FPROF_T() - q0;
+      tcgen05_after_sync();
       if (elected) {
-        umma_commit_arrive(&empty_a[astage]);                       // arrives when this thread's MMAs so far have completed
-        if (q + AS == BS) umma_commit_arrive(&empty_b[sb]);         // last steps of the B stage
+#pragma unroll
+        for (uint32_t a = 0; a < kSuperSteps; ++a) {  // slot of step (step + a) = ss * kSuperSteps + a: group a / AS, its step a % AS
+          const uint32_t b_bytes = sb * G::kStageBytes + (q + a) * 2 * kFLBO;
+          umma_mxf4_ts(d_addr, a_addr + (ss * kSuperSteps + a) * 24, b_desc0 + uint64_t(b_bytes >> 4), idesc, sf_addr, (step + a) > 0 ? 1u : 0u);
+        }
+        umma_commit_arrive(&empty_a[ss]);                            // arrives when this thread's MMAs so far have completed
+        if (q + kSuperSteps == BS) umma_commit_arrive(&empty_b[sb]);  // last steps of the B stage
       }
       __syncwarp();
       const unsigned long long q1 = FPROF_T();
