@@ -12,13 +12,13 @@
 // dispatch (king_screen_kernel.cu: launch_king_screen) uses this level when the cohort's call rate predicts that
 // unrelated pairs stay clear of the threshold, the three-product screen otherwise.
 //
-// With one 80-column accumulator per column tile there is TMEM for a 128 x 160 tile (two column tiles of the mxf4 kernel's
-// enumeration side by side: 0.44 instead of 0.63 bytes of genotype codes per pair from L2, which is what bounds the wider
+// With one 80-column accumulator per column tile there is TMEM for a 128 x 320 tile (four column tiles of the mxf4 kernel's
+// enumeration side by side: 0.34 instead of 0.63 bytes of genotype codes per pair from L2, which is what bounds these
 // kernels) and a 16-slot A ring.  Roles as in king_fp4_kernel.cu: warps 0-7 expand the row samples' x into TMEM, warps
-// 8-12 the column samples' x into shared memory (each thread two columns), one lane of warp 13 issues the N = 160 MMAs of a
-// four-step A stage behind one barrier wait; all 16 warps screen the accumulators.  The CTA of an even column tile of a band takes its right-hand
-// neighbour along (when that one is inside the launch range); a tile whose left-hand neighbour lies outside the range
-// runs alone.  Output: one flag byte per tile of the launch, as in king_screen_kernel.cu.
+// 8-12 the column samples' x into shared memory (each thread four columns), one lane each of warps 13 and 14 issues the N = 160
+// MMAs of two column tiles for a four-step A stage behind one barrier wait; all 16 warps screen the accumulators.  The CTA of
+// the first column tile of a group of four takes the following ones along (as far as they are inside the launch range); a
+// tile whose left-hand neighbour lies outside the range leads the rest of its group.  Output: one flag byte per tile of the launch, as in king_screen_kernel.cu.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -32,20 +32,22 @@ namespace ck {
 namespace {
 
 constexpr uint32_t kSM = 128, kSN = 80;       // tile rows x columns of ONE column tile (the mxf4 kernel's tile)
-constexpr uint32_t kSWide = 2 * kSN;           // columns a CTA screens
+constexpr uint32_t kSTiles = 4;                // column tiles a CTA screens side by side
+constexpr uint32_t kSWide = kSTiles * kSN;     // 320 columns
 constexpr uint32_t kSSlots = 16;               // A ring in TMEM: one 64-site step (8 columns of x) per slot
 constexpr uint32_t kSAS = 4;                   // steps per A stage: ONE barrier pair, wait and commit per stage - the issuing
                                                // lane's loop (wait ~75 clk, MMA ~55, commit ~100) is what bounds a step otherwise
 constexpr uint32_t kSAStages = kSSlots / kSAS;
 constexpr uint32_t kSGroups = 2;               // groups of four A warps; group g fills the A stages with stage % 2 == g
-constexpr uint32_t kSBS = 8, kSNS = 3;         // steps per B stage, B stages
-constexpr uint32_t kSSub = 4;                  // B expanders work in sub-stages of 4 steps
+constexpr uint32_t kSBS = 8, kSNS = 2;         // steps per B stage, B stages
+constexpr uint32_t kSSub = 2;                  // B expanders work in sub-stages of 2 steps (register prefetch unit)
 constexpr uint32_t kSLBO = 128;                // bytes between K-adjacent 8x16-byte core matrices
 constexpr uint32_t kSSBO = kSBS * 2 * kSLBO;   // bytes between 8-row groups: a stage holds 32 K-bytes (64 sites) per step
-constexpr uint32_t kSStageBytes = (kSWide / 8) * kSSBO;  // 40 KB
+constexpr uint32_t kSStageBytes = (kSWide / 8) * kSSBO;  // 80 KB
 constexpr size_t kSSmem = size_t(kSNS) * kSStageBytes + 1024;
 constexpr uint32_t kSThreads = 512;
 constexpr uint32_t kSAWarps = 8, kSBWarps = (2 * kSN) / 32, kSExpWarps = kSAWarps + kSBWarps;  // 8 + 5
+constexpr uint32_t kSIssuers = 2;              // warps 13, 14: column tiles {0, 1} and {2, 3} (N = 160 each, own accumulator columns)
 constexpr uint32_t kSAPrefetchItems = 1;       // A register prefetch depth in items (stages) of the group
 constexpr uint32_t kSBPrefetch = 2;            // B register prefetch depth in sub-stages
 constexpr uint32_t kSColAcc = 0, kSColA = kSWide, kSColSF = kSColA + 8 * kSSlots;
@@ -53,7 +55,7 @@ constexpr uint32_t kSTmemCols = 512;
 static_assert(kSColSF + 16 <= kSTmemCols, "TMEM budget");
 static_assert(kSM == kBandTileRows && kSN == kBandTileCols, "band enumeration tile shape");
 static_assert(kChunkWords % (2 * kSAS * kSGroups * kSAPrefetchItems) == 0 && kChunkWords % (2 * kSSub * kSBPrefetch) == 0 &&
-                  kChunkWords % (2 * kSBS) == 0 && kSBS % kSAS == 0, "loop unrolling");
+                  kChunkWords % (2 * kSBS) == 0 && kSBS % kSAS == 0 && kSBS % kSSub == 0 && kSTiles == 2 * kSIssuers, "loop unrolling");
 
 __host__ __device__ constexpr uint32_t make_idesc_mxf4(uint32_t M, uint32_t N) {  // see king_fp4_kernel.cu
   return (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
@@ -95,11 +97,16 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
   const uint32_t q = uint32_t(t - tiles.band_prefix[band]);
   const uint32_t ti = band * kBandRowTiles + q % band_rows, col_rel = q / band_rows;
   const uint32_t tj = tiles.band_first_col[band] + col_rel;
-  if ((col_rel & 1u) && t - band_rows >= p.tile_begin) return;  // screened by the CTA of the tile to the left
-  const bool wide = !(col_rel & 1u) && tj + 1 < tiles.num_col_tiles && t + band_rows < p.tile_end;
+  // Groups of kSTiles adjacent column tiles of a band: the first member that lies inside the launch range leads (it is
+  // member 0, or its left neighbour is outside the range) and takes the following members along as far as they exist and lie
+  // inside the range; everybody else returns.
+  const uint32_t member = col_rel % kSTiles;
+  if (member != 0 && t - band_rows >= p.tile_begin) return;
+  uint32_t ntiles = 1;
+  while (member + ntiles < kSTiles && tj + ntiles < tiles.num_col_tiles && t + (unsigned long long)ntiles * band_rows < p.tile_end) ++ntiles;
   const uint32_t row0 = ti * kSM, col0 = tj * kSN;  // offsets inside the sub-matrix
   if (row0 >= p.num_rows) return;  // phantom row tile that pads an odd last band
-  const uint32_t rows_here = min(kSM, p.num_rows - row0), cols_here = min(wide ? kSWide : kSN, p.num_cols - col0);
+  const uint32_t rows_here = min(kSM, p.num_rows - row0), cols_here = min(ntiles * kSN, p.num_cols - col0);
   const uint32_t i0 = p.row_global0 + row0, j0 = p.col_global0 + col0;
   if (j0 + cols_here - 1 <= i0) return;  // no i < j pair in these tiles: their flags stay 0
 
@@ -110,12 +117,12 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
   }
   if (tid == 0) {
     for (uint32_t s = 0; s < kSAStages; ++s) mbar_init(&full_a[s], kSAWarps / kSGroups);  // the four warps of the filling group
-    for (uint32_t s = 0; s < kSAStages; ++s) mbar_init(&empty_a[s], 1);                  // one commit of the issuer
+    for (uint32_t s = 0; s < kSAStages; ++s) mbar_init(&empty_a[s], kSIssuers);          // one commit per issuer
     for (uint32_t s = 0; s < kSNS; ++s) {
       mbar_init(&full_b[s], kSBWarps);
-      mbar_init(&empty_b[s], 1);
+      mbar_init(&empty_b[s], kSIssuers);
     }
-    mbar_init(&acc_bar, 1);
+    mbar_init(&acc_bar, kSIssuers);
     mbar_fence_init();
   }
   tcgen05_before_sync();
@@ -176,28 +183,28 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
       }
     }
   } else if (warp < kSExpWarps) {
-    // ===== B expanders: two threads per column pair (srow, srow + 80), 32 sites of every step each, kSBS steps per stage =====
+    // ===== B expanders: two threads per column quadruple (srow + 80 c), 32 sites of every step each, kSBS steps per stage =====
     const uint32_t idx = tid - kSAWarps * 32;
     const uint32_t half = idx / kSN, srow = idx % kSN;  // half: K bytes 16*half .. 16*half+15 of every step
-    const uint4 *src[2];
-    uint32_t b_off[2];
+    const uint4 *codes4 = reinterpret_cast<const uint4 *>(p.codes);
+    uint32_t src[kSTiles];  // element offsets into codes4 (the buffer holds far fewer than 2^32 uint4)
 #pragma unroll
-    for (uint32_t c = 0; c < 2; ++c) {
+    for (uint32_t c = 0; c < kSTiles; ++c) {
       const uint32_t col = srow + c * kSN;
       const uint32_t slot = p.col_slot0 + col0 + (col < cols_here ? col : 0u);  // columns beyond the edge re-read the first one
       const uint32_t blk = slot / kTileSamples, ln = slot % kTileSamples;
-      src[c] = reinterpret_cast<const uint4 *>(p.codes) + (size_t(blk) * p.words + half) * kTileSamples + ln;
-      b_off[c] = (col >> 3) * kSSBO + (col & 7) * 16 + half * kSLBO;
+      src[c] = (blk * p.words + half) * kTileSamples + ln;
     }
+    const uint32_t b_off0 = (srow >> 3) * kSSBO + (srow & 7) * 16 + half * kSLBO;  // column srow + 80 c: + c * (80 / 8) * kSSBO
     const uint32_t num_subs = num_steps / kSSub;
     const uint32_t smem_base = smem_u32(smem);
     constexpr uint32_t kSubsPerStage = kSBS / kSSub;
-    uint4 z[kSBPrefetch][2][kSSub];
-    auto load_sub = [&](uint32_t m, uint4 (&dst)[2][kSSub]) {
+    uint4 z[kSBPrefetch][kSTiles][kSSub];
+    auto load_sub = [&](uint32_t m, uint4 (&dst)[kSTiles][kSSub]) {
 #pragma unroll
-      for (uint32_t c = 0; c < 2; ++c)
+      for (uint32_t c = 0; c < kSTiles; ++c)
 #pragma unroll
-        for (uint32_t k = 0; k < kSSub; ++k) dst[c][k] = __ldg(src[c] + size_t(min(m, num_subs - 1) * kSSub + k) * (2 * kTileSamples));
+        for (uint32_t k = 0; k < kSSub; ++k) dst[c][k] = __ldg(codes4 + src[c] + size_t(min(m, num_subs - 1) * kSSub + k) * (2 * kTileSamples));
     };
 #pragma unroll
     for (uint32_t u = 0; u < kSBPrefetch; ++u) load_sub(u, z[u]);
@@ -207,21 +214,14 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
         const uint32_t m = m0 + u;
         const uint32_t st = m / kSubsPerStage, sub = m % kSubsPerStage;  // stage counter, sub-stage inside it
         const uint32_t s = st % kSNS, fill = st / kSNS;
-        uint32_t x[2][kSSub][4];
-#pragma unroll
-        for (uint32_t c = 0; c < 2; ++c)
-#pragma unroll
-          for (uint32_t k = 0; k < kSSub; ++k) {
-            x[c][k][0] = z[u][c][k].x & kXMask; x[c][k][1] = z[u][c][k].y & kXMask;
-            x[c][k][2] = z[u][c][k].z & kXMask; x[c][k][3] = z[u][c][k].w & kXMask;
-          }
-        load_sub(m + kSBPrefetch, z[u]);
         if (sub == 0 && fill > 0) mbar_wait_suspend(&empty_b[s], (fill - 1) & 1u);  // the MMAs that read this stage have completed
         const uint32_t stage = smem_base + s * kSStageBytes + sub * kSSub * 2 * kSLBO;
 #pragma unroll
-        for (uint32_t c = 0; c < 2; ++c)
+        for (uint32_t c = 0; c < kSTiles; ++c)
 #pragma unroll
-          for (uint32_t k = 0; k < kSSub; ++k) sts128(stage + b_off[c] + k * 2 * kSLBO, x[c][k][0], x[c][k][1], x[c][k][2], x[c][k][3]);
+          for (uint32_t k = 0; k < kSSub; ++k)
+            sts128(stage + b_off0 + c * (kSN / 8) * kSSBO + k * 2 * kSLBO, z[u][c][k].x & kXMask, z[u][c][k].y & kXMask, z[u][c][k].z & kXMask, z[u][c][k].w & kXMask);
+        load_sub(m + kSBPrefetch, z[u]);  // refill the registers just consumed
         if (sub == kSubsPerStage - 1) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (tensor core)
           __syncwarp();
@@ -229,11 +229,15 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
         }
       }
     }
-  } else if (warp == kSExpWarps) {
-    // ===== MMA issuer: one N = 160 (or 80 for a lone tile) MMA per step; the whole warp runs the loop, one lane issues =====
-    const uint32_t idesc = wide ? make_idesc_mxf4(kSM, kSWide) : make_idesc_mxf4(kSM, kSN);
-    const uint32_t d_addr = tmem_base + kSColAcc, a_addr = tmem_base + kSColA, sf_addr = tmem_base + kSColSF;
-    const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem), kSLBO, kSSBO);
+  } else if (warp < kSExpWarps + kSIssuers) {
+    // ===== MMA issuers: warp 13 the column tiles 0 and 1, warp 14 the tiles 2 and 3 - one N = 160 (80 where only one of the two
+    // exists) MMA per step each, into their own accumulator columns; the whole warp runs the loop, one lane issues.  An issuer
+    // without tiles keeps step with the barriers (its commits complete at once) so that the phase counts stay aligned.
+    const uint32_t which = warp - kSExpWarps;
+    const uint32_t my_tiles = ntiles > 2 * which ? min(2u, ntiles - 2 * which) : 0u;
+    const uint32_t idesc = make_idesc_mxf4(kSM, my_tiles == 2 ? 2 * kSN : kSN);
+    const uint32_t d_addr = tmem_base + kSColAcc + which * 2 * kSN, a_addr = tmem_base + kSColA, sf_addr = tmem_base + kSColSF;
+    const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem) + which * (2 * kSN / 8) * kSSBO, kSLBO, kSSBO);
     const uint32_t elected = elect_one();
     for (uint32_t step = 0; step < num_steps; step += kSAS) {
       const uint32_t stage_no = step / kSAS, astage = stage_no % kSAStages, mb = step / kSBS, sb = mb % kSNS, qb = step % kSBS;
@@ -241,23 +245,23 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
       mbar_wait_suspend(&full_a[astage], (stage_no / kSAStages) & 1u);
       tcgen05_after_sync();
       if (elected) {
+        if (my_tiles != 0) {
 #pragma unroll
-        for (uint32_t a = 0; a < kSAS; ++a) {
-          const uint32_t b_bytes = sb * kSStageBytes + (qb + a) * 2 * kSLBO;
-          umma_mxf4_ts(d_addr, a_addr + (astage * kSAS + a) * 8, b_desc0 + uint64_t(b_bytes >> 4), idesc, sf_addr, (step + a) > 0 ? 1u : 0u);
+          for (uint32_t a = 0; a < kSAS; ++a) {
+            const uint32_t b_bytes = sb * kSStageBytes + (qb + a) * 2 * kSLBO;
+            umma_mxf4_ts(d_addr, a_addr + (astage * kSAS + a) * 8, b_desc0 + uint64_t(b_bytes >> 4), idesc, sf_addr, (step + a) > 0 ? 1u : 0u);
+          }
         }
-      }
-      if (elected) {
-        umma_commit_arrive(&empty_a[astage]);                 // arrives when this thread's MMAs so far have completed
+        umma_commit_arrive(&empty_a[astage]);                     // arrives when this thread's MMAs so far have completed
         if (qb + kSAS == kSBS) umma_commit_arrive(&empty_b[sb]);  // last steps of the B stage
       }
       __syncwarp();
     }
-    if (elected) umma_commit_arrive(&acc_bar);  // the accumulator is final
+    if (elected) umma_commit_arrive(&acc_bar);  // this issuer's accumulator columns are final
   }
 
   // ===== epilogue: all 16 warps; thread = row (TMEM lane quadrant warp % 4), 20 columns of each column tile per warp group =====
-  bool any0 = false, any1 = false;
+  uint32_t any_mask = 0;  // bit k: column tile k holds a candidate seen by this thread
   {
     __syncwarp();
     mbar_wait_suspend(&acc_bar, 0);
@@ -282,9 +286,7 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
     };
     constexpr uint32_t kColsPerGroup = kSN / 4;  // 20
     const uint32_t c0 = group * kColsPerGroup;
-#pragma unroll
-    for (uint32_t tile = 0; tile < 2; ++tile) {
-      if (tile == 1 && !wide) break;
+    for (uint32_t tile = 0; tile < ntiles; ++tile) {  // ntiles is uniform over the CTA
       const uint32_t cb = tile * kSN + c0;
       bool any = false;
       {
@@ -301,15 +303,18 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
 #pragma unroll
         for (uint32_t k = 0; k < 4; ++k) any = screen(cb + 16 + k, xx[k]) || any;
       }
-      if (tile == 0) any0 = any; else any1 = any;
+      if (any) any_mask |= 1u << tile;
     }
   }
   tcgen05_before_sync();
-  const int f0 = __syncthreads_or(any0 ? 1 : 0), f1 = __syncthreads_or(any1 ? 1 : 0);  // one round per column tile
-  if (tid == 0) {
-    if (f0) p.tile_flags[blockIdx.x] = 1;
-    if (wide && f1) p.tile_flags[blockIdx.x + band_rows] = 1;
-    if (f0 || (wide && f1)) atomicAdd(p.flagged_counter, (unsigned long long)((f0 ? 1 : 0) + ((wide && f1) ? 1 : 0)));
+  uint32_t flagged = 0;
+#pragma unroll
+  for (uint32_t tile = 0; tile < kSTiles; ++tile)  // one round per column tile (every thread takes part in every round)
+    if (__syncthreads_or(int((any_mask >> tile) & 1u))) flagged |= 1u << tile;
+  if (tid == 0 && flagged != 0) {
+    for (uint32_t tile = 0; tile < ntiles; ++tile)
+      if ((flagged >> tile) & 1u) p.tile_flags[blockIdx.x + size_t(tile) * band_rows] = 1;
+    atomicAdd(p.flagged_counter, (unsigned long long)__popc(flagged));
   }
   __syncwarp();
   if (warp == kSExpWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kSTmemCols));
