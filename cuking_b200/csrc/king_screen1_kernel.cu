@@ -75,6 +75,11 @@ __device__ __forceinline__ void pin8(const uint32_t (&v)[8]) {  // see king_fp4_
   asm volatile("" ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
 }
 constexpr uint32_t kXMask = 0xAAAAAAAAu;  // x = z & mask: +1 hom-alt (0x2), -1 hom-ref (0xA)
+// The register prefetch covers ~4 steps; a quarter of the loads miss L2 (the band's working set is larger than L2) and then
+// take longer than that: ncu shows the B warps parked on the long scoreboard.  An L2 prefetch kPrefetchSteps ahead costs no
+// register and turns those misses into hits (DRAM runs at 15 % of its bandwidth).
+constexpr uint32_t kL2PrefetchSteps = 24;
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLaunch p, const BandTiles tiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -152,9 +157,14 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
       n = min(n, num_items - 1);  // the prefetch beyond the last item re-reads it
 #pragma unroll
       for (uint32_t a = 0; a < kSAS; ++a) {
-        const uint4 *s0 = src + size_t((n * kSGroups + group) * kSAS + a) * (2 * kTileSamples);
+        const uint32_t step = (n * kSGroups + group) * kSAS + a;
+        const uint4 *s0 = src + size_t(step) * (2 * kTileSamples);
         dst[a][0] = __ldg(s0);
         dst[a][1] = __ldg(s0 + kTileSamples);
+        if (step + kL2PrefetchSteps < num_steps) {
+          prefetch_l2(s0 + size_t(kL2PrefetchSteps) * (2 * kTileSamples));
+          prefetch_l2(s0 + size_t(kL2PrefetchSteps) * (2 * kTileSamples) + kTileSamples);
+        }
       }
     };
 #pragma unroll
@@ -204,7 +214,12 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
 #pragma unroll
       for (uint32_t c = 0; c < kSTiles; ++c)
 #pragma unroll
-        for (uint32_t k = 0; k < kSSub; ++k) dst[c][k] = __ldg(codes4 + src[c] + size_t(min(m, num_subs - 1) * kSSub + k) * (2 * kTileSamples));
+        for (uint32_t k = 0; k < kSSub; ++k) {
+          const uint32_t step = min(m, num_subs - 1) * kSSub + k;
+          const uint4 *s0 = codes4 + src[c] + size_t(step) * (2 * kTileSamples);
+          dst[c][k] = __ldg(s0);
+          if (step + kL2PrefetchSteps < num_steps) prefetch_l2(s0 + size_t(kL2PrefetchSteps) * (2 * kTileSamples));
+        }
     };
 #pragma unroll
     for (uint32_t u = 0; u < kSBPrefetch; ++u) load_sub(u, z[u]);
