@@ -109,11 +109,6 @@ __device__ unsigned long long g_fp4_prof[16];
 __device__ __forceinline__ void pin8(const uint32_t (&v)[8]) {
   asm volatile("" ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
 }
-// L2 prefetch kL2PrefetchSteps ahead of the register prefetch: the band's working set exceeds L2, about a quarter of the
-// operand loads miss it, and the expander warps then sit on the long scoreboard (ncu source view, profiles/r02_screen_kernels.md);
-// the prefetch costs no register and DRAM has bandwidth to spare.
-constexpr uint32_t kL2PrefetchSteps = 24;
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void expand_fp4(uint32_t z, uint32_t &x, uint32_t &y, uint32_t &h) {
   x = z & 0xAAAAAAAAu;  // +1 hom-alt (0x2), -1 hom-ref (0xA)
   y = z & 0x22222222u;  // 1 hom
@@ -190,14 +185,9 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
       n = min(n, num_items - 1);  // the prefetch beyond the last item re-reads it
 #pragma unroll
       for (uint32_t a = 0; a < AS; ++a) {
-        const uint32_t step = (n * kFGroups + group) * AS + a;
-        const uint4 *s0 = src + size_t(step) * (2 * kTileSamples);
+        const uint4 *s0 = src + size_t((n * kFGroups + group) * AS + a) * (2 * kTileSamples);
         dst[a][0] = __ldg(s0);
         dst[a][1] = __ldg(s0 + kTileSamples);
-        if (step + kL2PrefetchSteps < num_steps) {
-          prefetch_l2(s0 + size_t(kL2PrefetchSteps) * (2 * kTileSamples));
-          prefetch_l2(s0 + size_t(kL2PrefetchSteps) * (2 * kTileSamples) + kTileSamples);
-        }
       }
     };
 #pragma unroll
@@ -262,12 +252,7 @@ __global__ void __launch_bounds__(kFThreads, 1) king_fp4_kernel(const KingLaunch
     uint4 z[kFBPrefetch][kFSub];
     auto load_sub = [&](uint32_t m, uint4 (&dst)[kFSub]) {
 #pragma unroll
-      for (uint32_t q = 0; q < kFSub; ++q) {
-        const uint32_t step = min(m, num_subs - 1) * kFSub + q;
-        const uint4 *s0 = src + size_t(step) * (2 * kTileSamples);
-        dst[q] = __ldg(s0);
-        if (step + kL2PrefetchSteps < num_steps) prefetch_l2(s0 + size_t(kL2PrefetchSteps) * (2 * kTileSamples));
-      }
+      for (uint32_t q = 0; q < kFSub; ++q) dst[q] = __ldg(src + size_t(min(m, num_subs - 1) * kFSub + q) * (2 * kTileSamples));
     };
 #pragma unroll
     for (uint32_t u = 0; u < kFBPrefetch; ++u) load_sub(u, z[u]);
