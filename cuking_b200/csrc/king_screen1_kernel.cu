@@ -78,7 +78,12 @@ constexpr uint32_t kXMask = 0xAAAAAAAAu;  // x = z & mask: +1 hom-alt (0x2), -1 
 // The register prefetch covers ~4 steps; a quarter of the loads miss L2 (the band's working set is larger than L2) and then
 // take longer than that: ncu shows the B warps parked on the long scoreboard.  An L2 prefetch kPrefetchSteps ahead costs no
 // register and turns those misses into hits (DRAM runs at 15 % of its bandwidth).
-constexpr uint32_t kL2PrefetchSteps = 24;
+#ifndef CK_S1_PF_STEPS  // tuning: -DCK_S1_PF_STEPS=n -DCK_S1_PF_A=0/1 (profiles/r02_screen_kernels.md)
+#define CK_S1_PF_STEPS 24
+#define CK_S1_PF_A 0
+#endif
+constexpr uint32_t kL2PrefetchSteps = CK_S1_PF_STEPS;
+constexpr bool kL2PrefetchA = CK_S1_PF_A != 0;  // the row operand too: measured slower (281 vs 272 ms on cfg2; its expanders have slack and the board is at its power cap)
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLaunch p, const BandTiles tiles) {
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(kSThreads, 1) king_screen1_kernel(const KingLa
         const uint4 *s0 = src + size_t(step) * (2 * kTileSamples);
         dst[a][0] = __ldg(s0);
         dst[a][1] = __ldg(s0 + kTileSamples);
-        if (step + kL2PrefetchSteps < num_steps) {
+        if (kL2PrefetchA && step + kL2PrefetchSteps < num_steps) {
           prefetch_l2(s0 + size_t(kL2PrefetchSteps) * (2 * kTileSamples));
           prefetch_l2(s0 + size_t(kL2PrefetchSteps) * (2 * kTileSamples) + kTileSamples);
         }
