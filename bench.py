@@ -664,6 +664,9 @@ class Bench:
         # DRAM bytes of one king_fp4_kernel launch on the single-GPU cfg2 shape, from the committed ncu --set full capture
         traffic = None
         traffic_from = None
+        if variant == 5 and w["name"] == "cfg2" and self.n_gpus == 1 and (w.get("screen") or {}).get("level") == 1:
+            traffic, traffic_from = 392.85e9, ("profiles/r02_screen1_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                                               "of king_screen1_kernel on this launch shape; not re-measured by this run)")
         if variant == 3 and w["name"] == "cfg2" and self.n_gpus == 1:
             traffic, traffic_from = 425.21e9, ("profiles/r01_king_fp4_cfg2_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum of one "
                                                "ncu --set full capture of this launch shape; not re-measured by this run)")
