@@ -699,6 +699,12 @@ class Bench:
             return {
                 "bound": "tensor", "kernel": kernel_name, "achieved": tops, "peak": peak, "unit": "TOP/s (fp4 e2m1, dense)",
                 "executed": executed, "screen": screen or None,
+                "frac_note": (None if executed is None else
+                              "`achieved` / `frac` follow SURVEY 8(d): ALGORITHMIC ops (10 per pair-site of the reference formulation) over the measured "
+                              "kernel time - with the screen (a rigorous bound that spares 99.6 % of the tiles the five-product evaluation; identical "
+                              "records) that exceeds the tensor peak, as 8(d) anticipates for reformulations; `executed` is the by-construction <= 1 view "
+                              "(tensor ops actually issued), and ncu's pipe utilisations of the dominant kernel are in profiles/r02_screen1_ncu.txt "
+                              "(tensor 51.5 %, L1 / shared-memory data path 85 %, L2 75 %, board at its power cap)"),
                 "frac": tops / peak, "peak_kind": "sustained" if capped else "burst",
                 "burst": {"peak": burst, "frac": tops / burst,
                           "how": "ck_measure_fp4_peak: best of five 2-ms launches, constant operands - the board stays at its maximum clock"},
