@@ -323,7 +323,12 @@ Status Run(const Flags &flags) {
     auto acquire_slice = [&]() -> uint8_t * {
       std::unique_lock<std::mutex> l(q_mu);
       q_slices.wait(l, [&] { return failed || !free_slices.empty() || (slices_made == num_slices && all_slices.empty()); });
-      if (failed || free_slices.empty()) return nullptr;
+      if (!failed && free_slices.empty()) {  // not one slice could be page-locked
+        l.unlock();
+        fail_with(ResourceExhausted("Cannot allocate pinned host memory for the decode windows"));
+        return nullptr;
+      }
+      if (failed) return nullptr;
       uint8_t *p = free_slices.back();
       free_slices.pop_back();
       return p;
