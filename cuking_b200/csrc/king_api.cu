@@ -120,13 +120,15 @@ cudaError_t dispatch_king(int variant, const ck_planes *pl, const KingLaunch &k,
     // CUKING_SCREEN_LEVEL = 1 / 3 (read when the ctx is created) forces a screen.
     KingLaunch ks = k;
     const float floor1 = pl->screen1_floor, floor3 = floor1 >= 0.f ? 0.5f * floor1 : 0.015f;
-    if (pl->ctx->screen_level != 0) ks.screen_level = pl->ctx->screen_level;
-    else if (floor1 >= 0.f && k.kin_threshold - floor1 > 0.02f) ks.screen_level = 1;
+    int level = 0;  // 0 = no screen
+    if (pl->ctx->screen_level != 0) level = pl->ctx->screen_level;
+    else if (floor1 >= 0.f && k.kin_threshold - floor1 > 0.02f) level = 1;
+    else if (k.kin_threshold - floor3 > 0.015f) level = 3;
     // king_screen1_kernel indexes the codes with 32-bit element offsets (registers): cohorts beyond 2^32 uint4 of codes (64 GiB)
     // take the three-product screen
-    if (ks.screen_level == 1 && pl->codes_words() / 4 >= (size_t(1) << 32)) ks.screen_level = 3;
-    else if (k.kin_threshold - floor3 > 0.015f) ks.screen_level = 3;
-    else return launch_king_fp4(k, pl->map.num_blocks, pl->ctx, s, launches);
+    if (level == 1 && pl->codes_words() / 4 >= (size_t(1) << 32)) level = 3;
+    if (level == 0) return launch_king_fp4(k, pl->map.num_blocks, pl->ctx, s, launches);
+    ks.screen_level = level;
     return launch_king_screen(ks, pl->map.num_blocks, pl->ctx, s, launches);
   }
   if (variant == 4) return launch_king_fp4_pair(k, pl->map.num_blocks, pl->ctx, s, launches);
