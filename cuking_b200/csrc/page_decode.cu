@@ -238,13 +238,15 @@ int ck_pack_encoded(ck_planes *pl, const ck_encoded_column cols[3], uint32_t num
       aligned = aligned && a % p.align == 0;
     }
   }
-  lo &= ~uintptr_t(15);
+  // the span starts at the first byte of the lowest piece (never before it: that memory is not the caller's); the device copy
+  // keeps the span's offset inside a 16-byte unit, so every piece keeps the alignment it has on the host
+  const size_t skew = size_t(lo & 15);
   const bool one_copy = aligned && hi - lo <= sum + 4096;
   size_t off[3][3], total = 0;
   if (one_copy) {
-    total = align16(hi - lo) + 16;
+    total = align16(skew + (hi - lo)) + 16;
     for (int c = 0; c < 3; ++c)
-      for (int k = 0; k < 3; ++k) off[c][k] = pieces[c][k].bytes ? reinterpret_cast<uintptr_t>(pieces[c][k].host) - lo : 0;
+      for (int k = 0; k < 3; ++k) off[c][k] = pieces[c][k].bytes ? skew + (reinterpret_cast<uintptr_t>(pieces[c][k].host) - lo) : 0;
   } else {
     for (int c = 0; c < 3; ++c) {
       off[c][0] = total;
@@ -272,7 +274,7 @@ int ck_pack_encoded(ck_planes *pl, const ck_encoded_column cols[3], uint32_t num
   CK_CUDA(cudaMemsetAsync(lane->d_err, 0xff, 4 * sizeof(unsigned long long), s));
   CK_CUDA(cudaEventRecord(lane->ev[0], s));
   if (one_copy) {
-    CK_CUDA(cudaMemcpyAsync(d, reinterpret_cast<const void *>(lo), hi - lo, cudaMemcpyHostToDevice, s));
+    CK_CUDA(cudaMemcpyAsync(d + skew, reinterpret_cast<const void *>(lo), hi - lo, cudaMemcpyHostToDevice, s));
   } else {
     for (int c = 0; c < 3; ++c) {
       const size_t nb = pieces[c][0].bytes;
