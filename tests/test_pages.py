@@ -303,3 +303,19 @@ def test_cli_device_decode_equals_host_decode(tmp_path):
         assert outs[mode].num_rows == count > 0
         assert np.array_equal(outs[mode].column("kin").to_numpy().view(np.uint32), want["kin"].view(np.uint32))
     assert outs["device"].equals(outs["host"]) and outs["device"].equals(outs["small_windows"])
+
+
+def test_host_reader_degenerate_files(tmp_path):
+    """No rows at all, one row, row groups of one row: the window reader must agree with libparquet on these too."""
+    assert os.path.exists(CHECK), "run __graft_entry__.build() first"
+    g = np.full((3, 4), -1, dtype=np.int8)
+    empty = str(tmp_path / "empty.parquet")
+    pq.write_table(triple_table(g), empty)
+    g[1, 2] = 2
+    one = str(tmp_path / "one.parquet")
+    pq.write_table(triple_table(g), one)
+    g[:] = 1
+    tiny_groups = str(tmp_path / "tiny_groups.parquet")
+    pq.write_table(triple_table(g), tiny_groups, row_group_size=1)
+    out = subprocess.run([CHECK, "1000:4096", empty, one, tiny_groups], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0].startswith("OK 0 rows") and out[1].startswith("OK 1 rows") and out[2].startswith("OK 12 rows, 12 windows"), out
