@@ -96,6 +96,12 @@ __device__ unsigned long long g_screen_prof[16];
 __device__ __forceinline__ void pin8(const uint32_t (&v)[8]) {
   asm volatile("" ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
 }
+#ifndef CK_S3_PF_STEPS  // L2 prefetch of the column operand this many steps ahead (see king_screen1_kernel.cu).  Off: this kernel
+                        // runs at the board's power cap, where the prefetch costs more than it saves (cfg2: 622 vs 611 ms with 24)
+#define CK_S3_PF_STEPS 0
+#endif
+constexpr uint32_t kL2PrefetchSteps = CK_S3_PF_STEPS;
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void expand_fp4(uint32_t z, uint32_t &x, uint32_t &y, uint32_t &h) {  // A operands
   x = z & 0xAAAAAAAAu;  // +1 hom-alt (0x2), -1 hom-ref (0xA)
   y = z & 0x22222222u;  // 1 hom
@@ -249,7 +255,12 @@ __global__ void __launch_bounds__(kFThreads, 1) king_screen_kernel(const KingLau
     uint4 z[kFBPrefetch][kFSub];
     auto load_sub = [&](uint32_t m, uint4 (&dst)[kFSub]) {
 #pragma unroll
-      for (uint32_t q = 0; q < kFSub; ++q) dst[q] = __ldg(src + size_t(min(m, num_subs - 1) * kFSub + q) * (2 * kTileSamples));
+      for (uint32_t q = 0; q < kFSub; ++q) {
+        const uint32_t step = min(m, num_subs - 1) * kFSub + q;
+        const uint4 *s0 = src + size_t(step) * (2 * kTileSamples);
+        dst[q] = __ldg(s0);
+        if (kL2PrefetchSteps != 0 && step + kL2PrefetchSteps < num_steps) prefetch_l2(s0 + size_t(kL2PrefetchSteps) * (2 * kTileSamples));
+      }
     };
 #pragma unroll
     for (uint32_t u = 0; u < kFBPrefetch; ++u) load_sub(u, z[u]);
